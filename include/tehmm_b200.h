@@ -1,0 +1,200 @@
+/*
+ * tehmm_b200.h -- C ABI of libtehmm_b200.so, the B200 (sm_100a) replacement for
+ * teHmm's multitrack-HMM hot path.
+ *
+ * The reference has no FFI of its own: its native layer is five Cython modules
+ * whose Python-visible `def` functions take NumPy arrays.  The entry points
+ * below are what a ctypes/cffi binding for those functions binds (the binding a
+ * maintainer would add is shown in INTEGRATION.md).  Plain C: pointers, sizes,
+ * scalars.  No torch / NumPy / C++ types appear in any signature.
+ *
+ * Two layers.
+ *
+ *  L0 "strict" entry points  (tehmm_strict_*): HOST pointers, float64, one
+ *     sequence per call, caller owns every buffer -- a 1:1 replacement for
+ *       _hmm._forward            /root/reference/_hmm.pyx:120-158
+ *       _hmm._backward           /root/reference/_hmm.pyx:160-198
+ *       _hmm._viterbi            /root/reference/_hmm.pyx:201-259
+ *       _hmm._log_sum_lneta      /root/reference/_hmm.pyx:62-117
+ *       _emission.fastAllLogProbs      /root/reference/_emission.pyx:20-144
+ *       _emission.fastAccumulateStats  /root/reference/_emission.pyx:146-234
+ *       _emission.fastUpdateCounts     /root/reference/_emission.pyx:236-332
+ *     They run CUDA kernels that keep the reference's operation order in fp64
+ *     (including every quirk listed in SURVEY.md section 8a / Appendix).
+ *
+ *  L1 "batched" entry points (tehmm_set_model / tehmm_set_batch / tehmm_run_* ):
+ *     DEVICE pointers, many sequences per call, chunked parallel-in-time
+ *     scaled-space kernels in fp32 (production) or fp64 (verification).  They
+ *     back MultitrackHmm.fit / decode / score / score_samples
+ *     (/root/reference/hmm.py:155-277,545-729, basehmm.py:238-541) and
+ *     IndependentMultinomialEmissionModel.allLogProbs / accumulateStats
+ *     (/root/reference/emission.py:179-241).
+ *
+ * Error handling: every function returns 0 on success or a negative
+ * TEHMM_E* code; tehmm_last_error() returns a thread-local message.  The
+ * Python layer maps TEHMM_EINVAL to AssertionError (the reference asserts on
+ * bad shapes, _emission.pyx:24-32) and everything else to RuntimeError.
+ *
+ * Threading: a context is bound to one device and one CUDA stream; calls on one
+ * context must be serialised by the caller; distinct contexts may be used from
+ * distinct threads (teHmmTrain --reps uses a ThreadPool, teHmmTrain.py:279-292).
+ * Nothing here is stored on Python model objects (they are pickled and
+ * deep-copied, modelIO.py:26-32, hmm.py:694).
+ */
+#ifndef TEHMM_B200_H
+#define TEHMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEHMM_ABI_VERSION 1
+
+#define TEHMM_OK 0
+#define TEHMM_EINVAL (-1)   /* bad argument / shape (reference: AssertionError) */
+#define TEHMM_ECUDA (-2)    /* CUDA runtime error */
+#define TEHMM_ENOMEM (-3)   /* host or device allocation failed */
+#define TEHMM_ESTATE (-4)   /* call order (no model / no batch / workspace too small) */
+#define TEHMM_ELIMIT (-5)   /* shape outside the supported envelope */
+
+/* element type of the batched lattices */
+#define TEHMM_F32 0
+#define TEHMM_F64 1
+
+/* tehmm_run_backward output selection (bit mask) */
+#define TEHMM_BWD_POSTERIORS 1   /* write T x N posteriors                        */
+#define TEHMM_BWD_MAP 2          /* write argmax-posterior states + sum of maxima   */
+#define TEHMM_BWD_TRANS 4        /* accumulate start / transition expected counts   */
+#define TEHMM_BWD_RENORM_EPS 8   /* score_samples tail: += float32 eps, /= row sum  */
+
+#define TEHMM_MAX_STATES 64      /* batched path; strict path has no limit */
+
+typedef struct tehmm_ctx tehmm_ctx;
+
+int tehmm_abi_version(void);
+const char *tehmm_last_error(void);
+int tehmm_device_count(void);
+
+int tehmm_ctx_create(int device, tehmm_ctx **out);
+int tehmm_ctx_destroy(tehmm_ctx *ctx);
+/* block until everything enqueued on the context's stream has finished */
+int tehmm_ctx_sync(tehmm_ctx *ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
+ * caller's allocations, copies and events are ordered with the kernels;
+ * 0 = back to the context's own stream */
+int tehmm_ctx_set_stream(tehmm_ctx *ctx, uint64_t stream);
+/* the context's cudaStream_t as an integer (for event timing by the caller) */
+uint64_t tehmm_ctx_stream(tehmm_ctx *ctx);
+/* number of kernels this context has launched since creation */
+int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
+/* options: "chunk_tiles" (tiles of 64 steps per chunk, 0 = auto),
+ * "warmup" (speculative warm-up steps, 0 = auto), "max_repair" (passes) */
+int tehmm_ctx_set_option(tehmm_ctx *ctx, const char *name, int64_t value);
+int64_t tehmm_ctx_get_stat(tehmm_ctx *ctx, const char *name);
+
+/* ------------------------------------------------------------------ L0 strict
+ * obs is (T,K) row-major, obs_bytes = 1 (uint8), 2 (uint16) or 4 (int32)
+ * (the three dtype clones of _emission.pyx).  table is (K,N,S) float64,
+ * [track][state][symbol].  ratios is NULL for segRatios=None.              */
+int tehmm_strict_all_log_probs(tehmm_ctx *ctx, const void *obs, int obs_bytes,
+                               int64_t T, int K, const double *table, int N, int S,
+                               double *out /*T*N*/, double normalize,
+                               const double *ratios /*T or NULL*/);
+int tehmm_strict_forward(tehmm_ctx *ctx, int64_t T, int N, const double *log_start,
+                         const double *log_trans, const double *frame,
+                         const double *ratios, double *fwd /*T*N out*/);
+int tehmm_strict_backward(tehmm_ctx *ctx, int64_t T, int N, const double *log_start,
+                          const double *log_trans, const double *frame,
+                          const double *ratios, double *bwd /*T*N out*/);
+int tehmm_strict_viterbi(tehmm_ctx *ctx, int64_t T, int N, const double *log_start,
+                         const double *log_trans, const double *ratios,
+                         const double *frame, int64_t *states /*T out*/,
+                         double *logprob /*out*/);
+int tehmm_strict_log_sum_lneta(tehmm_ctx *ctx, int64_t T, int N, const double *fwd,
+                               const double *log_trans, const double *bwd,
+                               const double *frame, double logprob,
+                               const double *ratios, double *out /*N*N in: zeros, out*/);
+int tehmm_strict_accumulate_stats(tehmm_ctx *ctx, const void *obs, int obs_bytes,
+                                  int64_t T, int K, double *stats /*K*N*S in-out*/,
+                                  int N, int S, const double *post /*T*N*/,
+                                  const double *ratios);
+int tehmm_strict_update_counts(tehmm_ctx *ctx, const void *obs, int obs_bytes,
+                               int64_t T, int K, int64_t start, int64_t end, int state,
+                               double *stats /*K*N*S in-out*/, int N, int S,
+                               const double *ratios);
+
+/* ----------------------------------------------------------------- L1 batched
+ * Model: HOST pointers (small).  log_start (N), log_trans (N,N), table (K,N,S)
+ * as stored by the reference (hmm.py:625-666, emission.py:43-44,136-159);
+ * track_nsym[k] = number of table columns in use for track k (<= S), or NULL
+ * for "all S".  normalize = emission.normalizeFac (emission.py:58-60).      */
+int tehmm_set_model(tehmm_ctx *ctx, int N, int K, int S, const double *log_start,
+                    const double *log_trans, const double *table, double normalize,
+                    const int32_t *track_nsym);
+
+/* Batch: nseq sequences concatenated along time.  d_obs is a DEVICE pointer to
+ * (total,K) symbols; h_offsets is a HOST array of nseq+1 row offsets.  The
+ * pointer must stay valid until the next tehmm_set_batch.                    */
+int tehmm_set_batch(tehmm_ctx *ctx, const void *d_obs, int obs_bytes, int64_t nseq,
+                    const int64_t *h_offsets);
+int64_t tehmm_batch_total(tehmm_ctx *ctx);  /* total rows */
+int64_t tehmm_batch_chunks(tehmm_ctx *ctx); /* chunks in the time partition */
+/* bytes of d_scratch the tehmm_run_* calls need for the current batch+model */
+int64_t tehmm_scratch_bytes(tehmm_ctx *ctx, int prec);
+
+/* Emission gather-and-sum (emission.py:179-198 -> _emission.pyx:50-80).
+ * Writes, per row t: M[t] = max_j frame[t][j] (float64) and, when non-NULL,
+ *   d_elog[t][j] = frame[t][j] - M[t]            (log space, <= 0)
+ *   d_blin[t][j] = exp(frame[t][j] - M[t])       (linear,   <= 1)
+ * in the element type `prec`.  d_ratios (DEVICE, float64, total) or NULL.     */
+int tehmm_run_emission(tehmm_ctx *ctx, int prec, const double *d_ratios,
+                       void *d_elog, void *d_blin, double *d_rowmax);
+/* Reference-layout frame: d_frame[t][j] float64 = what fastAllLogProbs writes */
+int tehmm_run_emission_f64(tehmm_ctx *ctx, const double *d_ratios, double *d_frame);
+
+/* Forward (hmm.py:678-713 -> _hmm.pyx:120-158).  d_alpha (total*N, may be NULL
+ * for score-only) receives the per-step max-normalised forward vector;
+ * d_logprob (nseq, float64) the sequence log-likelihoods.                    */
+int tehmm_run_forward(tehmm_ctx *ctx, int prec, const void *d_blin,
+                      const double *d_rowmax, const double *d_ratios, void *d_alpha,
+                      double *d_logprob, void *d_scratch);
+
+/* Backward + posterior glue + expected counts (hmm.py:715-729,545-574,
+ * basehmm.py:265-272,516-517, _hmm.pyx:62-117,160-198).  flags = TEHMM_BWD_*.
+ *   d_post        total*N, element type prec            (POSTERIORS)
+ *   d_map_states  total, uint8;  d_map_score nseq f64   (MAP)
+ *   d_start_trans N + N*N float64, ACCUMULATED into     (TRANS)             */
+int tehmm_run_backward(tehmm_ctx *ctx, int prec, int flags, const void *d_blin,
+                       const void *d_alpha, const double *d_ratios, void *d_post,
+                       uint8_t *d_map_states, double *d_map_score,
+                       double *d_start_trans, void *d_scratch);
+
+/* Posterior-weighted emission histograms (emission.py:221-241 ->
+ * _emission.pyx:171-190): d_obs_stats (K,N,stats_S) float64, ACCUMULATED into.
+ * stats_S is the width of the caller's obsStats array (initStats gives
+ * max(numSymbolsPerTrack)+1, emission.py:212-214, which differs from the table
+ * width S when zeroAsMissingData is off).                                    */
+int tehmm_run_emission_stats(tehmm_ctx *ctx, int prec, const void *d_post,
+                             const double *d_ratios, double *d_obs_stats,
+                             int stats_S, void *d_scratch);
+
+/* Viterbi with traceback (hmm.py:668-676 -> _hmm.pyx:201-259).
+ * d_states total uint8 (or d_states64 total int64, either may be NULL),
+ * d_logprob nseq float64 (fp64 re-score of the returned path).
+ * d_bp: workspace of tehmm_viterbi_bp_bytes().                              */
+int64_t tehmm_viterbi_bp_bytes(tehmm_ctx *ctx);
+int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
+                      const double *d_ratios_emission, const double *d_ratios_dp,
+                      void *d_bp, uint8_t *d_states, int64_t *d_states64,
+                      double *d_logprob, void *d_scratch);
+
+/* widen / convert on the device before a D2H copy */
+int tehmm_widen_states(tehmm_ctx *ctx, const uint8_t *d_in, int64_t *d_out, int64_t n);
+int tehmm_convert_lattice(tehmm_ctx *ctx, int prec, const void *d_in, double *d_out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEHMM_B200_H */

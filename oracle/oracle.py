@@ -142,7 +142,8 @@ def estep_sequence(obs, logProbs, normalize, log_startprob, log_transmat, segRat
     a, b, r = _f64(log_startprob), _f64(log_transmat), _f64(segRatios)
     return lib().orc_estep_sequence(obs.ctypes.data_as(ctypes.c_void_p), nb, ctypes.c_long(T), K,
                                     _d(tab), N, S, ctypes.c_double(normalize), _d(a), _d(b), _d(r),
-                                    _d(start_stats), _d(trans_stats), _d(obs_stats))
+                                    _d(start_stats), _d(trans_stats), _d(obs_stats),
+                                    int(obs_stats.shape[2]))
 
 
 def sweep_sequence(obs, logProbs, normalize, log_startprob, log_transmat, segRatios=None):

@@ -299,13 +299,16 @@ void orc_update_counts(const void *obs, int obs_bytes, int K, long start, long e
  * posterior glue, start += post[0], trans += exp(logsum_lneta),
  * emission histograms.  Used as the timed "port" CPU baseline and as the
  * checker for the fused device E-step.  Returns the forward log-likelihood.
- * All stats are accumulated in place.  Scratch is allocated internally.
+ * All stats are accumulated in place (obs_stats is (K,N,stats_S): initStats,
+ * emission.py:212-214, is one wider than the table when zeroAsMissingData is off).
+ * Scratch is allocated internally.
  */
 double orc_estep_sequence(const void *obs, int obs_bytes, long T, int K,
                           const double *table, int N, int S, double normalize,
                           const double *log_start, const double *log_trans,
                           const double *ratios,
-                          double *start_stats, double *trans_stats, double *obs_stats)
+                          double *start_stats, double *trans_stats, double *obs_stats,
+                          int stats_S)
 {
     size_t cells = (size_t)T * N;
     double *frame = (double *)malloc(sizeof(double) * cells);
@@ -324,7 +327,7 @@ double orc_estep_sequence(const void *obs, int obs_bytes, long T, int K,
         for (long e = 0; e < (long)N * N; ++e) trans_stats[e] += exp(ls[e]);
         free(ls);
     }
-    orc_accumulate_stats(obs, obs_bytes, T, K, obs_stats, N, S, post, ratios);
+    orc_accumulate_stats(obs, obs_bytes, T, K, obs_stats, N, stats_S, post, ratios);
     free(frame); free(fwd); free(bwd); free(post);
     return lp;
 }

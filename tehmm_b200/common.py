@@ -1,0 +1,45 @@
+"""Numerics contract shared with the reference (common.py:24-33, basehmm.py:65-67)."""
+import logging
+
+import numpy as np
+
+LOGZERO = -1e100
+EPSILON = np.finfo(float).eps
+ZEROLOGPROB = -1e200
+NEGINF = -np.inf
+EPS = np.finfo(float).eps
+
+logger = logging.getLogger("tehmm_b200")
+
+
+def myLog(x, logZeroVal=LOGZERO, epsilonVal=EPSILON):
+    """np.log that maps |x| < eps to a finite sentinel instead of -inf
+    (reference common.py:27-33; vectorised with np.where instead of np.vectorize).
+    Returns an array for array input and a numpy scalar for scalar input."""
+    a = np.asarray(x, dtype=np.float64)
+    small = np.abs(a) < epsilonVal
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(small, logZeroVal, np.log(np.where(small, 1.0, a)))
+    return out if out.ndim else np.float64(out)
+
+
+def logsumexp(arr, axis=0):
+    """log(sum(exp(arr))) along `axis` with the max pulled out (basehmm.py:70-93)."""
+    arr = np.moveaxis(np.asarray(arr, dtype=np.float64), axis, 0)
+    vmax = arr.max(axis=0)
+    out = np.log(np.sum(np.exp(arr - vmax), axis=0))
+    out += vmax
+    return out
+
+
+def normalize(A, axis=None):
+    """Adds EPS to every entry IN PLACE, then returns A / A.sum(axis)
+    (basehmm.py:113-141; the in-place epsilon is part of the contract)."""
+    A += EPS
+    Asum = A.sum(axis)
+    if axis and A.ndim > 1:
+        Asum[Asum == 0] = 1
+        shape = list(A.shape)
+        shape[axis] = 1
+        Asum.shape = shape
+    return A / Asum

@@ -1,0 +1,738 @@
+// C ABI of libtehmm_b200.so (see include/tehmm_b200.h): context, model and
+// batch management, time partitioning, and the speculate / verify / repair
+// drivers around the scan kernels.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ---- launchers defined in the other translation units
+void tehmm_launch_strict_emission(cudaStream_t, const void *, int, int64_t, int, const double *, int, int, double *, double, const double *, unsigned long long *);
+void tehmm_launch_strict_forward(cudaStream_t, int64_t, int, const double *, const double *, const double *, const double *, double *);
+void tehmm_launch_strict_backward(cudaStream_t, int64_t, int, const double *, const double *, const double *, double *);
+void tehmm_launch_strict_viterbi(cudaStream_t, int64_t, int, const double *, const double *, const double *, const double *, int16_t *, int64_t *, double *);
+void tehmm_launch_strict_lneta(cudaStream_t, int64_t, int, const double *, const double *, const double *, const double *, double, const double *, double *);
+void tehmm_launch_strict_accumulate(cudaStream_t, const void *, int, int64_t, int, double *, int, int, const double *, const double *);
+void tehmm_launch_strict_counts(cudaStream_t, const void *, int, int, int64_t, int64_t, int, double *, int, int, const double *);
+size_t tehmm_emission_table_budget(int K);
+int tehmm_launch_emission(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const double *, void *, void *, double *, double *, int *, int, cudaError_t *);
+cudaError_t tehmm_launch_forward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, const double *, void *, void *, void *, double *, const int *, int, int);
+cudaError_t tehmm_launch_verify(cudaStream_t, const TehmmBatchDev &, int, int, void *, const void *, double, double, int, int *, int *);
+cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, int, int, const void *, const double *, double *);
+cudaError_t tehmm_launch_backward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, int, const void *, const void *, const double *, void *, uint8_t *, double *, void *, void *, void *, void *, void *, const int *, int, int);
+cudaError_t tehmm_launch_trans_reduce(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const void *, const void *, double *);
+cudaError_t tehmm_launch_map_reduce(cudaStream_t, const TehmmBatchDev &, const double *, double *);
+cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, uint8_t *, uint8_t *, void *, void *, const int *, int, int);
+cudaError_t tehmm_launch_traceback(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const uint8_t *, const uint8_t *, uint8_t *, uint8_t *, uint8_t *, int64_t *, const double *, const double *, double *, double *, int, int);
+cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, double *, double *, int, int);
+size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
+cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
+cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x)                                                                                 \
+    do {                                                                                      \
+        cudaError_t e__ = (x);                                                                \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(TEHMM_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e__),    \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+struct DevBuf {   // RAII device allocation for the strict host-pointer entry points
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    template <typename T> T *as() { return (T *)p; }
+};
+
+struct tehmm_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int64_t launches = 0;
+    int64_t opt_chunk_tiles = 0, opt_warmup = 0, opt_max_repair = 0;
+    int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
+    int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0;
+    int *h_nbad = nullptr;            // pinned
+    // model
+    bool has_model = false;
+    TehmmModelDev m{};
+    void *model_blob = nullptr;
+    // batch
+    bool has_batch = false;
+    TehmmBatchDev b{};
+    void *batch_blob = nullptr;
+    int *d_seq_flag = nullptr;
+    int64_t max_tiles_per_chunk = 1;
+};
+
+extern "C" {
+
+int tehmm_abi_version(void) { return TEHMM_ABI_VERSION; }
+const char *tehmm_last_error(void) { return g_err.c_str(); }
+
+int tehmm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tehmm_ctx_create(int device, tehmm_ctx **out)
+{
+    if (!out) return fail(TEHMM_EINVAL, "out is NULL");
+    int n = tehmm_device_count();
+    if (n <= 0) return fail(TEHMM_ECUDA, "no CUDA device visible: libtehmm_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(TEHMM_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    CU(cudaSetDevice(device));
+    tehmm_ctx *c = new tehmm_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaMallocHost((void **)&c->h_nbad, sizeof(int)));
+    *out = c;
+    return TEHMM_OK;
+}
+
+int tehmm_ctx_destroy(tehmm_ctx *c)
+{
+    if (!c) return TEHMM_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->model_blob) cudaFree(c->model_blob);
+    if (c->batch_blob) cudaFree(c->batch_blob);
+    if (c->d_seq_flag) cudaFree(c->d_seq_flag);
+    if (c->h_nbad) cudaFreeHost(c->h_nbad);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return TEHMM_OK;
+}
+
+int tehmm_ctx_sync(tehmm_ctx *c)
+{
+    if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return TEHMM_OK;
+}
+
+int tehmm_ctx_set_stream(tehmm_ctx *c, uint64_t stream)
+{
+    if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = stream ? (cudaStream_t)(uintptr_t)stream : c->own_stream;
+    return TEHMM_OK;
+}
+
+uint64_t tehmm_ctx_stream(tehmm_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+int64_t tehmm_ctx_launch_count(tehmm_ctx *c) { return c ? c->launches : 0; }
+
+int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
+{
+    if (!c || !name) return fail(TEHMM_EINVAL, "NULL argument");
+    if (!strcmp(name, "chunk_tiles")) c->opt_chunk_tiles = v;
+    else if (!strcmp(name, "warmup")) c->opt_warmup = v;
+    else if (!strcmp(name, "max_repair")) c->opt_max_repair = v;
+    else return fail(TEHMM_EINVAL, "unknown option %s", name);
+    return TEHMM_OK;
+}
+
+int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
+{
+    if (!c || !name) return -1;
+    if (!strcmp(name, "launches")) return c->launches;
+    if (!strcmp(name, "repair_passes_forward")) return c->stat_repair_fwd;
+    if (!strcmp(name, "repair_passes_backward")) return c->stat_repair_bwd;
+    if (!strcmp(name, "repair_passes_viterbi")) return c->stat_repair_vit;
+    if (!strcmp(name, "repaired_chunks_forward")) return c->stat_bad_fwd;
+    if (!strcmp(name, "repaired_chunks_backward")) return c->stat_bad_bwd;
+    if (!strcmp(name, "repaired_chunks_viterbi")) return c->stat_bad_vit;
+    if (!strcmp(name, "sms")) return c->sms;
+    if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
+    if (!strcmp(name, "warmup")) return c->has_batch ? c->b.warmup : 0;
+    return -1;
+}
+
+// ================================================================ L0 strict
+#define STRICT_PROLOGUE()                                                      \
+    if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");                          \
+    CU(cudaSetDevice(c->device));                                              \
+    cudaStream_t st = c->stream
+#define H2D(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st))
+#define D2H(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+
+static int check_obs_bytes(int nb)
+{
+    if (nb != 1 && nb != 2 && nb != 4) return fail(TEHMM_EINVAL, "obs_bytes must be 1, 2 or 4 (got %d)", nb);
+    return 0;
+}
+
+int tehmm_strict_all_log_probs(tehmm_ctx *c, const void *obs, int obs_bytes, int64_t T, int K,
+                               const double *table, int N, int S, double *out, double normalize,
+                               const double *ratios)
+{
+    STRICT_PROLOGUE();
+    if (!obs || !table || !out || T < 0 || K <= 0 || N <= 0 || S <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    if (check_obs_bytes(obs_bytes)) return TEHMM_EINVAL;
+    if (T == 0) return TEHMM_OK;
+    DevBuf dobs, dtab, dout, drat, dfirst;
+    size_t ob = (size_t)T * K * obs_bytes, tb = (size_t)K * N * S * 8, fb = (size_t)T * N * 8;
+    CU(dobs.alloc(ob)); CU(dtab.alloc(tb)); CU(dout.alloc(fb)); CU(dfirst.alloc(8));
+    H2D(dobs.p, obs, ob); H2D(dtab.p, table, tb);
+    if (ratios) { CU(drat.alloc((size_t)T * 8)); H2D(drat.p, ratios, (size_t)T * 8); }
+    CU(cudaMemsetAsync(dfirst.p, 0xff, 8, st));
+    tehmm_launch_strict_emission(st, dobs.p, obs_bytes, T, K, dtab.as<double>(), N, S, dout.as<double>(),
+                                 normalize, ratios ? drat.as<double>() : nullptr, dfirst.as<unsigned long long>());
+    c->launches += 2;
+    CU(cudaGetLastError());
+    D2H(out, dout.p, fb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_forward(tehmm_ctx *c, int64_t T, int N, const double *log_start,
+                         const double *log_trans, const double *frame, const double *ratios,
+                         double *fwd)
+{
+    STRICT_PROLOGUE();
+    if (!log_start || !log_trans || !frame || !fwd || T <= 0 || N <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    if ((size_t)N * 16 > 200 * 1024) return fail(TEHMM_ELIMIT, "N=%d too large", N);
+    DevBuf ds, dt, df, dr, dout;
+    size_t fb = (size_t)T * N * 8;
+    CU(ds.alloc((size_t)N * 8)); CU(dt.alloc((size_t)N * N * 8)); CU(df.alloc(fb)); CU(dout.alloc(fb));
+    H2D(ds.p, log_start, (size_t)N * 8); H2D(dt.p, log_trans, (size_t)N * N * 8); H2D(df.p, frame, fb);
+    if (ratios) { CU(dr.alloc((size_t)T * 8)); H2D(dr.p, ratios, (size_t)T * 8); }
+    tehmm_launch_strict_forward(st, T, N, ds.as<double>(), dt.as<double>(), df.as<double>(),
+                                ratios ? dr.as<double>() : nullptr, dout.as<double>());
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(fwd, dout.p, fb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_backward(tehmm_ctx *c, int64_t T, int N, const double *log_start,
+                          const double *log_trans, const double *frame, const double *ratios,
+                          double *bwd)
+{
+    (void)log_start;   // accepted and ignored, as in _hmm.pyx:160-198
+    STRICT_PROLOGUE();
+    if (!log_trans || !frame || !bwd || T <= 0 || N <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    DevBuf dt, df, dr, dout;
+    size_t fb = (size_t)T * N * 8;
+    CU(dt.alloc((size_t)N * N * 8)); CU(df.alloc(fb)); CU(dout.alloc(fb));
+    H2D(dt.p, log_trans, (size_t)N * N * 8); H2D(df.p, frame, fb);
+    if (ratios) { CU(dr.alloc((size_t)T * 8)); H2D(dr.p, ratios, (size_t)T * 8); }
+    tehmm_launch_strict_backward(st, T, N, dt.as<double>(), df.as<double>(),
+                                 ratios ? dr.as<double>() : nullptr, dout.as<double>());
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(bwd, dout.p, fb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_viterbi(tehmm_ctx *c, int64_t T, int N, const double *log_start,
+                         const double *log_trans, const double *ratios, const double *frame,
+                         int64_t *states, double *logprob)
+{
+    STRICT_PROLOGUE();
+    if (!log_start || !log_trans || !frame || !states || !logprob || T <= 0 || N <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    if (N > 32767) return fail(TEHMM_ELIMIT, "N=%d exceeds the int16 back-pointer range", N);
+    DevBuf ds, dt, df, dr, dbp, dst_, dlp;
+    size_t fb = (size_t)T * N * 8;
+    CU(ds.alloc((size_t)N * 8)); CU(dt.alloc((size_t)N * N * 8)); CU(df.alloc(fb));
+    CU(dbp.alloc((size_t)T * N * 2)); CU(dst_.alloc((size_t)T * 8)); CU(dlp.alloc(8));
+    H2D(ds.p, log_start, (size_t)N * 8); H2D(dt.p, log_trans, (size_t)N * N * 8); H2D(df.p, frame, fb);
+    if (ratios) { CU(dr.alloc((size_t)T * 8)); H2D(dr.p, ratios, (size_t)T * 8); }
+    tehmm_launch_strict_viterbi(st, T, N, ds.as<double>(), dt.as<double>(), ratios ? dr.as<double>() : nullptr,
+                                df.as<double>(), dbp.as<int16_t>(), dst_.as<int64_t>(), dlp.as<double>());
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(states, dst_.p, (size_t)T * 8);
+    D2H(logprob, dlp.p, 8);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_log_sum_lneta(tehmm_ctx *c, int64_t T, int N, const double *fwd,
+                               const double *log_trans, const double *bwd, const double *frame,
+                               double logprob, const double *ratios, double *out)
+{
+    STRICT_PROLOGUE();
+    if (!fwd || !log_trans || !bwd || !frame || !out || T <= 0 || N <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    DevBuf dfw, dt, dbw, dfr, dr, dout;
+    size_t fb = (size_t)T * N * 8, nb = (size_t)N * N * 8;
+    CU(dfw.alloc(fb)); CU(dbw.alloc(fb)); CU(dfr.alloc(fb)); CU(dt.alloc(nb)); CU(dout.alloc(nb));
+    H2D(dfw.p, fwd, fb); H2D(dbw.p, bwd, fb); H2D(dfr.p, frame, fb); H2D(dt.p, log_trans, nb); H2D(dout.p, out, nb);
+    if (ratios) { CU(dr.alloc((size_t)T * 8)); H2D(dr.p, ratios, (size_t)T * 8); }
+    tehmm_launch_strict_lneta(st, T, N, dfw.as<double>(), dt.as<double>(), dbw.as<double>(), dfr.as<double>(),
+                              logprob, ratios ? dr.as<double>() : nullptr, dout.as<double>());
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(out, dout.p, nb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_accumulate_stats(tehmm_ctx *c, const void *obs, int obs_bytes, int64_t T, int K,
+                                  double *stats, int N, int S, const double *post,
+                                  const double *ratios)
+{
+    STRICT_PROLOGUE();
+    if (!obs || !stats || !post || T < 0 || K <= 0 || N <= 0 || S <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    if (check_obs_bytes(obs_bytes)) return TEHMM_EINVAL;
+    if (T == 0) return TEHMM_OK;
+    DevBuf dobs, dst_, dp, dr;
+    size_t ob = (size_t)T * K * obs_bytes, sb = (size_t)K * N * S * 8, pb = (size_t)T * N * 8;
+    CU(dobs.alloc(ob)); CU(dst_.alloc(sb)); CU(dp.alloc(pb));
+    H2D(dobs.p, obs, ob); H2D(dst_.p, stats, sb); H2D(dp.p, post, pb);
+    if (ratios) { CU(dr.alloc((size_t)T * 8)); H2D(dr.p, ratios, (size_t)T * 8); }
+    tehmm_launch_strict_accumulate(st, dobs.p, obs_bytes, T, K, dst_.as<double>(), N, S, dp.as<double>(),
+                                   ratios ? dr.as<double>() : nullptr);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(stats, dst_.p, sb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+int tehmm_strict_update_counts(tehmm_ctx *c, const void *obs, int obs_bytes, int64_t T, int K,
+                               int64_t start, int64_t end, int state, double *stats, int N, int S,
+                               const double *ratios)
+{
+    STRICT_PROLOGUE();
+    if (!obs || !stats || T < 0 || K <= 0 || N <= 0 || S <= 0) return fail(TEHMM_EINVAL, "bad argument");
+    if (check_obs_bytes(obs_bytes)) return TEHMM_EINVAL;
+    if (start < 0 || end > T || state < 0 || state >= N) return fail(TEHMM_EINVAL, "interval [%lld,%lld) state %d outside table (T=%lld, N=%d)", (long long)start, (long long)end, state, (long long)T, N);
+    if (end <= start) return TEHMM_OK;
+    DevBuf dobs, dst_, dr;
+    // only the rows of the interval travel
+    size_t ob = (size_t)(end - start) * K * obs_bytes, sb = (size_t)K * N * S * 8;
+    CU(dobs.alloc(ob)); CU(dst_.alloc(sb));
+    H2D(dobs.p, (const char *)obs + (size_t)start * K * obs_bytes, ob); H2D(dst_.p, stats, sb);
+    if (ratios) { CU(dr.alloc((size_t)(end - start) * 8)); H2D(dr.p, ratios + start, (size_t)(end - start) * 8); }
+    tehmm_launch_strict_counts(st, dobs.p, obs_bytes, K, 0, end - start, state, dst_.as<double>(), N, S,
+                               ratios ? dr.as<double>() : nullptr);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    D2H(stats, dst_.p, sb);
+    CU(cudaStreamSynchronize(st));
+    return TEHMM_OK;
+}
+
+// ================================================================ L1 batched
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
+                    const double *log_trans, const double *table, double normalize,
+                    const int32_t *track_nsym)
+{
+    if (!c || !log_start || !log_trans || !table) return fail(TEHMM_EINVAL, "NULL argument");
+    if (N <= 0 || K <= 0 || S <= 0) return fail(TEHMM_EINVAL, "bad shape N=%d K=%d S=%d", N, K, S);
+    if (N > TEHMM_MAX_STATES) return fail(TEHMM_ELIMIT, "batched path supports N <= %d (got %d)", TEHMM_MAX_STATES, N);
+    CU(cudaSetDevice(c->device));
+    const int NS = N <= 32 ? 1 : 2, NP = 32 * NS;
+    std::vector<int32_t> nsym(K), off(K);
+    int rows = 0;
+    for (int k = 0; k < K; ++k) {
+        int n = track_nsym ? track_nsym[k] : S;
+        if (n < 1 || n > S) return fail(TEHMM_EINVAL, "track_nsym[%d]=%d outside 1..%d", k, n, S);
+        nsym[k] = n; off[k] = rows; rows += n;
+    }
+    // host-side staging of everything in one blob
+    size_t o_ls = 0, o_lt = align_up(o_ls + (size_t)N * 8), o_tab = align_up(o_lt + (size_t)N * N * 8);
+    size_t o_tt = align_up(o_tab + (size_t)K * N * S * 8), o_off = align_up(o_tt + (size_t)rows * N * 8);
+    size_t o_ns = align_up(o_off + (size_t)K * 4), o_lins = align_up(o_ns + (size_t)K * 4);
+    size_t o_lint = align_up(o_lins + (size_t)NP * 8), o_cuts = align_up(o_lint + (size_t)NP * NP * 8);
+    size_t o_cutt = align_up(o_cuts + (size_t)NP * 8), total = align_up(o_cutt + (size_t)NP * NP * 8);
+    std::vector<unsigned char> h(total, 0);
+    memcpy(&h[o_ls], log_start, (size_t)N * 8);
+    memcpy(&h[o_lt], log_trans, (size_t)N * N * 8);
+    memcpy(&h[o_tab], table, (size_t)K * N * S * 8);
+    double *tt = (double *)&h[o_tt];
+    for (int k = 0; k < K; ++k)
+        for (int s = 0; s < nsym[k]; ++s)
+            for (int j = 0; j < N; ++j)
+                tt[(size_t)(off[k] + s) * N + j] = table[((size_t)k * N + j) * S + s];
+    memcpy(&h[o_off], off.data(), (size_t)K * 4);
+    memcpy(&h[o_ns], nsym.data(), (size_t)K * 4);
+    double *lins = (double *)&h[o_lins], *lint = (double *)&h[o_lint];
+    double *cuts = (double *)&h[o_cuts], *cutt = (double *)&h[o_cutt];
+    const double NEG = -INFINITY;
+    for (int i = 0; i < NP; ++i) {
+        bool ok = i < N && log_start[i] > TEHMM_LOGZERO_CUT;
+        lins[i] = ok ? exp(log_start[i]) : 0.0;
+        cuts[i] = ok ? log_start[i] : NEG;
+        for (int j = 0; j < NP; ++j) {
+            bool okt = i < N && j < N && log_trans[(size_t)i * N + j] > TEHMM_LOGZERO_CUT;
+            lint[(size_t)i * NP + j] = okt ? exp(log_trans[(size_t)i * N + j]) : 0.0;
+            cutt[(size_t)i * NP + j] = okt ? log_trans[(size_t)i * N + j] : NEG;
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->model_blob) { cudaFree(c->model_blob); c->model_blob = nullptr; }
+    CU(cudaMalloc(&c->model_blob, total));
+    CU(cudaMemcpy(c->model_blob, h.data(), total, cudaMemcpyHostToDevice));
+    unsigned char *d = (unsigned char *)c->model_blob;
+    TehmmModelDev &m = c->m;
+    m.N = N; m.K = K; m.S = S; m.NS = NS; m.NP = NP; m.tab_rows = rows; m.normalize = normalize;
+    m.table_in_smem = (size_t)rows * N * 8 <= tehmm_emission_table_budget(K) ? 1 : 0;
+    m.log_start = (const double *)(d + o_ls); m.log_trans = (const double *)(d + o_lt);
+    m.table = (const double *)(d + o_tab); m.table_t = (const double *)(d + o_tt);
+    m.tab_off = (const int32_t *)(d + o_off); m.track_nsym = (const int32_t *)(d + o_ns);
+    m.lin_start = (const double *)(d + o_lins); m.lin_trans = (const double *)(d + o_lint);
+    m.cut_start = (const double *)(d + o_cuts); m.cut_trans = (const double *)(d + o_cutt);
+    c->has_model = true;
+    return TEHMM_OK;
+}
+
+int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq,
+                    const int64_t *h_offsets)
+{
+    if (!c || !d_obs || !h_offsets) return fail(TEHMM_EINVAL, "NULL argument");
+    if (check_obs_bytes(obs_bytes)) return TEHMM_EINVAL;
+    if (nseq <= 0) return fail(TEHMM_EINVAL, "nseq must be positive");
+    if (h_offsets[0] != 0) return fail(TEHMM_EINVAL, "offsets[0] must be 0");
+    for (int64_t s = 0; s < nseq; ++s)
+        if (h_offsets[s + 1] < h_offsets[s]) return fail(TEHMM_EINVAL, "offsets must be non-decreasing");
+    CU(cudaSetDevice(c->device));
+    const int64_t total = h_offsets[nseq];
+    if (total <= 0) return fail(TEHMM_EINVAL, "empty batch");
+    // time partition: tiles of TEHMM_TILE steps, chunks of `tpc` tiles
+    int64_t tpc = c->opt_chunk_tiles;
+    if (tpc <= 0) {
+        const int64_t target = (int64_t)c->sms * 32;          // one chunk per resident warp
+        tpc = (total + target * TEHMM_TILE - 1) / (target * TEHMM_TILE);
+        tpc = std::max<int64_t>(4, std::min<int64_t>(tpc, 2048));
+    }
+    const int64_t L = tpc * TEHMM_TILE;
+    std::vector<TehmmChunk> chunks;
+    std::vector<int64_t> seq_chunk0(nseq + 1);
+    int64_t tile_base = 0;
+    for (int64_t s = 0; s < nseq; ++s) {
+        seq_chunk0[s] = (int64_t)chunks.size();
+        const int64_t s0 = h_offsets[s], s1 = h_offsets[s + 1];
+        for (int64_t t0 = s0; t0 < s1; t0 += L) {
+            TehmmChunk ch;
+            ch.t0 = t0; ch.t1 = std::min(s1, t0 + L); ch.s0 = s0; ch.s1 = s1;
+            ch.seq = (int32_t)s;
+            ch.ntiles = (int32_t)((ch.t1 - ch.t0 + TEHMM_TILE - 1) / TEHMM_TILE);
+            ch.tile0 = tile_base;
+            tile_base += ch.ntiles;
+            chunks.push_back(ch);
+        }
+    }
+    seq_chunk0[nseq] = (int64_t)chunks.size();
+    const int64_t nchunks = (int64_t)chunks.size();
+    size_t o_off = 0, o_sc = align_up(o_off + (size_t)(nseq + 1) * 8), o_ch = align_up(o_sc + (size_t)(nseq + 1) * 8);
+    size_t bytes = align_up(o_ch + (size_t)nchunks * sizeof(TehmmChunk));
+    std::vector<unsigned char> h(bytes, 0);
+    memcpy(&h[o_off], h_offsets, (size_t)(nseq + 1) * 8);
+    memcpy(&h[o_sc], seq_chunk0.data(), (size_t)(nseq + 1) * 8);
+    memcpy(&h[o_ch], chunks.data(), (size_t)nchunks * sizeof(TehmmChunk));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->batch_blob) { cudaFree(c->batch_blob); c->batch_blob = nullptr; }
+    if (c->d_seq_flag) { cudaFree(c->d_seq_flag); c->d_seq_flag = nullptr; }
+    CU(cudaMalloc(&c->batch_blob, bytes));
+    CU(cudaMemcpy(c->batch_blob, h.data(), bytes, cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&c->d_seq_flag, sizeof(int) * (size_t)nseq));
+    unsigned char *d = (unsigned char *)c->batch_blob;
+    TehmmBatchDev &b = c->b;
+    b.obs = d_obs; b.obs_bytes = obs_bytes; b.nseq = nseq; b.total = total;
+    b.nchunks = nchunks; b.ntiles = tile_base;
+    b.seq_off = (const int64_t *)(d + o_off); b.seq_chunk0 = (const int64_t *)(d + o_sc);
+    b.chunks = (const TehmmChunk *)(d + o_ch);
+    b.warmup = (int)(c->opt_warmup > 0 ? c->opt_warmup : 64);
+    c->max_tiles_per_chunk = tpc;
+    c->has_batch = true;
+    return TEHMM_OK;
+}
+
+int64_t tehmm_batch_total(tehmm_ctx *c) { return c && c->has_batch ? c->b.total : 0; }
+int64_t tehmm_batch_chunks(tehmm_ctx *c) { return c && c->has_batch ? c->b.nchunks : 0; }
+int64_t tehmm_viterbi_bp_bytes(tehmm_ctx *c)
+{
+    if (!c || !c->has_batch || !c->has_model) return 0;
+    return c->b.total * (int64_t)c->m.NP;
+}
+
+// scratch carving shared by tehmm_scratch_bytes and the run_* entry points
+struct Scratch {
+    size_t start_vec, end_vec, cscale, part_a, bad, nbad, xi, xdiag, gamma0, tilemap, cmap, chunk_end, hist, total;
+    int nparts;
+};
+static Scratch carve(const tehmm_ctx *c, int prec)
+{
+    const size_t ts = prec == TEHMM_F32 ? 4 : 8;
+    const size_t NP = (size_t)c->m.NP, nc = (size_t)c->b.nchunks;
+    Scratch s;
+    size_t o = 0;
+    s.start_vec = o; o = align_up(o + nc * NP * ts);
+    s.end_vec = o; o = align_up(o + nc * NP * ts);
+    s.cscale = o; o = align_up(o + nc * 8);
+    s.part_a = o; o = align_up(o + nc * 8);
+    s.bad = o; o = align_up(o + nc * 4);
+    s.nbad = o; o = align_up(o + 4);
+    s.xi = o; o = align_up(o + nc * NP * NP * ts);
+    s.xdiag = o; o = align_up(o + nc * NP * ts);
+    s.gamma0 = o; o = align_up(o + (size_t)c->b.nseq * NP * ts);
+    s.tilemap = o; o = align_up(o + (size_t)c->b.ntiles * NP);
+    s.cmap = o; o = align_up(o + nc * NP);
+    s.chunk_end = o; o = align_up(o + nc);
+    const size_t smem = tehmm_stats_smem_bytes(c->m.tab_rows, c->m.N, c->m.K, prec);
+    s.nparts = 0;
+    if (smem <= 200 * 1024) {
+        int per_sm = smem <= 100 * 1024 ? 2 : 1;
+        int64_t want = (int64_t)c->sms * per_sm;
+        int64_t cap = (c->b.total + 255) / 256;     // at least 256 steps per CTA
+        s.nparts = (int)std::max<int64_t>(1, std::min(want, cap));
+    }
+    s.hist = o; o = align_up(o + (size_t)s.nparts * c->m.tab_rows * c->m.N * 8);
+    s.total = o;
+    return s;
+}
+
+int64_t tehmm_scratch_bytes(tehmm_ctx *c, int prec)
+{
+    if (!c || !c->has_batch || !c->has_model) return 0;
+    return (int64_t)carve(c, prec).total;
+}
+
+#define RUN_PROLOGUE()                                                                  \
+    if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");                                   \
+    if (!c->has_model) return fail(TEHMM_ESTATE, "tehmm_set_model has not been called");\
+    if (!c->has_batch) return fail(TEHMM_ESTATE, "tehmm_set_batch has not been called");\
+    if (prec != TEHMM_F32 && prec != TEHMM_F64) return fail(TEHMM_EINVAL, "bad prec");  \
+    CU(cudaSetDevice(c->device));                                                       \
+    cudaStream_t st = c->stream
+
+static int scan_grid(const tehmm_ctx *c)
+{
+    int64_t need = (c->b.nchunks + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
+    int64_t cap = (int64_t)c->sms * 8;
+    return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+static int read_nbad(tehmm_ctx *c, const int *d_nbad, int *out)
+{
+    CU(cudaMemcpyAsync(c->h_nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = *c->h_nbad;
+    return TEHMM_OK;
+}
+
+int tehmm_run_emission(tehmm_ctx *c, int prec, const double *d_ratios, void *d_elog, void *d_blin,
+                       double *d_rowmax)
+{
+    RUN_PROLOGUE();
+    if (!d_rowmax || (!d_elog && !d_blin)) return fail(TEHMM_EINVAL, "need d_rowmax and at least one of d_elog / d_blin");
+    cudaError_t e;
+    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, d_elog, d_blin, d_rowmax, nullptr, c->d_seq_flag, c->sms, &e);
+    if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
+    c->launches += n;
+    return TEHMM_OK;
+}
+
+int tehmm_run_emission_f64(tehmm_ctx *c, const double *d_ratios, double *d_frame)
+{
+    int prec = TEHMM_F64;
+    RUN_PROLOGUE();
+    if (!d_frame) return fail(TEHMM_EINVAL, "d_frame is NULL");
+    cudaError_t e;
+    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, nullptr, nullptr, nullptr, d_frame, c->d_seq_flag, c->sms, &e);
+    if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
+    c->launches += n;
+    return TEHMM_OK;
+}
+
+static void tolerances(int prec, bool log_space, double *ta, double *tr)
+{
+    if (log_space) { *ta = prec == TEHMM_F32 ? 1e-5 : 1e-11; *tr = prec == TEHMM_F32 ? 1e-6 : 1e-14; }
+    else { *ta = prec == TEHMM_F32 ? 2e-6 : 1e-13; *tr = 0.0; }
+}
+
+int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *d_rowmax,
+                      const double *d_ratios, void *d_alpha, double *d_logprob, void *d_scratch)
+{
+    RUN_PROLOGUE();
+    if (!d_blin || !d_rowmax || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument");
+    const Scratch s = carve(c, prec);
+    char *w = (char *)d_scratch;
+    void *sv = w + s.start_vec, *ev = w + s.end_vec;
+    double *cs = (double *)(w + s.cscale);
+    int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
+    const int grid = scan_grid(c);
+    CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 0, grid));
+    c->launches += 1;
+    double ta, tr;
+    tolerances(prec, false, &ta, &tr);
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    for (int64_t pass = 0;; ++pass) {
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, +1, bad, nbad));
+        c->launches += 1;
+        int nb = 0;
+        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (nb == 0) break;
+        if (pass >= max_pass) return fail(TEHMM_ESTATE, "forward repair did not converge (%d chunks left)", nb);
+        c->stat_repair_fwd += 1; c->stat_bad_fwd += nb;
+        CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 1, grid));
+        c->launches += 1;
+    }
+    CU(tehmm_launch_forward_logprob(st, c->b, prec, c->m.NP, ev, cs, d_logprob));
+    c->launches += 1;
+    return TEHMM_OK;
+}
+
+int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, const void *d_alpha,
+                       const double *d_ratios, void *d_post, uint8_t *d_map_states,
+                       double *d_map_score, double *d_start_trans, void *d_scratch)
+{
+    RUN_PROLOGUE();
+    if (!d_blin || !d_alpha || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument");
+    if ((flags & TEHMM_BWD_POSTERIORS) && !d_post) return fail(TEHMM_EINVAL, "POSTERIORS needs d_post");
+    if ((flags & TEHMM_BWD_MAP) && (!d_map_states || !d_map_score)) return fail(TEHMM_EINVAL, "MAP needs d_map_states and d_map_score");
+    if ((flags & TEHMM_BWD_TRANS) && !d_start_trans) return fail(TEHMM_EINVAL, "TRANS needs d_start_trans");
+    const Scratch s = carve(c, prec);
+    char *w = (char *)d_scratch;
+    void *sv = w + s.start_vec, *ev = w + s.end_vec;
+    double *mp = (double *)(w + s.part_a);
+    int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
+    void *xi = w + s.xi, *xd = w + s.xdiag, *g0 = w + s.gamma0;
+    const int grid = scan_grid(c);
+    CU(tehmm_launch_backward(st, c->m, c->b, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, 0, grid));
+    c->launches += 1;
+    double ta, tr;
+    tolerances(prec, false, &ta, &tr);
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    for (int64_t pass = 0;; ++pass) {
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, -1, bad, nbad));
+        c->launches += 1;
+        int nb = 0;
+        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (nb == 0) break;
+        if (pass >= max_pass) return fail(TEHMM_ESTATE, "backward repair did not converge (%d chunks left)", nb);
+        c->stat_repair_bwd += 1; c->stat_bad_bwd += nb;
+        CU(tehmm_launch_backward(st, c->m, c->b, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, 1, grid));
+        c->launches += 1;
+    }
+    if (flags & TEHMM_BWD_MAP) { CU(tehmm_launch_map_reduce(st, c->b, mp, d_map_score)); c->launches += 1; }
+    if (flags & TEHMM_BWD_TRANS) { CU(tehmm_launch_trans_reduce(st, c->m, c->b, prec, xi, xd, g0, d_start_trans)); c->launches += 1; }
+    return TEHMM_OK;
+}
+
+int tehmm_run_emission_stats(tehmm_ctx *c, int prec, const void *d_post, const double *d_ratios,
+                             double *d_obs_stats, int stats_S, void *d_scratch)
+{
+    RUN_PROLOGUE();
+    if (!d_post || !d_obs_stats || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument");
+    if (stats_S <= 0) return fail(TEHMM_EINVAL, "stats_S must be positive");
+    const Scratch s = carve(c, prec);
+    double *part = (double *)((char *)d_scratch + s.hist);
+    CU(tehmm_launch_emission_stats(st, c->m, c->b, prec, d_post, d_ratios, d_obs_stats, part, s.nparts, stats_S));
+    c->launches += s.nparts > 0 ? 2 * ((c->m.K + 31) / 32) : 1;
+    return TEHMM_OK;
+}
+
+int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *d_ratios_emission,
+                      const double *d_ratios_dp, void *d_bp, uint8_t *d_states,
+                      int64_t *d_states64, double *d_logprob, void *d_scratch)
+{
+    RUN_PROLOGUE();
+    if (!d_elog || !d_bp || !d_states || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument (d_states is required; d_states64 is optional)");
+    const Scratch s = carve(c, prec);
+    char *w = (char *)d_scratch;
+    void *sv = w + s.start_vec, *ev = w + s.end_vec;
+    double *sp = (double *)(w + s.part_a);
+    int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
+    uint8_t *tilemap = (uint8_t *)(w + s.tilemap), *cmap = (uint8_t *)(w + s.cmap), *cend = (uint8_t *)(w + s.chunk_end);
+    const int grid = scan_grid(c);
+    CU(cudaMemsetAsync(tilemap, 0, (size_t)c->b.ntiles * c->m.NP, st));
+    CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, (uint8_t *)d_bp, tilemap, sv, ev, bad, 0, grid));
+    c->launches += 1;
+    double ta, tr;
+    tolerances(prec, true, &ta, &tr);
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    for (int64_t pass = 0;; ++pass) {
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, +1, bad, nbad));
+        c->launches += 1;
+        int nb = 0;
+        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (nb == 0) break;
+        if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
+        c->stat_repair_vit += 1; c->stat_bad_vit += nb;
+        CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, (uint8_t *)d_bp, tilemap, sv, ev, bad, 1, grid));
+        c->launches += 1;
+    }
+    CU(tehmm_launch_traceback(st, c->m, c->b, prec, ev, (const uint8_t *)d_bp, tilemap, cmap, cend, d_states, d_states64,
+                              d_ratios_emission, d_ratios_dp, sp, d_logprob, (int)c->max_tiles_per_chunk, grid));
+    c->launches += 5;
+    return TEHMM_OK;
+}
+
+int tehmm_widen_states(tehmm_ctx *c, const uint8_t *d_in, int64_t *d_out, int64_t n)
+{
+    if (!c || !d_in || !d_out || n < 0) return fail(TEHMM_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TEHMM_OK;
+    CU(tehmm_launch_widen(c->stream, d_in, d_out, n));
+    c->launches += 1;
+    return TEHMM_OK;
+}
+
+int tehmm_convert_lattice(tehmm_ctx *c, int prec, const void *d_in, double *d_out, int64_t n)
+{
+    if (!c || !d_in || !d_out || n < 0) return fail(TEHMM_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return TEHMM_OK;
+    CU(tehmm_launch_convert(c->stream, prec, d_in, d_out, n));
+    c->launches += 1;
+    return TEHMM_OK;
+}
+
+}   // extern "C"
+
+// ---------------------------------------------------------------- tiny utility kernels
+__global__ void widen_kernel(const uint8_t *__restrict__ in, int64_t *__restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+template <typename T>
+__global__ void convert_kernel(const T *__restrict__ in, double *__restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+cudaError_t tehmm_launch_widen(cudaStream_t st, const uint8_t *in, int64_t *out, int64_t n)
+{
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    widen_kernel<<<grid, 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+cudaError_t tehmm_launch_convert(cudaStream_t st, int prec, const void *in, double *out, int64_t n)
+{
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    if (prec == TEHMM_F32) convert_kernel<float><<<grid, 256, 0, st>>>((const float *)in, out, n);
+    else convert_kernel<double><<<grid, 256, 0, st>>>((const double *)in, out, n);
+    return cudaGetLastError();
+}

@@ -1,0 +1,224 @@
+// Batched emission gather-and-sum (emission.py:179-198 -> _emission.pyx:50-80).
+//
+// HBM-bound: reads K bytes of symbols per time step and writes N values (twice
+// when both the log-space and the linear copy are requested) + one float64 row
+// maximum.  The per-track tables are staged once per CTA in shared memory,
+// transposed to [symbol-row][state] so that the 32 lanes of a warp (= states)
+// read consecutive words (conflict-free).  One warp per time step, 32 steps of
+// symbols staged per warp iteration with a coalesced load.
+#include "scan.cuh"
+
+#define EM_WARPS 8
+#define EM_ROWS 32   // time steps staged per warp iteration
+
+// frame value of one (t, state): ((sum_k table) * normalize) * ratio, float64.
+template <bool SMEM_TABLE>
+__device__ __forceinline__ double em_gather(const TehmmModelDev &m, const double *tab,
+                                            const int32_t *offs, const int32_t *nsyms,
+                                            const int *syms, int j)
+{
+    double v = 0.0;
+    for (int k = 0; k < m.K; ++k) {
+        int sym = syms[k];
+        if (sym < nsyms[k])
+            v += tab[(int64_t)(offs[k] + sym) * m.N + j];
+        else   // symbol outside the compact table: dense table as the reference indexes it
+            v += m.table[((int64_t)k * m.N + j) * m.S + sym];
+    }
+    return v;
+}
+
+// MODE 0: write normalised log (elog) / linear (blin) copies in type T + rowmax
+// MODE 1: write the reference-layout float64 frame only
+template <typename T, typename OBS, int MODE>
+__global__ void __launch_bounds__(EM_WARPS * 32)
+emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
+                const double *__restrict__ ratios, T *__restrict__ elog, T *__restrict__ blin,
+                double *__restrict__ rowmax, double *__restrict__ frame,
+                int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq)
+{
+    extern __shared__ __align__(16) unsigned char em_smem[];
+    // layout: [K] offs | [K] nsyms | per-warp symbol staging | table
+    int32_t *offs = reinterpret_cast<int32_t *>(em_smem);
+    int32_t *nsyms = offs + m.K;
+    int *stage_all = reinterpret_cast<int *>(nsyms + m.K);
+    size_t head = ((size_t)(2 * m.K + EM_WARPS * EM_ROWS * m.K) * 4 + 15) & ~(size_t)15;
+    double *tab_s = reinterpret_cast<double *>(em_smem + head);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < m.K; k += blockDim.x) {
+        offs[k] = m.tab_off[k];
+        nsyms[k] = m.track_nsym[k];
+    }
+    const double *tab = m.table_t;
+    if (m.table_in_smem) {
+        int64_t n = (int64_t)m.tab_rows * m.N;
+        for (int64_t e = threadIdx.x; e < n; e += blockDim.x) tab_s[e] = m.table_t[e];
+        tab = tab_s;
+    }
+    __syncthreads();
+
+    int *stage = stage_all + warp * EM_ROWS * m.K;
+    const int64_t nblocks = (total + EM_ROWS - 1) / EM_ROWS;
+    for (int64_t blk = (int64_t)blockIdx.x * EM_WARPS + warp; blk < nblocks;
+         blk += (int64_t)gridDim.x * EM_WARPS) {
+        const int64_t tb = blk * EM_ROWS;
+        const int rows = (int)min((int64_t)EM_ROWS, total - tb);
+        __syncwarp();
+        for (int e = lane; e < rows * m.K; e += 32) stage[e] = (int)obs[tb * m.K + e];
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const int64_t t = tb + r;
+            const int *syms = stage + r * m.K;
+            const double rt = ratios ? ratios[t] : 1.0;
+            double v[2];
+            double vmax = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                int j = lane + 32 * s;
+                v[s] = -INFINITY;
+                if (j < m.N) {
+                    double x = em_gather<true>(m, tab, offs, nsyms, syms, j);
+                    x *= m.normalize;
+                    if (ratios) x *= rt;
+                    v[s] = x;
+                    vmax = fmax(vmax, x);
+                }
+            }
+            if (MODE == 1) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    int j = lane + 32 * s;
+                    if (j < m.N) frame[t * m.N + j] = v[s];
+                }
+                float mf = warp_max_any((float)vmax);
+                if (!(mf > (float)TEHMM_MINDBL) && seq_flag) {
+                    // candidate for the "no state can emit" quirk; exact test on doubles
+                    double md = warp_max(vmax);
+                    if (!(md > TEHMM_MINDBL) && lane == 0) {
+                        int64_t lo = 0, hi = nseq;   // find sequence of row t
+                        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
+                        seq_flag[lo] = 1;
+                    }
+                }
+                continue;
+            }
+            // row maximum: float REDUX first; exact double fallback when it overflows fp32
+            float mf = warp_max_any((float)vmax);
+            double M = (double)mf;
+            if (!(mf > -INFINITY)) M = warp_max(vmax);
+            if (!(M > TEHMM_MINDBL) && seq_flag && lane == 0) {
+                int64_t lo = 0, hi = nseq;
+                while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
+                seq_flag[lo] = 1;
+            }
+            if (lane == 0) rowmax[t] = M;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                int j = lane + 32 * s;
+                if (j < m.N) {
+                    double d = (M > -INFINITY) ? v[s] - M : 0.0;
+                    if (elog) elog[t * m.N + j] = (T)d;
+                    if (blin) blin[t * m.N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
+                }
+            }
+        }
+    }
+}
+
+// _emission.pyx:59,73-80: the running maximum is never reset, so rows are
+// zeroed only while no earlier row of the sequence had a value > -1e20.
+// One warp per flagged sequence; almost never runs.
+template <typename T>
+__global__ void emission_fix_kernel(int N, const int *__restrict__ seq_flag,
+                                    const int64_t *__restrict__ seq_off, int64_t nseq,
+                                    T *elog, T *blin, double *rowmax, double *frame)
+{
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= nseq || !seq_flag[s]) return;
+    for (int64_t t = seq_off[s]; t < seq_off[s + 1]; ++t) {
+        bool infeasible;
+        if (frame) {
+            double mx = -INFINITY;
+            for (int j = lane; j < N; j += 32) mx = fmax(mx, frame[t * N + j]);
+            mx = warp_max(mx);
+            infeasible = !(mx > TEHMM_MINDBL);
+        } else {
+            infeasible = !(rowmax[t] > TEHMM_MINDBL);
+        }
+        if (!infeasible) break;
+        for (int j = lane; j < N; j += 32) {
+            if (frame) frame[t * N + j] = 0.0;
+            if (elog) elog[t * N + j] = (T)0;
+            if (blin) blin[t * N + j] = (T)1;
+        }
+        if (rowmax && lane == 0) rowmax[t] = 0.0;
+        __syncwarp();
+    }
+}
+
+static size_t em_smem_bytes(const TehmmModelDev &m)
+{
+    size_t head = ((size_t)(2 * m.K + EM_WARPS * EM_ROWS * m.K) * 4 + 15) & ~(size_t)15;
+    return head + (m.table_in_smem ? (size_t)m.tab_rows * m.N * sizeof(double) : 0);
+}
+
+size_t tehmm_emission_table_budget(int K)
+{
+    size_t head = ((size_t)(2 * K + EM_WARPS * EM_ROWS * K) * 4 + 15) & ~(size_t)15;
+    return (size_t)220 * 1024 - head;
+}
+
+template <typename T, typename OBS, int MODE>
+static cudaError_t launch_em(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                             const double *ratios, T *elog, T *blin, double *rowmax,
+                             double *frame, int *seq_flag, int sms)
+{
+    size_t smem = em_smem_bytes(m);
+    auto kern = emission_kernel<T, OBS, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = smem > 110 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+    int64_t need = ((b.total + EM_ROWS - 1) / EM_ROWS + EM_WARPS - 1) / EM_WARPS;
+    if (need < 1) need = 1;
+    int64_t cap = (int64_t)sms * per_sm;
+    int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, EM_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
+                                            rowmax, frame, seq_flag, b.seq_off, b.nseq);
+    return cudaGetLastError();
+}
+
+template <typename T, int MODE>
+static cudaError_t launch_em_obs(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                 const double *ratios, T *elog, T *blin, double *rowmax,
+                                 double *frame, int *seq_flag, int sms)
+{
+    if (b.obs_bytes == 1) return launch_em<T, uint8_t, MODE>(st, m, b, ratios, elog, blin, rowmax, frame, seq_flag, sms);
+    if (b.obs_bytes == 2) return launch_em<T, uint16_t, MODE>(st, m, b, ratios, elog, blin, rowmax, frame, seq_flag, sms);
+    return launch_em<T, int32_t, MODE>(st, m, b, ratios, elog, blin, rowmax, frame, seq_flag, sms);
+}
+
+// returns number of kernels launched, or -1 with *err set
+int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b, int prec,
+                          const double *ratios, void *elog, void *blin, double *rowmax,
+                          double *frame, int *seq_flag, int sms, cudaError_t *err)
+{
+    cudaError_t e = cudaMemsetAsync(seq_flag, 0, sizeof(int) * (size_t)b.nseq, st);
+    if (e == cudaSuccess) {
+        if (frame) e = launch_em_obs<float, 1>(st, m, b, ratios, nullptr, nullptr, nullptr, frame, seq_flag, sms);
+        else if (prec == TEHMM_F32) e = launch_em_obs<float, 0>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, nullptr, seq_flag, sms);
+        else e = launch_em_obs<double, 0>(st, m, b, ratios, (double *)elog, (double *)blin, rowmax, nullptr, seq_flag, sms);
+    }
+    if (e == cudaSuccess) {
+        int warps = 4;
+        int grid = (int)((b.nseq + warps - 1) / warps);
+        if (frame || prec == TEHMM_F32)
+            emission_fix_kernel<float><<<grid, warps * 32, 0, st>>>(m.N, seq_flag, b.seq_off, b.nseq, (float *)elog, (float *)blin, rowmax, frame);
+        else
+            emission_fix_kernel<double><<<grid, warps * 32, 0, st>>>(m.N, seq_flag, b.seq_off, b.nseq, (double *)elog, (double *)blin, rowmax, frame);
+        e = cudaGetLastError();
+    }
+    *err = e;
+    return e == cudaSuccess ? 2 : -1;
+}

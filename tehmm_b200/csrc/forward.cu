@@ -1,0 +1,276 @@
+// Chunked parallel-in-time forward pass in scaled-probability space
+// (hmm.py:678-713 -> _hmm.pyx:120-158).
+//
+// The time axis of every sequence is cut into chunks; one warp per chunk.
+// A chunk that does not begin its sequence needs alpha at t0-1, which the
+// serial recursion would only know after all earlier chunks.  SPECULATE: run
+// `warmup` extra steps from a uniform vector before t0 (the forward filter
+// forgets its initial condition geometrically); VERIFY: compare the speculated
+// vector with the true end vector of the previous chunk; REPAIR: re-run only
+// the chunks that disagree, from the true vector, until none disagree.
+//
+// Scaling is by exact powers of two (canonicalise), so a chunk's output does
+// not depend on the scaling history, only on its (canonical) start vector.
+//
+// Per step and warp: 1 STS + NP/4 LDS.128 (broadcast) + NP*NS FFMA + 1 REDUX +
+// 1 coalesced load of b_t (N values) + 1 coalesced store of alpha_t.
+// Algorithmic HBM bytes per step: 4N read + 4N written (fp32).
+#include "scan.cuh"
+
+#define FWD_U 4   // register prefetch depth (time steps)
+
+template <typename T, int NS, bool RATIO>
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
+               const double *__restrict__ rowmax, const double *__restrict__ ratios,
+               T *__restrict__ alpha, T *__restrict__ start_vec, T *__restrict__ end_vec,
+               double *__restrict__ cscale, const int *__restrict__ bad, int mode)
+{
+    constexpr int NP = 32 * NS;
+    __shared__ __align__(16) T xs_all[TEHMM_WARPS_PER_CTA][2][NP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T(*xs)[NP] = xs_all[warp];
+
+    // column j of the transition matrix for each owned state
+    T c[NS][NP];
+    T pi[NS];
+    double dg[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        int j = lane + 32 * s;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) c[s][i] = (T)m.lin_trans[(int64_t)i * NP + j];
+        pi[s] = (T)m.lin_start[j];
+        dg[s] = RATIO ? m.cut_trans[(int64_t)j * NP + j] : 0.0;
+    }
+    const int N = m.N;
+
+    for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
+         ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
+        if (mode == 1 && !bad[ci]) continue;
+        const TehmmChunk ch = b.chunks[ci];
+        T x[NS];
+        int64_t esum = 0;
+        double lsum = 0.0;
+        int buf = 0;
+
+        // one recursion step: x <- canonical( (x A) .* b_t [.* g_t] ); returns the exponent
+        auto step = [&](int64_t t, const T (&bt)[NS], bool first) -> int {
+            T raw[NS];
+            if (first) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) raw[s] = pi[s] * bt[s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) xs[buf][lane + 32 * s] = x[s];
+                __syncwarp();
+                T y[NS];
+                matvec_sum<T, NS>(xs[buf], c, y);
+                buf ^= 1;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) raw[s] = y[s] * bt[s];
+            }
+            if (RATIO) {
+                double r = ratios[t];
+                if (r > 1.0) {
+                    double lg[NS], mg = -INFINITY;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) { lg[s] = dg[s] * (r - 1.0); mg = fmax(mg, lg[s]); }
+                    mg = warp_max(mg);
+                    if (mg > -INFINITY) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) raw[s] *= (T)exp(lg[s] - mg);
+                        lsum += mg;
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) raw[s] = (T)0;
+                    }
+                }
+            }
+            int e = canonicalise<T, NS>(raw);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) x[s] = raw[s];
+            return e;
+        };
+        auto load_b = [&](int64_t t, T (&bt)[NS]) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                int j = lane + 32 * s;
+                bt[s] = j < N ? blin[t * N + j] : (T)0;
+            }
+        };
+
+        int64_t t = ch.t0;
+        if (ch.t0 > ch.s0) {
+            if (mode == 0) {
+                int64_t tw = ch.t0 - b.warmup;
+                T bt[NS];
+                if (tw <= ch.s0) {
+                    tw = ch.s0;
+                    load_b(tw, bt);
+                    step(tw, bt, true);
+                    ++tw;
+                } else {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) x[s] = (lane + 32 * s) < N ? (T)1 : (T)0;
+                }
+                for (; tw < ch.t0; ++tw) {
+                    load_b(tw, bt);
+                    step(tw, bt, false);
+                }
+                lsum = 0.0;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = x[s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) x[s] = start_vec[ci * NP + lane + 32 * s];
+            }
+        } else {
+            T bt[NS];
+            load_b(t, bt);
+            esum += step(t, bt, true);
+            if (alpha) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (lane + 32 * s < N) alpha[t * N + lane + 32 * s] = x[s];
+            }
+            ++t;
+        }
+
+        // main loop with a FWD_U-deep register prefetch of b
+        T bn[FWD_U][NS];
+#pragma unroll
+        for (int u = 0; u < FWD_U; ++u) load_b(min(t + u, ch.t1 - 1), bn[u]);
+        for (; t < ch.t1; t += FWD_U) {
+            T bc[FWD_U][NS];
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) bc[u][s] = bn[u][s];
+            }
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u) load_b(min(t + FWD_U + u, ch.t1 - 1), bn[u]);
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u) {
+                if (t + u < ch.t1) {
+                    esum += step(t + u, bc[u], false);
+                    if (alpha) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            if (lane + 32 * s < N) alpha[(t + u) * N + lane + 32 * s] = x[s];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) end_vec[ci * NP + lane + 32 * s] = x[s];
+
+        // log of everything taken out of the chunk: exponents, ratio maxima, row maxima
+        double ms = 0.0;
+        for (int64_t tt = ch.t0 + lane; tt < ch.t1; tt += 32) ms += rowmax[tt];
+        ms = warp_sum(ms);
+        if (lane == 0) cscale[ci] = (double)esum * 0.6931471805599453094 + lsum + ms;
+    }
+}
+
+// bad[c] = speculated start vector of chunk c differs from the neighbour's end
+// vector by more than tol (both canonical).  dir=+1: neighbour is c-1 (forward,
+// Viterbi); dir=-1: neighbour is c+1 (backward).  A bad chunk gets the true
+// vector copied into its start slot for the repair pass.
+template <typename T>
+__global__ void verify_kernel(TehmmBatchDev b, int NP, T *start_vec, const T *end_vec,
+                              double tol_abs, double tol_rel, int dir, int *bad, int *nbad)
+{
+    int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= b.nchunks) return;
+    const TehmmChunk ch = b.chunks[ci];
+    bool has = dir > 0 ? (ch.t0 > ch.s0) : (ch.t1 < ch.s1);
+    int flag = 0;
+    if (has) {
+        const T *tv = end_vec + (ci - dir) * NP;
+        T *sv = start_vec + ci * NP;
+        for (int j = 0; j < NP; ++j) {
+            double a = (double)sv[j], t = (double)tv[j];
+            if (a == t) continue;                       // covers equal infinities
+            double d = fabs(a - t);
+            if (!(d <= tol_abs + tol_rel * fabs(t))) flag = 1;   // NaN counts as bad
+        }
+        if (flag)
+            for (int j = 0; j < NP; ++j) sv[j] = tv[j];
+    }
+    bad[ci] = flag;
+    if (flag) atomicAdd(nbad, 1);
+}
+
+// logprob[seq] = sum of chunk scales + log(sum_j alpha_hat[T-1][j])
+template <typename T>
+__global__ void forward_logprob_kernel(TehmmBatchDev b, int NP, const T *__restrict__ end_vec,
+                                       const double *__restrict__ cscale,
+                                       double *__restrict__ logprob)
+{
+    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (s >= b.nseq) return;
+    int64_t c0 = b.seq_chunk0[s], c1 = b.seq_chunk0[s + 1];
+    if (c1 <= c0) { if (lane == 0) logprob[s] = 0.0; return; }
+    double acc = 0.0;
+    for (int64_t c = c0 + lane; c < c1; c += 32) acc += cscale[c];
+    acc = warp_sum(acc);
+    double tail = 0.0;
+    for (int j = lane; j < NP; j += 32) tail += (double)end_vec[(c1 - 1) * NP + j];
+    tail = warp_sum(tail);
+    if (lane == 0) logprob[s] = acc + log(tail);
+}
+
+template <typename T, int NS>
+static cudaError_t launch_fwd(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                              const T *blin, const double *rowmax, const double *ratios, T *alpha,
+                              T *start_vec, T *end_vec, double *cscale, const int *bad, int mode,
+                              int grid)
+{
+    if (ratios)
+        forward_kernel<T, NS, true><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, blin, rowmax, ratios, alpha, start_vec, end_vec, cscale, bad, mode);
+    else
+        forward_kernel<T, NS, false><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, blin, rowmax, ratios, alpha, start_vec, end_vec, cscale, bad, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t tehmm_launch_forward(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                 int prec, const void *blin, const double *rowmax,
+                                 const double *ratios, void *alpha, void *start_vec, void *end_vec,
+                                 double *cscale, const int *bad, int mode, int grid)
+{
+    if (prec == TEHMM_F32) {
+        if (m.NS == 1) return launch_fwd<float, 1>(st, m, b, (const float *)blin, rowmax, ratios, (float *)alpha, (float *)start_vec, (float *)end_vec, cscale, bad, mode, grid);
+        return launch_fwd<float, 2>(st, m, b, (const float *)blin, rowmax, ratios, (float *)alpha, (float *)start_vec, (float *)end_vec, cscale, bad, mode, grid);
+    }
+    if (m.NS == 1) return launch_fwd<double, 1>(st, m, b, (const double *)blin, rowmax, ratios, (double *)alpha, (double *)start_vec, (double *)end_vec, cscale, bad, mode, grid);
+    return launch_fwd<double, 2>(st, m, b, (const double *)blin, rowmax, ratios, (double *)alpha, (double *)start_vec, (double *)end_vec, cscale, bad, mode, grid);
+}
+
+cudaError_t tehmm_launch_verify(cudaStream_t st, const TehmmBatchDev &b, int prec, int NP,
+                                void *start_vec, const void *end_vec, double tol_abs,
+                                double tol_rel, int dir, int *bad, int *nbad)
+{
+    cudaError_t e = cudaMemsetAsync(nbad, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    int grid = (int)((b.nchunks + 127) / 128);
+    if (prec == TEHMM_F32)
+        verify_kernel<float><<<grid, 128, 0, st>>>(b, NP, (float *)start_vec, (const float *)end_vec, tol_abs, tol_rel, dir, bad, nbad);
+    else
+        verify_kernel<double><<<grid, 128, 0, st>>>(b, NP, (double *)start_vec, (const double *)end_vec, tol_abs, tol_rel, dir, bad, nbad);
+    return cudaGetLastError();
+}
+
+cudaError_t tehmm_launch_forward_logprob(cudaStream_t st, const TehmmBatchDev &b, int prec, int NP,
+                                         const void *end_vec, const double *cscale,
+                                         double *logprob)
+{
+    int warps = 4;
+    int grid = (int)((b.nseq + warps - 1) / warps);
+    if (prec == TEHMM_F32)
+        forward_logprob_kernel<float><<<grid, warps * 32, 0, st>>>(b, NP, (const float *)end_vec, cscale, logprob);
+    else
+        forward_logprob_kernel<double><<<grid, warps * 32, 0, st>>>(b, NP, (const double *)end_vec, cscale, logprob);
+    return cudaGetLastError();
+}

@@ -1,0 +1,167 @@
+// Posterior-weighted per-track emission histograms for Baum-Welch
+// (emission.py:221-241 -> _emission.pyx:171-190):
+//     stats[k][j][obs[t][k]] += post[t][j] (* ratio[t])
+//
+// One CTA per contiguous slice of time, ONE WARP PER TRACK, lane = state.  The
+// CTA keeps a private float64 histogram [symbol-row][state] in shared memory
+// (same compact layout as the emission table), so warps never collide (they
+// own disjoint rows) and no atomics are needed.  Annotation tracks are
+// run-length structured, so each lane accumulates in a register while the
+// track's symbol does not change and touches shared memory only on a change.
+// CTA histograms go to global memory and are summed in fixed order (float64),
+// which makes the result deterministic.
+//
+// Algorithmic HBM bytes per step: 4N (posteriors) + K (symbols).
+#include "scan.cuh"
+
+#define ST_TILE 32   // time steps staged per CTA iteration
+
+template <typename T, typename OBS>
+__global__ void __launch_bounds__(1024)
+emission_stats_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
+                      const T *__restrict__ post, const double *__restrict__ ratios,
+                      double *__restrict__ part, double *__restrict__ dense_stats,
+                      int64_t steps_per_cta, int track_base, int statS)
+{
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int N = m.N, K = m.K;
+    const int64_t cells = (int64_t)m.tab_rows * N;
+    double *hist = reinterpret_cast<double *>(st_smem);
+    T *post_s = reinterpret_cast<T *>(hist + cells);                  // [ST_TILE][N]
+    double *ratio_s = reinterpret_cast<double *>(post_s + ST_TILE * N + (ST_TILE * N & 1));
+    int *sym_s = reinterpret_cast<int *>(ratio_s + ST_TILE);          // [ST_TILE][K]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t e = threadIdx.x; e < cells; e += blockDim.x) hist[e] = 0.0;
+
+    const int k = track_base + warp;
+    const bool active = k < K;
+    const int off = active ? m.tab_off[k] : 0, nsym = active ? m.track_nsym[k] : 0;
+    const int64_t ta = (int64_t)blockIdx.x * steps_per_cta;
+    const int64_t tz = min(total, ta + steps_per_cta);
+    int cur = -1;
+    double acc0 = 0.0, acc1 = 0.0;
+    auto flush = [&]() {
+        if (cur < 0) return;
+        if (cur < nsym) {
+            if (lane < N) hist[(int64_t)(off + cur) * N + lane] += acc0;
+            if (lane + 32 < N) hist[(int64_t)(off + cur) * N + lane + 32] += acc1;
+        } else {   // symbol outside the compact table: dense layout, rare
+            if (lane < N) atomicAdd(&dense_stats[((int64_t)k * N + lane) * statS + cur], acc0);
+            if (lane + 32 < N) atomicAdd(&dense_stats[((int64_t)k * N + lane + 32) * statS + cur], acc1);
+        }
+    };
+    for (int64_t tb = ta; tb < tz; tb += ST_TILE) {
+        const int rows = (int)min((int64_t)ST_TILE, tz - tb);
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * N; e += blockDim.x) post_s[e] = post[tb * N + e];
+        for (int e = threadIdx.x; e < rows * K; e += blockDim.x) sym_s[e] = (int)obs[tb * K + e];
+        if (ratios)
+            for (int e = threadIdx.x; e < rows; e += blockDim.x) ratio_s[e] = ratios[tb + e];
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+            const int sym = sym_s[r * K + k];
+            double g0 = lane < N ? (double)post_s[r * N + lane] : 0.0;
+            double g1 = lane + 32 < N ? (double)post_s[r * N + lane + 32] : 0.0;
+            if (ratios) { const double rr = ratio_s[r]; g0 *= rr; g1 *= rr; }
+            if (sym != cur) {
+                flush();
+                cur = sym;
+                acc0 = 0.0;
+                acc1 = 0.0;
+            }
+            acc0 += g0;
+            acc1 += g1;
+        }
+    }
+    if (active) flush();
+    __syncthreads();
+    double *dst = part + (int64_t)blockIdx.x * cells;
+    for (int64_t e = threadIdx.x; e < cells; e += blockDim.x) dst[e] = hist[e];
+}
+
+// Slow path when the compact histogram does not fit shared memory: global atomics.
+template <typename T, typename OBS>
+__global__ void emission_stats_global_kernel(TehmmModelDev m, const OBS *__restrict__ obs,
+                                             int64_t total, const T *__restrict__ post,
+                                             const double *__restrict__ ratios,
+                                             double *__restrict__ dense_stats, int statS)
+{
+    const int N = m.N, K = m.K;
+    const int64_t cells = total * K;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < cells;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = e / K;
+        const int k = (int)(e - t * K);
+        const int sym = (int)obs[e];
+        const double r = ratios ? ratios[t] : 1.0;
+        for (int j = 0; j < N; ++j)
+            atomicAdd(&dense_stats[((int64_t)k * N + j) * statS + sym], (double)post[t * N + j] * r);
+    }
+}
+
+// obs_stats[k][j][sym] += sum over CTAs of part[cta][off_k+sym][j]
+__global__ void emission_stats_reduce_kernel(TehmmModelDev m, const double *__restrict__ part,
+                                             int nparts, double *__restrict__ obs_stats, int statS)
+{
+    const int N = m.N;
+    const int64_t cells = (int64_t)m.tab_rows * N;
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= cells) return;
+    const int row = (int)(e / N), j = (int)(e - (int64_t)row * N);
+    int k = 0;
+    while (k + 1 < m.K && m.tab_off[k + 1] <= row) ++k;
+    const int sym = row - m.tab_off[k];
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += part[(int64_t)p * cells + e];
+    if (sym < statS) obs_stats[((int64_t)k * N + j) * statS + sym] += acc;
+}
+
+template <typename T, typename OBS>
+static cudaError_t launch_stats(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                const T *post, const double *ratios, double *obs_stats,
+                                double *part, int nparts, int statS)
+{
+    const size_t smem = (size_t)m.tab_rows * m.N * sizeof(double) + (size_t)(ST_TILE * m.N + 1) * sizeof(T)
+                        + ST_TILE * sizeof(double) + (size_t)ST_TILE * m.K * sizeof(int) + 16;
+    if (nparts <= 0) {
+        emission_stats_global_kernel<T, OBS><<<148 * 8, 256, 0, st>>>(m, (const OBS *)b.obs, b.total, post, ratios, obs_stats, statS);
+        return cudaGetLastError();
+    }
+    auto kern = emission_stats_kernel<T, OBS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t steps = (b.total + nparts - 1) / nparts;
+    for (int base = 0; base < m.K; base += 32) {
+        int warps = m.K - base < 32 ? m.K - base : 32;
+        kern<<<nparts, warps * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, post, ratios, part, obs_stats, steps, base, statS);
+        const int64_t cells = (int64_t)m.tab_rows * m.N;
+        emission_stats_reduce_kernel<<<(int)((cells + 127) / 128), 128, 0, st>>>(m, part, nparts, obs_stats, statS);
+    }
+    return cudaGetLastError();
+}
+
+// nparts = number of CTA-private histograms (0 = global-atomics slow path)
+cudaError_t tehmm_launch_emission_stats(cudaStream_t st, const TehmmModelDev &m,
+                                        const TehmmBatchDev &b, int prec, const void *post,
+                                        const double *ratios, double *obs_stats, double *part,
+                                        int nparts, int statS)
+{
+#define STATS_GO(TT)                                                                              \
+    do {                                                                                          \
+        if (b.obs_bytes == 1) return launch_stats<TT, uint8_t>(st, m, b, (const TT *)post, ratios, obs_stats, part, nparts, statS);   \
+        if (b.obs_bytes == 2) return launch_stats<TT, uint16_t>(st, m, b, (const TT *)post, ratios, obs_stats, part, nparts, statS);  \
+        return launch_stats<TT, int32_t>(st, m, b, (const TT *)post, ratios, obs_stats, part, nparts, statS);                         \
+    } while (0)
+    if (prec == TEHMM_F32) STATS_GO(float);
+    STATS_GO(double);
+#undef STATS_GO
+}
+
+size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec)
+{
+    size_t ts = prec == TEHMM_F32 ? sizeof(float) : sizeof(double);
+    return (size_t)tab_rows * N * sizeof(double) + (size_t)(ST_TILE * N + 1) * ts +
+           ST_TILE * sizeof(double) + (size_t)ST_TILE * K * sizeof(int) + 16;
+}

@@ -1,0 +1,317 @@
+"""Batched device path behind MultitrackHmm / IndependentMultinomialEmissionModel.
+
+PyTorch is used only for plumbing: device buffers, H2D/D2H copies, the CUDA
+stream and (in parallel.py) torch.distributed.  All arithmetic is in
+libtehmm_b200.so.  Sequences of one call are concatenated along time and
+described by row offsets; the library partitions time into chunks and runs one
+warp per chunk (see csrc/forward.cu for the speculate / verify / repair scheme).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+from .track import is_track_table
+
+_PRECISION = os.environ.get("TEHMM_B200_PRECISION", "f32").lower()
+
+
+def set_precision(p):
+    """'f32' (production) or 'f64' (verification) element type of the batched lattices."""
+    global _PRECISION
+    p = str(p).lower()
+    assert p in ("f32", "f64")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def as_obs_array(obs):
+    """Observation matrix of anything the reference accepts: TrackTable, or an
+    ndarray / nested list of any numeric dtype (non-fast dtypes are indexed with
+    int(symbol) by the reference, emission.py:176,239)."""
+    if is_track_table(obs):
+        obs = obs.getNumPyArray()
+    a = np.asarray(obs)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    assert a.ndim == 2, "observations must be (T, numTracks)"
+    if a.dtype in (np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.int32)):
+        return np.ascontiguousarray(a)
+    return np.ascontiguousarray(a.astype(np.int32))
+
+
+class Engine(object):
+    """One per Context.  Holds nothing of the model between calls except what
+    upload_model() put on the device."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx if ctx is not None else _lib.get_context()
+        self.lib = self.ctx.lib
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device("cuda", self.ctx.device)
+        self._keep = {}
+        self.N = self.K = self.S = None
+
+    # ------------------------------------------------------------ plumbing
+    def _bind_stream(self):
+        torch = self.torch
+        torch.cuda.set_device(self.device)
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.tehmm_ctx_set_stream(self.ctx.handle, ctypes.c_uint64(s)))
+
+    def _prec(self, precision=None):
+        p = precision or _PRECISION
+        return (_lib.F32, self.torch.float32) if p == "f32" else (_lib.F64, self.torch.float64)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def upload_model(self, log_start, log_trans, table, normalize, track_nsym=None):
+        self._bind_stream()
+        ls = _lib.f64(log_start)
+        lt = _lib.f64(log_trans)
+        tab = _lib.f64(table)
+        K, N, S = tab.shape
+        assert ls.shape == (N,) and lt.shape == (N, N)
+        ns = None
+        if track_nsym is not None:
+            ns = np.ascontiguousarray(np.minimum(np.asarray(track_nsym, dtype=np.int64), S), dtype=np.int32)
+            assert ns.shape == (K,)
+        _lib.check(self.lib.tehmm_set_model(self.ctx.handle, N, K, S, _lib.ptr(ls), _lib.ptr(lt), _lib.ptr(tab),
+                                            float(normalize), _lib.ptr(ns)))
+        self.N, self.K, self.S = N, K, S
+
+    def upload_batch(self, obs_list, pinned=None):
+        """Concatenate, copy to the device and describe to the library.
+        Returns (offsets ndarray int64[nseq+1])."""
+        torch = self.torch
+        self._bind_stream()
+        arrays = [as_obs_array(o) for o in obs_list]
+        assert len(arrays) > 0
+        K = arrays[0].shape[1]
+        for a in arrays:
+            assert a.shape[1] == K, "all sequences must have the same number of tracks"
+        dt = arrays[0].dtype
+        if any(a.dtype != dt for a in arrays):
+            dt = np.dtype(np.int32)
+            arrays = [a.astype(np.int32) for a in arrays]
+        lens = np.array([a.shape[0] for a in arrays], dtype=np.int64)
+        offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        host = arrays[0] if len(arrays) == 1 else np.concatenate(arrays, axis=0)
+        if dt == np.uint16:   # torch has no full uint16 support everywhere: move raw bytes
+            d_obs = torch.from_numpy(host.view(np.uint8).reshape(-1)).to(self.device)
+        else:
+            d_obs = torch.from_numpy(host.reshape(-1)).to(self.device)
+        self._keep["obs"] = d_obs
+        self._keep["offsets"] = offsets
+        _lib.check(self.lib.tehmm_set_batch(self.ctx.handle, self._p(d_obs), dt.itemsize, len(arrays),
+                                            _lib.ptr(offsets)))
+        self.total = int(offsets[-1])
+        self.nseq = len(arrays)
+        self.h2d_bytes = host.nbytes
+        return offsets
+
+    def use_device_batch(self, d_obs, obs_bytes, offsets):
+        """Batch already resident on the device (bench / multi-call reuse)."""
+        self._bind_stream()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._keep["obs"] = d_obs
+        self._keep["offsets"] = offsets
+        _lib.check(self.lib.tehmm_set_batch(self.ctx.handle, self._p(d_obs), int(obs_bytes), len(offsets) - 1,
+                                            _lib.ptr(offsets)))
+        self.total = int(offsets[-1])
+        self.nseq = len(offsets) - 1
+        return offsets
+
+    def upload_ratios(self, ratios_list):
+        """list of per-sequence float64 arrays (or None) -> device tensor or None."""
+        if ratios_list is None or all(r is None for r in ratios_list):
+            return None
+        offsets = self._keep["offsets"]
+        host = np.ones(self.total, dtype=np.float64)
+        for i, r in enumerate(ratios_list):
+            if r is not None:
+                r = np.asarray(r, dtype=np.float64)
+                assert r.shape[0] == offsets[i + 1] - offsets[i]
+                host[offsets[i]:offsets[i + 1]] = r
+        return self.torch.from_numpy(host).to(self.device)
+
+    def scratch(self, prec):
+        n = int(self.lib.tehmm_scratch_bytes(self.ctx.handle, prec))
+        buf = self._keep.get("scratch")
+        if buf is None or buf.numel() < n:
+            buf = self.torch.empty(max(n, 256), dtype=self.torch.uint8, device=self.device)
+            self._keep["scratch"] = buf
+        return buf
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ------------------------------------------------------------ device ops
+    def run_emission(self, prec, tdt, d_ratios, want_log, want_lin):
+        n = self.total * self.N
+        elog = self.empty(n, tdt) if want_log else None
+        blin = self.empty(n, tdt) if want_lin else None
+        rowmax = self.empty(self.total, self.torch.float64)
+        _lib.check(self.lib.tehmm_run_emission(self.ctx.handle, prec, self._p(d_ratios), self._p(elog),
+                                               self._p(blin), self._p(rowmax)))
+        return elog, blin, rowmax
+
+    def run_forward(self, prec, tdt, blin, rowmax, d_ratios, want_alpha=True):
+        alpha = self.empty(self.total * self.N, tdt) if want_alpha else None
+        logprob = self.empty(self.nseq, self.torch.float64)
+        sc = self.scratch(prec)
+        _lib.check(self.lib.tehmm_run_forward(self.ctx.handle, prec, self._p(blin), self._p(rowmax),
+                                              self._p(d_ratios), self._p(alpha), self._p(logprob), self._p(sc)))
+        return alpha, logprob
+
+    def run_backward(self, prec, tdt, flags, blin, alpha, d_ratios, start_trans=None):
+        torch = self.torch
+        post = self.empty(self.total * self.N, tdt) if flags & _lib.BWD_POSTERIORS else None
+        mstates = self.empty(self.total, torch.uint8) if flags & _lib.BWD_MAP else None
+        mscore = self.empty(self.nseq, torch.float64) if flags & _lib.BWD_MAP else None
+        sc = self.scratch(prec)
+        _lib.check(self.lib.tehmm_run_backward(self.ctx.handle, prec, flags, self._p(blin), self._p(alpha),
+                                               self._p(d_ratios), self._p(post), self._p(mstates),
+                                               self._p(mscore), self._p(start_trans), self._p(sc)))
+        return post, mstates, mscore
+
+    def run_emission_stats(self, prec, post, d_ratios, obs_stats, stats_S):
+        sc = self.scratch(prec)
+        _lib.check(self.lib.tehmm_run_emission_stats(self.ctx.handle, prec, self._p(post), self._p(d_ratios),
+                                                     self._p(obs_stats), int(stats_S), self._p(sc)))
+
+    def run_viterbi(self, prec, elog, d_ratios_em, d_ratios_dp, want64=True):
+        torch = self.torch
+        bp = self.empty(int(self.lib.tehmm_viterbi_bp_bytes(self.ctx.handle)), torch.uint8)
+        states = self.empty(self.total, torch.uint8)
+        states64 = self.empty(self.total, torch.int64) if want64 else None
+        logprob = self.empty(self.nseq, torch.float64)
+        sc = self.scratch(prec)
+        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), self._p(d_ratios_em),
+                                              self._p(d_ratios_dp), self._p(bp), self._p(states),
+                                              self._p(states64), self._p(logprob), self._p(sc)))
+        return states, states64, logprob
+
+    def to_f64(self, prec, t):
+        if prec == _lib.F64:
+            return t
+        out = self.empty(t.numel(), self.torch.float64)
+        _lib.check(self.lib.tehmm_convert_lattice(self.ctx.handle, prec, self._p(t), self._p(out), t.numel()))
+        return out
+
+    def split(self, host, width=None):
+        """Cut a concatenated host array back into per-sequence views."""
+        offsets = self._keep["offsets"]
+        if width:
+            host = host.reshape(-1, width)
+        return [host[offsets[i]:offsets[i + 1]] for i in range(len(offsets) - 1)]
+
+    # ------------------------------------------------------------ API-level ops
+    def emission_frames(self, ratios_list=None):
+        """allLogProbs for the current batch: list of (T_i, N) float64 (emission.py:179-198)."""
+        d_r = self.upload_ratios(ratios_list)
+        frame = self.empty(self.total * self.N, self.torch.float64)
+        _lib.check(self.lib.tehmm_run_emission_f64(self.ctx.handle, self._p(d_r), self._p(frame)))
+        return self.split(frame.cpu().numpy(), self.N)
+
+    def score(self, ratios_em=None, ratios_dp=None, precision=None):
+        prec, tdt = self._prec(precision)
+        d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
+        _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
+        _, logprob = self.run_forward(prec, tdt, blin, rowmax, d_rd, want_alpha=False)
+        return logprob.cpu().numpy()
+
+    def posteriors(self, ratios_em=None, ratios_dp=None, renorm_eps=True, want_map=False,
+                   want_post=True, precision=None):
+        """score_samples / _decode_map for the batch (basehmm.py:238-273,332-359)."""
+        prec, tdt = self._prec(precision)
+        d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
+        _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
+        alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_rd)
+        flags = (_lib.BWD_POSTERIORS if want_post else 0) | (_lib.BWD_MAP if want_map else 0) | \
+                (_lib.BWD_RENORM_EPS if renorm_eps else 0)
+        post, mstates, mscore = self.run_backward(prec, tdt, flags, blin, alpha, d_rd)
+        out = {"logprob": logprob.cpu().numpy()}
+        if want_post:
+            out["post"] = self.split(self.to_f64(prec, post).cpu().numpy(), self.N)
+        if want_map:
+            st64 = self.empty(self.total, self.torch.int64)
+            _lib.check(self.lib.tehmm_widen_states(self.ctx.handle, self._p(mstates), self._p(st64), self.total))
+            out["map_states"] = self.split(st64.cpu().numpy())
+            out["map_score"] = mscore.cpu().numpy()
+        return out
+
+    def viterbi(self, ratios_em=None, ratios_dp=None, precision=None):
+        """decode(algorithm='viterbi') for the batch (basehmm.py:301-330, hmm.py:668-676)."""
+        prec, tdt = self._prec(precision)
+        d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
+        elog, _, _ = self.run_emission(prec, tdt, d_re, True, False)
+        _, states64, logprob = self.run_viterbi(prec, elog, d_re, d_rd)
+        return logprob.cpu().numpy(), self.split(states64.cpu().numpy())
+
+    def estep(self, ratios=None, want_start=True, want_trans=True, want_obs=True,
+              precision=None, device_result=False, seq_slots=None, stats_S=None):
+        """One E-step over the batch (basehmm.py:507-522 + hmm.py:545-574).
+        Returns the packed float64 device tensor
+            [sum logprob | nseq | start N | trans N*N | obs K*N*S | per-sequence logprob]
+        (ready for ONE all-reduce) or, by default, a dict of host arrays.
+        seq_slots = (n_total, indices): where this batch's sequences sit in the
+        job-wide per-sequence tail (other ranks fill the other slots)."""
+        torch = self.torch
+        prec, tdt = self._prec(precision)
+        N, K = self.N, self.K
+        S = self.stats_S = int(stats_S) if stats_S else self.S    # width of the caller's obsStats
+        n_total, slots = seq_slots if seq_slots is not None else (self.nseq, list(range(self.nseq)))
+        d_r = self.upload_ratios(ratios)
+        _, blin, rowmax = self.run_emission(prec, tdt, d_r, False, True)
+        alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_r)
+        base = 2 + N + N * N + K * N * S
+        packed = torch.zeros(base + n_total, dtype=torch.float64, device=self.device)
+        flags = 0
+        if want_trans or want_start:
+            flags |= _lib.BWD_TRANS
+        if want_obs:
+            flags |= _lib.BWD_POSTERIORS
+        if flags:
+            post, _, _ = self.run_backward(prec, tdt, flags, blin, alpha, d_r,
+                                           start_trans=packed[2:2 + N + N * N])
+            if want_obs:
+                self.run_emission_stats(prec, post, d_r, packed[2 + N + N * N:base], S)
+        packed[0] = logprob.sum()
+        packed[1] = float(self.nseq)
+        packed[base:].index_copy_(0, torch.as_tensor(slots, dtype=torch.int64, device=self.device), logprob)
+        if device_result:
+            return packed
+        return self.unpack_stats(packed.cpu().numpy())
+
+    def unpack_stats(self, host):
+        N, K, S = self.N, self.K, getattr(self, "stats_S", self.S)
+        base = 2 + N + N * N + K * N * S
+        return {"logprob": float(host[0]), "nobs": int(round(host[1])),
+                "start": host[2:2 + N].copy(), "trans": host[2 + N:2 + N + N * N].reshape(N, N).copy(),
+                "obs": host[2 + N + N * N:base].reshape(K, N, S).copy(), "logprobs": host[base:].copy()}
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Engine of the calling thread's context (contexts are per thread, see _lib.get_context)."""
+    ctx = _lib.get_context(device)
+    eng = _engines.get(id(ctx))
+    if eng is None or eng.ctx is not ctx:
+        eng = _engines[id(ctx)] = Engine(ctx)
+    return eng

@@ -1,0 +1,217 @@
+"""-m gpu: the batched chunked-parallel kernels (C ABI tehmm_run_*) against the
+oracle and the reference's golden vectors.
+
+Tolerances (north_star): float32 path <= 1e-5 relative on log-likelihood,
+posteriors and expected counts; float64 verification mode <= 1e-10.  Viterbi
+paths must be identical except at documented near-ties: wherever the path
+differs, the float64 score of our path must equal the reference's score to the
+same tolerance.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+from conftest import golden, golden_names, ratios_of
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-5, "f64": 1e-10}
+# absolute floor for posteriors / counts: values below it are rounding of zero
+ATOL = {"f32": 2e-6, "f64": 1e-12}
+
+
+def engine(chunk_tiles=0, warmup=0):
+    from tehmm_b200.engine import get_engine
+    eng = get_engine(0)
+    eng.ctx.set_option("chunk_tiles", chunk_tiles)
+    eng.ctx.set_option("warmup", warmup)
+    return eng
+
+
+def oracle_all(oracle, obs, m_table, normalize, log_start, log_trans, r_em=None, r_dp=None):
+    T, N = obs.shape[0], log_start.shape[0]
+    frame = np.zeros((T, N))
+    oracle.fastAllLogProbs(obs, m_table, frame, normalize, r_em)
+    fwd, bwd = np.zeros((T, N)), np.zeros((T, N))
+    oracle._forward(T, N, log_start, log_trans, frame, r_dp, fwd)
+    oracle._backward(T, N, log_start, log_trans, frame, r_dp, bwd)
+    lp = oracle.logsumexp(fwd[-1])
+    post = oracle.posteriors(fwd, bwd)
+    states, vlp = oracle._viterbi(T, N, log_start, log_trans, r_dp, frame)
+    return dict(frame=frame, fwd=fwd, bwd=bwd, logprob=lp, post=post, vit_states=states, vit_logprob=vlp)
+
+
+def path_score(oracle, frame, log_start, log_trans, states):
+    """float64 score of a path (no ratios)"""
+    s = log_start[states[0]] + frame[0, states[0]]
+    s += np.sum(log_trans[states[:-1], states[1:]] + frame[np.arange(1, len(states)), states[1:]])
+    return s
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", golden_names("ll_"))
+def test_golden_batched(name, prec):
+    g = golden(name)
+    if int(g["N"]) > 64:
+        pytest.skip("batched path supports N <= 64")
+    eng = engine(chunk_tiles=1, warmup=8)          # T is small: force several chunks
+    r = ratios_of(g)
+    widths = [int(s) + 1 for s in g["syms"]]
+    eng.upload_model(g["log_start"], g["log_trans"], g["table"], float(g["normalize"]), widths)
+    eng.upload_batch([g["obs"]])
+    rl = None if r is None else [r]
+    frames = eng.emission_frames(rl)
+    assert_array_equal(frames[0], g["frame"])                   # float64 gather-sum is bit-exact
+    out = eng.posteriors(ratios_em=rl, ratios_dp=rl, renorm_eps=False, want_map=True, precision=prec)
+    assert out["logprob"][0] == pytest.approx(float(g["logprob"]), rel=TOL[prec])
+    assert_allclose(out["post"][0], g["post"], rtol=TOL[prec], atol=ATOL[prec])
+    lps, states = eng.viterbi(ratios_em=rl, ratios_dp=rl, precision=prec)
+    if prec == "f64":
+        assert_array_equal(states[0], g["vit_states"])
+    else:
+        assert np.mean(states[0] == g["vit_states"]) >= 0.98
+    assert lps[0] == pytest.approx(float(g["vit_logprob"]), rel=1e-6 if prec == "f32" else 1e-10)
+    st = eng.estep(ratios=rl, precision=prec)
+    T = g["obs"].shape[0]
+    assert st["logprob"] == pytest.approx(float(g["logprob"]), rel=TOL[prec])
+    assert_allclose(st["start"], g["post"][0], rtol=TOL[prec], atol=ATOL[prec])
+    if T > 1:
+        assert_allclose(st["trans"], np.exp(g["lneta"]), rtol=10 * TOL[prec], atol=ATOL[prec])
+    assert_allclose(st["obs"], g["obs_stats"], rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("warmup", [1, 64])
+def test_multi_sequence_ragged(oracle, prec, warmup):
+    """ragged batch incl. T=1 and T=2 sequences; warmup=1 forces the repair path."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=21)
+    lens = [1, 2, 700, 65, 64, 1300, 129]
+    obs = [synth.sample_obs(m, T, seed=30 + i)[0] for i, T in enumerate(lens)]
+    eng = engine(chunk_tiles=2, warmup=warmup)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    out = eng.posteriors(renorm_eps=True, want_map=True, precision=prec)
+    lps, states = eng.viterbi(precision=prec)
+    for i, o in enumerate(obs):
+        ref = oracle_all(oracle, o, m["table"], 1.0, m["log_start"], m["log_trans"])
+        assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=TOL[prec])
+        post = oracle.posteriors(ref["fwd"], ref["bwd"], renorm_eps=True)
+        assert_allclose(out["post"][i], post, rtol=TOL[prec], atol=ATOL[prec])
+        ref_map = np.argmax(post, axis=1)
+        agree = np.mean(out["map_states"][i] == ref_map)
+        assert agree >= (1.0 if prec == "f64" else 0.995)
+        assert out["map_score"][i] == pytest.approx(np.max(post, axis=1).sum(), rel=TOL[prec])
+        if prec == "f64":
+            assert_array_equal(states[i], ref["vit_states"])
+        else:
+            mine = path_score(oracle, ref["frame"], m["log_start"], m["log_trans"], states[i])
+            assert mine == pytest.approx(ref["vit_logprob"], rel=1e-6)       # near-tie rule
+            assert np.mean(states[i] == ref["vit_states"]) >= 0.97
+        assert lps[i] == pytest.approx(ref["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
+    if warmup == 1:
+        assert eng.ctx.stat("repair_passes_forward") > 0      # the repair path really ran
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_estep_matches_oracle(oracle, prec):
+    """Device E-step == sum over sequences of the reference's per-sequence E-step."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=41)
+    lens = [3000, 500, 1, 2500]
+    obs = [synth.sample_obs(m, T, seed=50 + i)[0] for i, T in enumerate(lens)]
+    eng = engine(chunk_tiles=4, warmup=64)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    st = eng.estep(precision=prec)
+    K, N, S = m["table"].shape
+    s0, tr, ob = np.zeros(N), np.zeros((N, N)), np.zeros((K, N, S))
+    lp = 0.0
+    for o in obs:
+        lp += oracle.estep_sequence(o, m["table"], 1.0, m["log_start"], m["log_trans"], None, s0, tr, ob)
+    assert st["logprob"] == pytest.approx(lp, rel=TOL[prec])
+    assert st["nobs"] == len(obs)
+    assert_allclose(st["start"], s0, rtol=TOL[prec], atol=ATOL[prec])
+    assert_allclose(st["trans"], tr, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+    assert_allclose(st["obs"], ob, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+    # size-independent properties: posterior mass is conserved
+    assert st["obs"].sum() == pytest.approx(sum(lens) * K, rel=1e-6)
+    assert st["trans"].sum() * N == pytest.approx(sum(lens) - len(lens), rel=1e-6)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_segment_ratios(oracle, prec):
+    """ratios in the emission and in the DP, including the Viterbi from-state-0 quirk."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=12, syms=(4, 8, 2), seed=61, zero_frac=0.0)
+    T = 900
+    obs = synth.sample_obs(m, T, seed=62)[0]
+    r = np.random.RandomState(63).uniform(0.05, 6.0, size=T)
+    eng = engine(chunk_tiles=2, warmup=64)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"], r_em=r, r_dp=r)
+    out = eng.posteriors(ratios_em=[r], ratios_dp=[r], renorm_eps=False, precision=prec)
+    assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL[prec])
+    assert_allclose(out["post"][0], ref["post"], rtol=10 * TOL[prec], atol=ATOL[prec])
+    # decode(): emission WITHOUT ratios, DP with ratios (basehmm.py:327, hmm.py:674)
+    ref2 = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"], r_em=None, r_dp=r)
+    lps, states = eng.viterbi(ratios_em=None, ratios_dp=[r], precision=prec)
+    assert lps[0] == pytest.approx(ref2["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
+    assert np.mean(states[0] == ref2["vit_states"]) >= (1.0 if prec == "f64" else 0.97)
+    # E-step with ratios
+    K, N, S = m["table"].shape
+    s0, tr, ob = np.zeros(N), np.zeros((N, N)), np.zeros((K, N, S))
+    oracle.estep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"], r, s0, tr, ob)
+    st = eng.estep(ratios=[r], precision=prec)
+    assert_allclose(st["trans"], tr, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+    assert_allclose(st["obs"], ob, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+
+
+def test_wide_model_50_states(oracle):
+    """N = 50 (two states per lane), int32 symbols."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=50, syms=(4, 8, 2, 2), seed=71)
+    obs = synth.sample_obs(m, 1500, seed=72, dtype=np.int32)[0]
+    eng = engine(chunk_tiles=4, warmup=64)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    for prec in ("f64", "f32"):
+        out = eng.posteriors(renorm_eps=False, precision=prec)
+        assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL[prec])
+        assert_allclose(out["post"][0], ref["post"], rtol=TOL[prec], atol=ATOL[prec])
+        lps, states = eng.viterbi(precision=prec)
+        assert lps[0] == pytest.approx(ref["vit_logprob"], rel=1e-6)
+        assert np.mean(states[0] == ref["vit_states"]) >= (1.0 if prec == "f64" else 0.97)
+    st = eng.estep(precision="f32")
+    K, N, S = m["table"].shape
+    s0, tr, ob = np.zeros(N), np.zeros((N, N)), np.zeros((K, N, S))
+    oracle.estep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"], None, s0, tr, ob)
+    assert_allclose(st["trans"], tr, rtol=1e-4, atol=1e-5)
+    assert_allclose(st["obs"], ob, rtol=1e-4, atol=1e-5)
+
+
+def test_f32_vs_f64_at_scale():
+    """T = 2e6 (oracle would take minutes): float32 production path against the
+    float64 verification path on the GPU, plus size-independent invariants."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=81)
+    T = 2_000_000
+    obs = synth.sample_obs(m, T, seed=82)[0]
+    eng = engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    a = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f64")
+    b = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f32")
+    assert b["logprob"][0] == pytest.approx(a["logprob"][0], rel=1e-7)
+    assert np.mean(a["map_states"][0] == b["map_states"][0]) > 0.9995
+    lp64, s64 = eng.viterbi(precision="f64")
+    lp32, s32 = eng.viterbi(precision="f32")
+    assert lp32[0] == pytest.approx(lp64[0], rel=1e-7)          # near-ties only
+    assert np.mean(s64[0] == s32[0]) > 0.995
+    assert lp64[0] <= a["logprob"][0]                            # best path <= total probability
+    st = eng.estep(precision="f32")
+    assert st["obs"].sum() == pytest.approx(T * m["K"], rel=1e-6)
+    assert st["trans"].sum() * m["N"] == pytest.approx(T - 1, rel=1e-6)
+    assert st["start"].sum() == pytest.approx(1.0, rel=1e-6)
