@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- trellis cells/s of one fwd-bwd + Viterbi sweep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: emission gather-sum ->
+forward -> backward with posterior argmax (MAP) -> Viterbi DP -> traceback +
+float64 re-score.  Workload at N=1 = BASELINE.json configs[1]: 10 tracks
+(6 multinomial + 4 binary), 30 states, ONE sequence of 10 M observations
+(alyrata-like synthetic, sampled from the model).  With N GPUs every rank runs
+its own sequence of the same shape (weak scaling, no data-path collective).
+
+value  : cells/s (sum over ranks of T*N, divided by the max-over-ranks device
+         time of the K timed steps), observations already resident in HBM.
+e2e    : the same metric through the public API with HOST buffers
+         (MultitrackHmm.decode_batch for Viterbi and for MAP): H2D of the
+         observations and D2H of the int64 state paths inside the timed region.
+--impl reference : the reference's own CPU implementation (oracle/_ref when it
+         is built, else the oracle port) on the host cores, one process per core
+         in the style of teHmmEval --chroms --proc.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hmm_trellis_cells_per_sec_fwd_bwd_viterbi"
+UNIT = "cells/s"
+N_STATES, T_DEFAULT = 30, 10_000_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--T", type=int, default=T_DEFAULT, help="observations per GPU")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="observations of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-em", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(T, gpus):
+    return {"workload": "c2: alyrata-like synthetic, 10 multinomial/binary tracks, 30 states, one "
+                        "sequence of %d observations per GPU, fwd-bwd(MAP)+Viterbi sweep" % T,
+            "states": N_STATES, "tracks": 10, "obs_per_gpu": T, "gpus": gpus,
+            "l2": "inputs larger than L2 (obs %.0f MB, lattices %.1f GB per GPU), no flush needed" % (
+                T * 10 / 1e6, T * N_STATES * 4 * 3 / 1e9)}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------ CPU arms
+def cpu_sweep_reference(R, m, obs):
+    """the reference's own Cython functions + its NumPy glue (basehmm.py:265-272,357)"""
+    T, N = obs.shape[0], m["N"]
+    frame = np.zeros((T, N))
+    R._emission.fastAllLogProbs(obs, m["table"], frame, 1.0, None)
+    fwd = np.zeros((T, N))
+    R._hmm._forward(T, N, m["log_start"], m["log_trans"], frame, None, fwd)
+    bwd = np.zeros((T, N))
+    R._hmm._backward(T, N, m["log_start"], m["log_trans"], frame, None, bwd)
+    gamma = fwd + bwd
+    post = np.exp(gamma.T - R.basehmm.logsumexp(gamma, axis=1)).T
+    post += np.finfo(np.float32).eps
+    post /= np.sum(post, axis=1).reshape((-1, 1))
+    mp = np.argmax(post, axis=1)
+    st, lp = R._hmm._viterbi(T, N, m["log_start"], m["log_trans"], None, frame)
+    return lp, st, mp
+
+
+def cpu_sweep(kind, m, obs):
+    if kind == "reference":
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_loader
+        return cpu_sweep_reference(ref_loader.load(), m, obs)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    r = orc.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    return r["vit_logprob"], r["vit_states"], r["map_states"]
+
+
+def cpu_kind():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_loader
+        if ref_loader.available():
+            ref_loader.load()
+            return "reference"
+    except Exception:
+        pass
+    import oracle as orc
+    orc.build()
+    return "port"
+
+
+def _cpu_worker(args):
+    kind, seed, T = args
+    from tehmm_b200 import synth
+    m = synth.make_model(N=N_STATES, seed=0)
+    obs, _ = synth.sample_obs(m, T, seed=seed)
+    t0 = time.perf_counter()
+    cpu_sweep(kind, m, obs)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    """--impl reference: every host core runs the reference sweep on its own slice."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    kind = cpu_kind()
+    cores = os.cpu_count() or 1
+    per = max(20_000, min(100_000, args.cpu_sample // 4))
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            # step time = slowest worker's sweep (data generation is outside the clock)
+            dt = max(pool.map(_cpu_worker, [(kind, 1000 + 97 * it + c, per) for c in range(cores)]))
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    cells = float(args.steps) * cores * per * N_STATES
+    value = cells / total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.T, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d processes x %d observations per step (one sequence each, "
+                                       "teHmmEval --chroms --proc style), N=30, K=10" % (cores, per)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tehmm_b200 import _lib, synth
+    from tehmm_b200.emission import IndependentMultinomialEmissionModel
+    from tehmm_b200.engine import Engine
+    from tehmm_b200.hmm import MultitrackHmm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    T = args.T
+
+    m = synth.make_model(N=N_STATES, seed=0)
+    obs, _ = synth.sample_obs(m, T, seed=1 + rank)
+    obs_pinned = torch.from_numpy(obs).pin_memory()
+
+    ctx = _lib.get_context(local)
+    eng = Engine(ctx)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    d_obs = obs_pinned.to(dev, non_blocking=True).reshape(-1)
+    eng.use_device_batch(d_obs, 1, np.array([0, T], dtype=np.int64))
+    prec, tdt = eng._prec(args.precision)
+    stage_names = ["emission", "forward", "backward_map", "viterbi_dp_traceback"]
+
+    def sweep(events=None):
+        def mark(i):
+            if events is not None:
+                events[i].record()
+        mark(0)
+        elog, blin, rowmax = eng.run_emission(prec, tdt, None, True, True)
+        mark(1)
+        alpha, logprob = eng.run_forward(prec, tdt, blin, rowmax, None)
+        mark(2)
+        _, mstates, mscore = eng.run_backward(prec, tdt, _lib.BWD_MAP, blin, alpha, None)
+        mark(3)
+        states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False)
+        mark(4)
+        return logprob, mscore, vlp, states, mstates
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = sweep()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        out = sweep(evs[k])
+    barrier()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = np.zeros(4)
+    total_ms = 0.0
+    for k in range(args.steps):
+        for i in range(4):
+            stage_ms[i] += evs[k][i].elapsed_time(evs[k][i + 1])
+        total_ms += evs[k][0].elapsed_time(evs[k][4])
+    # whole timed region incl. gaps between steps
+    region_ms = evs[0][0].elapsed_time(evs[-1][4])
+    t_max = torch.tensor([region_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    region_ms = float(t_max.item())
+    cells = float(world) * T * N_STATES * args.steps
+    value = cells / (region_ms * 1e-3)
+    logprob, mscore, vlp, states, mstates = out
+    sanity = {"logprob": float(logprob[0].item()), "viterbi_logprob": float(vlp[0].item()),
+              "map_score": float(mscore[0].item()),
+              "repairs": {k: ctx.stat("repaired_chunks_" + k) for k in ("forward", "backward", "viterbi")},
+              "chunks": ctx.stat("chunks")}
+
+    # ---- roofline of the dominant kernel (SURVEY.md section 8d per-step bytes)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    K = m["K"]
+    alg_bytes = {"emission": K, "forward": K + 4 * N_STATES, "backward_map": K + 4 * N_STATES + 1,
+                 "viterbi_dp_traceback": K + N_STATES + 2}
+    dom = int(np.argmax(stage_ms))
+    dom_ms = stage_ms[dom] / args.steps
+    achieved = alg_bytes[stage_names[dom]] * T / (dom_ms * 1e-3) / 1e9
+    sweep_achieved = (3 * K + 9 * N_STATES + 3) * T / (total_ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_step": alg_bytes[stage_names[dom]],
+                "sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,
+                          "algorithmic_bytes_per_step": 3 * K + 9 * N_STATES + 3},
+                "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(stage_names, stage_ms)}}
+
+    # ---- end to end through the public API, host buffers in and out
+    e2e = None
+    if not args.no_e2e:
+        em = IndependentMultinomialEmissionModel(N_STATES, list(m["syms"]), zeroAsMissingData=True)
+        em.logProbs = m["table"].copy()
+        hmm_v = MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy())
+        hmm_m = MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy(), algorithm="map")
+        host_obs = obs_pinned.numpy()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(1):
+            hmm_v.decode_batch([host_obs]); hmm_m.decode_batch([host_obs])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            rv = hmm_v.decode_batch([host_obs])
+            rm = hmm_m.decode_batch([host_obs])
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": float(world) * T * N_STATES * n_e2e / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * host_obs.nbytes), "d2h_bytes_per_step": int(2 * 8 * T + 32),
+               "steps": n_e2e, "ms_per_step": 1e3 * dt / n_e2e,
+               "api": "MultitrackHmm.decode_batch (viterbi) + MultitrackHmm(algorithm='map').decode_batch, "
+                      "NumPy uint8 in, int64 paths out"}
+        assert rv[0][1].dtype == np.int64 and rv[0][1].shape[0] == T
+
+    # ---- seconds per EM iteration (second half of the BASELINE metric)
+    em_iter = None
+    if not args.no_em:
+        eng.use_device_batch(d_obs, 1, np.array([0, T], dtype=np.int64))
+        eng.estep(device_result=True)
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        n_em = 2
+        for _ in range(n_em):
+            packed = eng.estep(device_result=True)
+            if world > 1:
+                dist.all_reduce(packed)
+        b_.record()
+        barrier()
+        em_iter = {"seconds": a.elapsed_time(b_) * 1e-3 / n_em, "obs_per_gpu": T,
+                   "what": "emission+forward+backward(xi,posteriors)+histograms+allreduce, device resident"}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        kind = cpu_kind()
+        Ts = args.cpu_sample
+        t0 = time.perf_counter()
+        lp_cpu, st_cpu, mp_cpu = cpu_sweep(kind, m, obs[:Ts])
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": Ts * N_STATES / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": "first %d observations of the rank-0 sequence, single thread, %.1f s" % (Ts, dt)}
+        # the CPU run doubles as a parity spot check of the production path on the real workload
+        eng.upload_batch([obs[:Ts]])
+        lps, sts = eng.viterbi(precision=args.precision)
+        cpu_baseline["viterbi_path_agreement"] = float(np.mean(sts[0] == st_cpu))
+        cpu_baseline["viterbi_logprob_rel_err"] = float(abs(lps[0] - lp_cpu) / abs(lp_cpu))
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": workload_config(T, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "em_iter": em_iter, "sanity": sanity}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

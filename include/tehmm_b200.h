@@ -82,8 +82,9 @@ int tehmm_ctx_destroy(tehmm_ctx *ctx);
 /* block until everything enqueued on the context's stream has finished */
 int tehmm_ctx_sync(tehmm_ctx *ctx);
 /* run on a caller-owned cudaStream_t (e.g. torch's current stream) so that the
- * caller's allocations, copies and events are ordered with the kernels;
- * 0 = back to the context's own stream */
+ * caller's allocations, copies and events are ordered with the kernels.
+ * 0 is the CUDA legacy default stream; UINT64_MAX = back to the context's own
+ * (non-blocking) stream */
 int tehmm_ctx_set_stream(tehmm_ctx *ctx, uint64_t stream);
 /* the context's cudaStream_t as an integer (for event timing by the caller) */
 uint64_t tehmm_ctx_stream(tehmm_ctx *ctx);

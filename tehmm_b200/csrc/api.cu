@@ -20,8 +20,8 @@ void tehmm_launch_strict_counts(cudaStream_t, const void *, int, int, int64_t, i
 size_t tehmm_emission_table_budget(int K);
 int tehmm_launch_emission(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const double *, void *, void *, double *, double *, int *, int, cudaError_t *);
 cudaError_t tehmm_launch_forward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, const double *, void *, void *, void *, double *, const int *, int, int);
-cudaError_t tehmm_launch_verify(cudaStream_t, const TehmmBatchDev &, int, int, void *, const void *, double, double, int, int *, int *);
-cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, int, int, const void *, const double *, double *);
+cudaError_t tehmm_launch_verify(cudaStream_t, const TehmmBatchDev &, int, int, void *, const void *, double, int, int, int *, int *, double *);
+cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, int, int, const void *, const double *, const double *, double *);
 cudaError_t tehmm_launch_backward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, int, const void *, const void *, const double *, void *, uint8_t *, double *, void *, void *, void *, void *, void *, const int *, int, int);
 cudaError_t tehmm_launch_trans_reduce(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const void *, const void *, double *);
 cudaError_t tehmm_launch_map_reduce(cudaStream_t, const TehmmBatchDev &, const double *, double *);
@@ -139,7 +139,8 @@ int tehmm_ctx_set_stream(tehmm_ctx *c, uint64_t stream)
     if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    c->stream = stream ? (cudaStream_t)(uintptr_t)stream : c->own_stream;
+    // 0 is a real stream (the legacy default stream torch uses unless told otherwise)
+    c->stream = stream == UINT64_MAX ? c->own_stream : (cudaStream_t)(uintptr_t)stream;
     return TEHMM_OK;
 }
 
@@ -565,10 +566,20 @@ int tehmm_run_emission_f64(tehmm_ctx *c, const double *d_ratios, double *d_frame
     return TEHMM_OK;
 }
 
-static void tolerances(int prec, bool log_space, double *ta, double *tr)
+// verification tolerance: spread of component ratios (linear space) or of
+// component differences (log space); see verify_kernel
+static double tolerance(int prec, bool log_space)
 {
-    if (log_space) { *ta = prec == TEHMM_F32 ? 1e-5 : 1e-11; *tr = prec == TEHMM_F32 ? 1e-6 : 1e-14; }
-    else { *ta = prec == TEHMM_F32 ? 2e-6 : 1e-13; *tr = 0.0; }
+    if (log_space) return prec == TEHMM_F32 ? 1e-5 : 1e-11;
+    return prec == TEHMM_F32 ? 4e-6 : 1e-12;
+}
+
+// The warm-up length adapts: if more than 2% of the chunks of a pass had to be
+// repaired, later passes of this context speculate twice as far back.
+static void adapt_warmup(tehmm_ctx *c, int first_pass_bad)
+{
+    if (c->opt_warmup > 0) return;
+    if ((int64_t)first_pass_bad * 50 > c->b.nchunks && c->b.warmup < 4096) c->b.warmup *= 2;
 }
 
 int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *d_rowmax,
@@ -579,26 +590,26 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     const Scratch s = carve(c, prec);
     char *w = (char *)d_scratch;
     void *sv = w + s.start_vec, *ev = w + s.end_vec;
-    double *cs = (double *)(w + s.cscale);
+    double *cs = (double *)(w + s.cscale), *lkap = (double *)(w + s.part_a);
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     const int grid = scan_grid(c);
     CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 0, grid));
     c->launches += 1;
-    double ta, tr;
-    tolerances(prec, false, &ta, &tr);
+    const double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, +1, bad, nbad));
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, +1, 1, bad, nbad, lkap));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (pass == 0) adapt_warmup(c, nb);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "forward repair did not converge (%d chunks left)", nb);
         c->stat_repair_fwd += 1; c->stat_bad_fwd += nb;
         CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 1, grid));
         c->launches += 1;
     }
-    CU(tehmm_launch_forward_logprob(st, c->b, prec, c->m.NP, ev, cs, d_logprob));
+    CU(tehmm_launch_forward_logprob(st, c->b, prec, c->m.NP, ev, cs, lkap, d_logprob));
     c->launches += 1;
     return TEHMM_OK;
 }
@@ -621,14 +632,14 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     const int grid = scan_grid(c);
     CU(tehmm_launch_backward(st, c->m, c->b, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, 0, grid));
     c->launches += 1;
-    double ta, tr;
-    tolerances(prec, false, &ta, &tr);
+    const double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, -1, bad, nbad));
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, -1, 1, bad, nbad, nullptr));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (pass == 0) adapt_warmup(c, nb);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "backward repair did not converge (%d chunks left)", nb);
         c->stat_repair_bwd += 1; c->stat_bad_bwd += nb;
@@ -669,14 +680,14 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     CU(cudaMemsetAsync(tilemap, 0, (size_t)c->b.ntiles * c->m.NP, st));
     CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, (uint8_t *)d_bp, tilemap, sv, ev, bad, 0, grid));
     c->launches += 1;
-    double ta, tr;
-    tolerances(prec, true, &ta, &tr);
+    const double tol = tolerance(prec, true);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, ta, tr, +1, bad, nbad));
+        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, +1, 0, bad, nbad, nullptr));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (pass == 0) adapt_warmup(c, nb);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
         c->stat_repair_vit += 1; c->stat_bad_vit += nb;

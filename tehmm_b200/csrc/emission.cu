@@ -8,37 +8,25 @@
 // symbols staged per warp iteration with a coalesced load.
 #include "scan.cuh"
 
-#define EM_WARPS 8
-#define EM_ROWS 32   // time steps staged per warp iteration
-
-// frame value of one (t, state): ((sum_k table) * normalize) * ratio, float64.
-template <bool SMEM_TABLE>
-__device__ __forceinline__ double em_gather(const TehmmModelDev &m, const double *tab,
-                                            const int32_t *offs, const int32_t *nsyms,
-                                            const int *syms, int j)
-{
-    double v = 0.0;
-    for (int k = 0; k < m.K; ++k) {
-        int sym = syms[k];
-        if (sym < nsyms[k])
-            v += tab[(int64_t)(offs[k] + sym) * m.N + j];
-        else   // symbol outside the compact table: dense table as the reference indexes it
-            v += m.table[((int64_t)k * m.N + j) * m.S + sym];
-    }
-    return v;
-}
+#define EM_WARPS 16
+#define EM_ROWS 16   // time steps staged per warp iteration
 
 // MODE 0: write normalised log (elog) / linear (blin) copies in type T + rowmax
 // MODE 1: write the reference-layout float64 frame only
-template <typename T, typename OBS, int MODE>
-__global__ void __launch_bounds__(EM_WARPS * 32)
+// Staging turns each symbol into the element offset of its table row
+// ((tab_off[k] + symbol) * N), so the inner loop is one broadcast LDS of the
+// offset and one conflict-free LDS.64 of the table entry per (row, track).
+// A symbol outside the compact table is staged as -(1 + k*S + symbol) and read
+// from the dense table exactly as the reference indexes it.
+template <typename T, typename OBS, int MODE, int NS>
+__global__ void __launch_bounds__(EM_WARPS * 32, 2)
 emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                 const double *__restrict__ ratios, T *__restrict__ elog, T *__restrict__ blin,
                 double *__restrict__ rowmax, double *__restrict__ frame,
                 int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq)
 {
     extern __shared__ __align__(16) unsigned char em_smem[];
-    // layout: [K] offs | [K] nsyms | per-warp symbol staging | table
+    // layout: [K] offs | [K] nsyms | per-warp offset staging | table
     int32_t *offs = reinterpret_cast<int32_t *>(em_smem);
     int32_t *nsyms = offs + m.K;
     int *stage_all = reinterpret_cast<int *>(nsyms + m.K);
@@ -46,80 +34,87 @@ emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
     double *tab_s = reinterpret_cast<double *>(em_smem + head);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = threadIdx.x; k < m.K; k += blockDim.x) {
+    const int K = m.K, N = m.N;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
         offs[k] = m.tab_off[k];
         nsyms[k] = m.track_nsym[k];
     }
     const double *tab = m.table_t;
     if (m.table_in_smem) {
-        int64_t n = (int64_t)m.tab_rows * m.N;
+        int64_t n = (int64_t)m.tab_rows * N;
         for (int64_t e = threadIdx.x; e < n; e += blockDim.x) tab_s[e] = m.table_t[e];
         tab = tab_s;
     }
     __syncthreads();
 
-    int *stage = stage_all + warp * EM_ROWS * m.K;
+    int *stage = stage_all + warp * EM_ROWS * K;
     const int64_t nblocks = (total + EM_ROWS - 1) / EM_ROWS;
     for (int64_t blk = (int64_t)blockIdx.x * EM_WARPS + warp; blk < nblocks;
          blk += (int64_t)gridDim.x * EM_WARPS) {
         const int64_t tb = blk * EM_ROWS;
         const int rows = (int)min((int64_t)EM_ROWS, total - tb);
         __syncwarp();
-        for (int e = lane; e < rows * m.K; e += 32) stage[e] = (int)obs[tb * m.K + e];
+        for (int e = lane; e < rows * K; e += 32) {
+            const int sym = (int)obs[tb * K + e];
+            const int k = e % K;
+            stage[e] = sym < nsyms[k] ? (offs[k] + sym) * N : -(1 + k * m.S + sym);
+        }
         __syncwarp();
         for (int r = 0; r < rows; ++r) {
             const int64_t t = tb + r;
-            const int *syms = stage + r * m.K;
-            const double rt = ratios ? ratios[t] : 1.0;
-            double v[2];
-            double vmax = -INFINITY;
+            const int *so = stage + r * K;
+            double v[NS];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                int j = lane + 32 * s;
-                v[s] = -INFINITY;
-                if (j < m.N) {
-                    double x = em_gather<true>(m, tab, offs, nsyms, syms, j);
-                    x *= m.normalize;
-                    if (ratios) x *= rt;
-                    v[s] = x;
-                    vmax = fmax(vmax, x);
-                }
-            }
-            if (MODE == 1) {
+            for (int s = 0; s < NS; ++s) v[s] = 0.0;
+#pragma unroll 5
+            for (int k = 0; k < K; ++k) {
+                const int o = so[k];
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    int j = lane + 32 * s;
-                    if (j < m.N) frame[t * m.N + j] = v[s];
-                }
-                float mf = warp_max_any((float)vmax);
-                if (!(mf > (float)TEHMM_MINDBL) && seq_flag) {
-                    // candidate for the "no state can emit" quirk; exact test on doubles
-                    double md = warp_max(vmax);
-                    if (!(md > TEHMM_MINDBL) && lane == 0) {
-                        int64_t lo = 0, hi = nseq;   // find sequence of row t
-                        while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
-                        seq_flag[lo] = 1;
+                for (int s = 0; s < NS; ++s) {
+                    const int j = lane + 32 * s;
+                    if (j < N) {
+                        if (o >= 0) {
+                            v[s] += tab[o + j];
+                        } else {
+                            const int code = -o - 1;
+                            v[s] += m.table[((int64_t)(code / m.S) * N + j) * m.S + code % m.S];
+                        }
                     }
                 }
-                continue;
+            }
+            double vmax = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                v[s] *= m.normalize;
+                if (ratios) v[s] *= ratios[t];
+                if (lane + 32 * s < N) vmax = fmax(vmax, v[s]); else v[s] = -INFINITY;
             }
             // row maximum: float REDUX first; exact double fallback when it overflows fp32
             float mf = warp_max_any((float)vmax);
             double M = (double)mf;
-            if (!(mf > -INFINITY)) M = warp_max(vmax);
-            if (!(M > TEHMM_MINDBL) && seq_flag && lane == 0) {
-                int64_t lo = 0, hi = nseq;
-                while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
-                seq_flag[lo] = 1;
+            if (!(mf > (float)TEHMM_MINDBL)) {
+                M = warp_max(vmax);
+                // candidate for the "no state can emit" quirk (_emission.pyx:73-80)
+                if (!(M > TEHMM_MINDBL) && seq_flag && lane == 0) {
+                    int64_t lo = 0, hi = nseq;   // sequence of row t
+                    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
+                    seq_flag[lo] = 1;
+                }
+            }
+            if (MODE == 1) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s)
+                    if (lane + 32 * s < N) frame[t * N + lane + 32 * s] = v[s];
+                continue;
             }
             if (lane == 0) rowmax[t] = M;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                int j = lane + 32 * s;
-                if (j < m.N) {
-                    double d = (M > -INFINITY) ? v[s] - M : 0.0;
-                    if (elog) elog[t * m.N + j] = (T)d;
-                    if (blin) blin[t * m.N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
+            for (int s = 0; s < NS; ++s) {
+                const int j = lane + 32 * s;
+                if (j < N) {
+                    const double d = (M > -INFINITY) ? v[s] - M : 0.0;
+                    if (elog) elog[t * N + j] = (T)d;
+                    if (blin) blin[t * N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
                 }
             }
         }
@@ -170,16 +165,16 @@ size_t tehmm_emission_table_budget(int K)
     return (size_t)220 * 1024 - head;
 }
 
-template <typename T, typename OBS, int MODE>
-static cudaError_t launch_em(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
-                             const double *ratios, T *elog, T *blin, double *rowmax,
-                             double *frame, int *seq_flag, int sms)
+template <typename T, typename OBS, int MODE, int NS>
+static cudaError_t launch_em_ns(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                const double *ratios, T *elog, T *blin, double *rowmax,
+                                double *frame, int *seq_flag, int sms)
 {
     size_t smem = em_smem_bytes(m);
-    auto kern = emission_kernel<T, OBS, MODE>;
+    auto kern = emission_kernel<T, OBS, MODE, NS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int per_sm = smem > 110 * 1024 ? 1 : (smem > 70 * 1024 ? 2 : 3);
+    int per_sm = smem > 112 * 1024 ? 1 : 2;
     int64_t need = ((b.total + EM_ROWS - 1) / EM_ROWS + EM_WARPS - 1) / EM_WARPS;
     if (need < 1) need = 1;
     int64_t cap = (int64_t)sms * per_sm;
@@ -187,6 +182,15 @@ static cudaError_t launch_em(cudaStream_t st, const TehmmModelDev &m, const Tehm
     kern<<<grid, EM_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
                                             rowmax, frame, seq_flag, b.seq_off, b.nseq);
     return cudaGetLastError();
+}
+
+template <typename T, typename OBS, int MODE>
+static cudaError_t launch_em(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                             const double *ratios, T *elog, T *blin, double *rowmax,
+                             double *frame, int *seq_flag, int sms)
+{
+    if (m.NS == 1) return launch_em_ns<T, OBS, MODE, 1>(st, m, b, ratios, elog, blin, rowmax, frame, seq_flag, sms);
+    return launch_em_ns<T, OBS, MODE, 2>(st, m, b, ratios, elog, blin, rowmax, frame, seq_flag, sms);
 }
 
 template <typename T, int MODE>

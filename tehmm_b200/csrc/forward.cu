@@ -174,38 +174,80 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
 }
 
 // bad[c] = speculated start vector of chunk c differs from the neighbour's end
-// vector by more than tol (both canonical).  dir=+1: neighbour is c-1 (forward,
-// Viterbi); dir=-1: neighbour is c+1 (backward).  A bad chunk gets the true
-// vector copied into its start slot for the repair pass.
+// vector by more than tol.  dir=+1: neighbour is c-1 (forward, Viterbi);
+// dir=-1: neighbour is c+1 (backward).
+// Linear-space vectors (forward / backward) are defined only up to a scale
+// factor, and what the recursion contracts is Hilbert's projective metric, so
+// they are compared by the spread of the component-wise ratios:
+//     max_j(a_j/t_j) / min_j(a_j/t_j) - 1 <= tol
+// (components that are negligible in both vectors are skipped).  A small
+// component matters as much as a large one here because the other pass
+// (beta for alpha, alpha for beta) may weight it up in the posterior.
+// Log-space vectors (Viterbi) are compared by the spread of the differences.
+// A bad chunk gets the true vector copied into its start slot for the repair.
 template <typename T>
 __global__ void verify_kernel(TehmmBatchDev b, int NP, T *start_vec, const T *end_vec,
-                              double tol_abs, double tol_rel, int dir, int *bad, int *nbad)
+                              double tol, int dir, int linear, int *bad, int *nbad,
+                              double *logkappa)
 {
     int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= b.nchunks) return;
     const TehmmChunk ch = b.chunks[ci];
     bool has = dir > 0 ? (ch.t0 > ch.s0) : (ch.t1 < ch.s1);
     int flag = 0;
+    double lk = 0.0;
     if (has) {
         const T *tv = end_vec + (ci - dir) * NP;
         T *sv = start_vec + ci * NP;
-        for (int j = 0; j < NP; ++j) {
-            double a = (double)sv[j], t = (double)tv[j];
-            if (a == t) continue;                       // covers equal infinities
-            double d = fabs(a - t);
-            if (!(d <= tol_abs + tol_rel * fabs(t))) flag = 1;   // NaN counts as bad
+        double lo = INFINITY, hi = -INFINITY;
+        if (linear) {
+            double ma = 0.0, mt = 0.0;
+            for (int j = 0; j < NP; ++j) { ma = fmax(ma, (double)sv[j]); mt = fmax(mt, (double)tv[j]); }
+            const double floor_rel = sizeof(T) == 4 ? 1e-30 : 1e-250;
+            for (int j = 0; j < NP; ++j) {
+                const double a = (double)sv[j], t = (double)tv[j];
+                const bool az = !(a > floor_rel * ma), tz = !(t > floor_rel * mt);
+                if (az && tz) continue;
+                if (az != tz) { flag = 1; break; }
+                const double r = a / t;
+                lo = fmin(lo, r); hi = fmax(hi, r);
+            }
+            if (!flag && hi > -INFINITY && !(hi / lo - 1.0 <= tol)) flag = 1;   // NaN counts as bad
+        } else {
+            for (int j = 0; j < NP; ++j) {
+                const double a = (double)sv[j], t = (double)tv[j];
+                const bool az = !(a > -1e30), tz = !(t > -1e30);
+                if (az && tz) continue;
+                if (az != tz) { flag = 1; break; }
+                const double d = a - t;
+                lo = fmin(lo, d); hi = fmax(hi, d);
+            }
+            if (!flag && hi > -INFINITY && !(hi - lo <= tol)) flag = 1;
         }
-        if (flag)
+        if (flag) {
             for (int j = 0; j < NP; ++j) sv[j] = tv[j];
+        } else if (linear && logkappa) {
+            // scale of the speculated vector relative to the true one (see forward_logprob_kernel)
+            double ss = 0.0, se = 0.0;
+            for (int j = 0; j < NP; ++j) { ss += (double)sv[j]; se += (double)tv[j]; }
+            lk = log(ss / se);
+        }
     }
     bad[ci] = flag;
+    if (logkappa) logkappa[ci] = lk;
     if (flag) atomicAdd(nbad, 1);
 }
 
 // logprob[seq] = sum of chunk scales + log(sum_j alpha_hat[T-1][j])
+//                - sum over chunk boundaries of log(kappa_c),
+// kappa_c = sum(start_vec[c]) / sum(end_vec[c-1]) (written by verify_kernel): a
+// chunk measures its scale relative to its own (speculated) start vector,
+// which points in the same direction as the previous chunk's end vector but
+// differs from it by an arbitrary factor in (1/2, 2).
 template <typename T>
 __global__ void forward_logprob_kernel(TehmmBatchDev b, int NP, const T *__restrict__ end_vec,
                                        const double *__restrict__ cscale,
+                                       const double *__restrict__ logkappa,
                                        double *__restrict__ logprob)
 {
     int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -214,7 +256,7 @@ __global__ void forward_logprob_kernel(TehmmBatchDev b, int NP, const T *__restr
     int64_t c0 = b.seq_chunk0[s], c1 = b.seq_chunk0[s + 1];
     if (c1 <= c0) { if (lane == 0) logprob[s] = 0.0; return; }
     double acc = 0.0;
-    for (int64_t c = c0 + lane; c < c1; c += 32) acc += cscale[c];
+    for (int64_t c = c0 + lane; c < c1; c += 32) acc += cscale[c] - logkappa[c];
     acc = warp_sum(acc);
     double tail = 0.0;
     for (int j = lane; j < NP; j += 32) tail += (double)end_vec[(c1 - 1) * NP + j];
@@ -249,28 +291,28 @@ cudaError_t tehmm_launch_forward(cudaStream_t st, const TehmmModelDev &m, const 
 }
 
 cudaError_t tehmm_launch_verify(cudaStream_t st, const TehmmBatchDev &b, int prec, int NP,
-                                void *start_vec, const void *end_vec, double tol_abs,
-                                double tol_rel, int dir, int *bad, int *nbad)
+                                void *start_vec, const void *end_vec, double tol, int dir,
+                                int linear, int *bad, int *nbad, double *logkappa)
 {
     cudaError_t e = cudaMemsetAsync(nbad, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     int grid = (int)((b.nchunks + 127) / 128);
     if (prec == TEHMM_F32)
-        verify_kernel<float><<<grid, 128, 0, st>>>(b, NP, (float *)start_vec, (const float *)end_vec, tol_abs, tol_rel, dir, bad, nbad);
+        verify_kernel<float><<<grid, 128, 0, st>>>(b, NP, (float *)start_vec, (const float *)end_vec, tol, dir, linear, bad, nbad, logkappa);
     else
-        verify_kernel<double><<<grid, 128, 0, st>>>(b, NP, (double *)start_vec, (const double *)end_vec, tol_abs, tol_rel, dir, bad, nbad);
+        verify_kernel<double><<<grid, 128, 0, st>>>(b, NP, (double *)start_vec, (const double *)end_vec, tol, dir, linear, bad, nbad, logkappa);
     return cudaGetLastError();
 }
 
 cudaError_t tehmm_launch_forward_logprob(cudaStream_t st, const TehmmBatchDev &b, int prec, int NP,
                                          const void *end_vec, const double *cscale,
-                                         double *logprob)
+                                         const double *logkappa, double *logprob)
 {
     int warps = 4;
     int grid = (int)((b.nseq + warps - 1) / warps);
     if (prec == TEHMM_F32)
-        forward_logprob_kernel<float><<<grid, warps * 32, 0, st>>>(b, NP, (const float *)end_vec, cscale, logprob);
+        forward_logprob_kernel<float><<<grid, warps * 32, 0, st>>>(b, NP, (const float *)end_vec, cscale, logkappa, logprob);
     else
-        forward_logprob_kernel<double><<<grid, warps * 32, 0, st>>>(b, NP, (const double *)end_vec, cscale, logprob);
+        forward_logprob_kernel<double><<<grid, warps * 32, 0, st>>>(b, NP, (const double *)end_vec, cscale, logkappa, logprob);
     return cudaGetLastError();
 }

@@ -165,24 +165,33 @@ class MultitrackHmm(BaseHMM):
     def _seg_ratios(self, obs):
         return self.emissionModel.getSegmentRatios(obs)
 
+    @staticmethod
+    def _gt(a, b):
+        """a > b with Python 2 ordering of None (None sorts below every number):
+        the reference compares against a best log-prob that starts out as None."""
+        if a is None:
+            return False
+        return True if b is None else a > b
+
     def _note_forward_logprob(self, lp):
         """Bookkeeping every forward pass does in the reference (hmm.py:688-713):
         running log-prob of the current iteration, --maxProb snapshots, --maxProbCut."""
         if self.last_forward_log_prob_it != self.current_iteration:
             if self.maxProb is True and (self.current_iteration == 1 or
-                                         self.last_forward_log_prob > self.best_forward_log_prob):
+                                         self._gt(self.last_forward_log_prob, self.best_forward_log_prob)):
                 self.best_forward_log_prob = self.last_forward_log_prob
                 self.bestCopy = copy.deepcopy(self)
             self.last_forward_log_prob = lp
             self.last_forward_log_prob_it = self.current_iteration
             if (self.maxProb is True and self.bestCopy is not None and self.maxProbCut is not None and
+                    self.current_iteration is not None and self.bestCopy.current_iteration is not None and
                     self.current_iteration - self.bestCopy.current_iteration > self.maxProbCut):
                 logger.info("Stopping due to --maxProbCut %d" % self.maxProbCut)
                 self.n_iter = self.current_iteration
         else:
             self.last_forward_log_prob += lp
             if self.maxProb is True and self.current_iteration > 1 and \
-                    self.last_forward_log_prob > self.best_forward_log_prob:
+                    self._gt(self.last_forward_log_prob, self.best_forward_log_prob):
                 self.best_forward_log_prob = self.last_forward_log_prob
                 self.bestCopy = copy.deepcopy(self)
 

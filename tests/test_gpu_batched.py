@@ -203,6 +203,7 @@ def test_f32_vs_f64_at_scale():
     eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
     eng.upload_batch([obs])
     a = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f64")
+    before = {k: eng.ctx.stat("repaired_chunks_" + k) for k in ("forward", "backward", "viterbi")}
     b = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f32")
     assert b["logprob"][0] == pytest.approx(a["logprob"][0], rel=1e-7)
     assert np.mean(a["map_states"][0] == b["map_states"][0]) > 0.9995
@@ -215,3 +216,7 @@ def test_f32_vs_f64_at_scale():
     assert st["obs"].sum() == pytest.approx(T * m["K"], rel=1e-6)
     assert st["trans"].sum() * m["N"] == pytest.approx(T - 1, rel=1e-6)
     assert st["start"].sum() == pytest.approx(1.0, rel=1e-6)
+    # the speculative warm-up must be good enough that (almost) nothing is repaired
+    nchunks = eng.ctx.stat("chunks")
+    for k in before:
+        assert eng.ctx.stat("repaired_chunks_" + k) - before[k] <= 0.02 * nchunks, k
