@@ -422,7 +422,7 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
     // time partition: tiles of TEHMM_TILE steps, chunks of `tpc` tiles
     int64_t tpc = c->opt_chunk_tiles;
     if (tpc <= 0) {
-        const int64_t target = (int64_t)c->sms * 32;          // one chunk per resident warp
+        const int64_t target = (int64_t)c->sms * 24;          // one chunk per resident warp (3 CTAs of 8 warps per SM)
         tpc = (total + target * TEHMM_TILE - 1) / (target * TEHMM_TILE);
         tpc = std::max<int64_t>(4, std::min<int64_t>(tpc, 2048));
     }
@@ -530,7 +530,7 @@ int64_t tehmm_scratch_bytes(tehmm_ctx *c, int prec)
 static int scan_grid(const tehmm_ctx *c)
 {
     int64_t need = (c->b.nchunks + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
-    int64_t cap = (int64_t)c->sms * 8;
+    int64_t cap = (int64_t)c->sms * 3;      // resident CTAs of the scan kernels (80 registers, 8 warps)
     return (int)std::max<int64_t>(1, std::min(need, cap));
 }
 

@@ -20,7 +20,7 @@
 #define BWD_U 4
 
 template <typename T, int NS, bool RATIO, bool TRANS>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1 && !TRANS) ? 3 : 1)
 backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict__ blin,
                 const T *__restrict__ alpha, const double *__restrict__ ratios,
                 T *__restrict__ post, uint8_t *__restrict__ map_states,
@@ -206,17 +206,27 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
                 }
                 if (want_map) {
                     // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
-                    T best = g[0];
-                    int arg = lane;
+                    T best;
+                    int arg;
+                    if (sizeof(T) == 4 && NS == 1) {
+                        // posteriors are >= 0: their bit patterns order like the values
+                        const unsigned bits = lane < N ? __float_as_uint((float)g[0]) : 0u;
+                        const unsigned mx = __reduce_max_sync(TEHMM_FULL, bits);
+                        arg = __ffs(__ballot_sync(TEHMM_FULL, bits == mx)) - 1;
+                        best = (T)__uint_as_float(mx);
+                    } else {
+                        best = g[0];
+                        arg = lane;
 #pragma unroll
-                    for (int s = 1; s < NS; ++s)
-                        if (g[s] > best) { best = g[s]; arg = lane + 32 * s; }
-                    if (arg >= N) best = (T)-1;
+                        for (int s = 1; s < NS; ++s)
+                            if (g[s] > best) { best = g[s]; arg = lane + 32 * s; }
+                        if (arg >= N) best = (T)-1;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        T ob = __shfl_xor_sync(TEHMM_FULL, best, o);
-                        int oa = __shfl_xor_sync(TEHMM_FULL, arg, o);
-                        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                        for (int o = 16; o > 0; o >>= 1) {
+                            T ob = __shfl_xor_sync(TEHMM_FULL, best, o);
+                            int oa = __shfl_xor_sync(TEHMM_FULL, arg, o);
+                            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                        }
                     }
                     if (lane == 0) {
                         map_states[tc] = (uint8_t)arg;

@@ -17,8 +17,54 @@
 // ((tab_off[k] + symbol) * N), so the inner loop is one broadcast LDS of the
 // offset and one conflict-free LDS.64 of the table entry per (row, track).
 // A symbol outside the compact table is staged as -(1 + k*S + symbol) and read
-// from the dense table exactly as the reference indexes it.
-template <typename T, typename OBS, int MODE, int NS>
+// from the dense table exactly as the reference indexes it (rare, per-row vote).
+// Two rows are in flight per iteration: the sum over tracks must stay
+// sequential (bit-exact against the reference), so the ILP comes from rows.
+template <typename T, int MODE, int NS>
+__device__ __forceinline__ void em_finish_row(const TehmmModelDev &m, int64_t t, double (&v)[NS],
+                                              const double *__restrict__ ratios, T *elog, T *blin,
+                                              double *rowmax, double *frame, int *seq_flag,
+                                              const int64_t *seq_off, int64_t nseq, int lane)
+{
+    const int N = m.N;
+    double vmax = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        v[s] *= m.normalize;
+        if (ratios) v[s] *= ratios[t];
+        if (lane + 32 * s < N) vmax = fmax(vmax, v[s]); else v[s] = -INFINITY;
+    }
+    // row maximum: float REDUX first; exact double fallback when it overflows fp32
+    float mf = warp_max_any((float)vmax);
+    double M = (double)mf;
+    if (!(mf > (float)TEHMM_MINDBL)) {
+        M = warp_max(vmax);
+        // candidate for the "no state can emit" quirk (_emission.pyx:73-80)
+        if (!(M > TEHMM_MINDBL) && seq_flag && lane == 0) {
+            int64_t lo = 0, hi = nseq;   // sequence of row t
+            while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
+            seq_flag[lo] = 1;
+        }
+    }
+    if (MODE == 1) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (lane + 32 * s < N) frame[t * N + lane + 32 * s] = v[s];
+        return;
+    }
+    if (lane == 0) rowmax[t] = M;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int j = lane + 32 * s;
+        if (j < N) {
+            const double d = (M > -INFINITY) ? v[s] - M : 0.0;
+            if (elog) elog[t * N + j] = (T)d;
+            if (blin) blin[t * N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
+        }
+    }
+}
+
+template <typename T, typename OBS, int MODE, int NS, bool SMEM>
 __global__ void __launch_bounds__(EM_WARPS * 32, 2)
 emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                 const double *__restrict__ ratios, T *__restrict__ elog, T *__restrict__ blin,
@@ -39,13 +85,33 @@ emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
         offs[k] = m.tab_off[k];
         nsyms[k] = m.track_nsym[k];
     }
-    const double *tab = m.table_t;
-    if (m.table_in_smem) {
+    if (SMEM) {
         int64_t n = (int64_t)m.tab_rows * N;
         for (int64_t e = threadIdx.x; e < n; e += blockDim.x) tab_s[e] = m.table_t[e];
-        tab = tab_s;
     }
     __syncthreads();
+    const double *__restrict__ tab_g = m.table_t;
+
+    auto entry = [&](int o, int j) -> double {
+        if (SMEM) return tab_s[o + j];
+        return tab_g[o + j];
+    };
+    auto slow_row = [&](const int *so, double (&v)[NS]) {
+        for (int k = 0; k < K; ++k) {
+            const int o = so[k];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int j = lane + 32 * s;
+                if (j < N) {
+                    if (o >= 0) v[s] += entry(o, j);
+                    else {
+                        const int code = -o - 1;
+                        v[s] += m.table[((int64_t)(code / m.S) * N + j) * m.S + code % m.S];
+                    }
+                }
+            }
+        }
+    };
 
     int *stage = stage_all + warp * EM_ROWS * K;
     const int64_t nblocks = (total + EM_ROWS - 1) / EM_ROWS;
@@ -54,69 +120,43 @@ emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
         const int64_t tb = blk * EM_ROWS;
         const int rows = (int)min((int64_t)EM_ROWS, total - tb);
         __syncwarp();
+        bool neg = false;
         for (int e = lane; e < rows * K; e += 32) {
             const int sym = (int)obs[tb * K + e];
             const int k = e % K;
-            stage[e] = sym < nsyms[k] ? (offs[k] + sym) * N : -(1 + k * m.S + sym);
+            const int o = sym < nsyms[k] ? (offs[k] + sym) * N : -(1 + k * m.S + sym);
+            neg |= o < 0;
+            stage[e] = o;
         }
+        const bool any_slow = __any_sync(TEHMM_FULL, neg);
         __syncwarp();
-        for (int r = 0; r < rows; ++r) {
-            const int64_t t = tb + r;
-            const int *so = stage + r * K;
+        // lanes beyond N read a valid (clamped) column and are discarded later
+        int jc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) jc[s] = min(lane + 32 * s, N - 1);
+        int r = 0;
+        if (!any_slow) {
+            for (; r + 1 < rows; r += 2) {
+                const int *so0 = stage + r * K, *so1 = so0 + K;
+                double v0[NS], v1[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) { v0[s] = 0.0; v1[s] = 0.0; }
+#pragma unroll 5
+                for (int k = 0; k < K; ++k) {
+                    const int o0 = so0[k], o1 = so1[k];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) { v0[s] += entry(o0, jc[s]); v1[s] += entry(o1, jc[s]); }
+                }
+                em_finish_row<T, MODE, NS>(m, tb + r, v0, ratios, elog, blin, rowmax, frame, seq_flag, seq_off, nseq, lane);
+                em_finish_row<T, MODE, NS>(m, tb + r + 1, v1, ratios, elog, blin, rowmax, frame, seq_flag, seq_off, nseq, lane);
+            }
+        }
+        for (; r < rows; ++r) {
             double v[NS];
 #pragma unroll
             for (int s = 0; s < NS; ++s) v[s] = 0.0;
-#pragma unroll 5
-            for (int k = 0; k < K; ++k) {
-                const int o = so[k];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const int j = lane + 32 * s;
-                    if (j < N) {
-                        if (o >= 0) {
-                            v[s] += tab[o + j];
-                        } else {
-                            const int code = -o - 1;
-                            v[s] += m.table[((int64_t)(code / m.S) * N + j) * m.S + code % m.S];
-                        }
-                    }
-                }
-            }
-            double vmax = -INFINITY;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                v[s] *= m.normalize;
-                if (ratios) v[s] *= ratios[t];
-                if (lane + 32 * s < N) vmax = fmax(vmax, v[s]); else v[s] = -INFINITY;
-            }
-            // row maximum: float REDUX first; exact double fallback when it overflows fp32
-            float mf = warp_max_any((float)vmax);
-            double M = (double)mf;
-            if (!(mf > (float)TEHMM_MINDBL)) {
-                M = warp_max(vmax);
-                // candidate for the "no state can emit" quirk (_emission.pyx:73-80)
-                if (!(M > TEHMM_MINDBL) && seq_flag && lane == 0) {
-                    int64_t lo = 0, hi = nseq;   // sequence of row t
-                    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
-                    seq_flag[lo] = 1;
-                }
-            }
-            if (MODE == 1) {
-#pragma unroll
-                for (int s = 0; s < NS; ++s)
-                    if (lane + 32 * s < N) frame[t * N + lane + 32 * s] = v[s];
-                continue;
-            }
-            if (lane == 0) rowmax[t] = M;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int j = lane + 32 * s;
-                if (j < N) {
-                    const double d = (M > -INFINITY) ? v[s] - M : 0.0;
-                    if (elog) elog[t * N + j] = (T)d;
-                    if (blin) blin[t * N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
-                }
-            }
+            slow_row(stage + r * K, v);
+            em_finish_row<T, MODE, NS>(m, tb + r, v, ratios, elog, blin, rowmax, frame, seq_flag, seq_off, nseq, lane);
         }
     }
 }
@@ -171,7 +211,7 @@ static cudaError_t launch_em_ns(cudaStream_t st, const TehmmModelDev &m, const T
                                 double *frame, int *seq_flag, int sms)
 {
     size_t smem = em_smem_bytes(m);
-    auto kern = emission_kernel<T, OBS, MODE, NS>;
+    auto kern = m.table_in_smem ? emission_kernel<T, OBS, MODE, NS, true> : emission_kernel<T, OBS, MODE, NS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = smem > 112 * 1024 ? 1 : 2;

@@ -20,7 +20,7 @@
 #define FWD_U 4   // register prefetch depth (time steps)
 
 template <typename T, int NS, bool RATIO>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
 forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
                const double *__restrict__ rowmax, const double *__restrict__ ratios,
                T *__restrict__ alpha, T *__restrict__ start_vec, T *__restrict__ end_vec,

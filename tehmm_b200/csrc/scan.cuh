@@ -94,6 +94,148 @@ __device__ __forceinline__ void matvec_sum_keep(const T *xs, const T (&c)[NS][32
     for (int s = 0; s < NS; ++s) y[s] = (acc[s][0] + acc[s][1]) + (acc[s][2] + acc[s][3]);
 }
 
+// ---- Blackwell packed fp32 pairs (FFMA2 / FADD2, sm_100+) and 3-input max (FMNMX3)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi)
+{
+    return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo);
+}
+__device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Lane-owned slice of the (padded) transition matrix: column j (forward,
+// Viterbi) or row i (backward) for each owned state.  float: packed pairs.
+template <typename T, int NS> struct MatSlice {
+    T c[NS][32 * NS];
+    __device__ __forceinline__ void set(int s, int i, T v) { c[s][i] = v; }
+};
+template <int NS> struct MatSlice<float, NS> {
+    u64 c[NS][16 * NS];
+    float tmp;
+    __device__ __forceinline__ void set(int s, int i, float v)
+    {
+        if (i & 1) c[s][i >> 1] = pk2(tmp, v); else tmp = v;
+    }
+};
+
+// y[s] = sum_i xs[i] * M[s][i]
+template <int NS>
+__device__ __forceinline__ void matvec_sum(const float *xs, const MatSlice<float, NS> &M, float (&y)[NS])
+{
+    constexpr int NP = 32 * NS;
+    u64 a[NS][4];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s][0] = a[s][1] = a[s][2] = a[s][3] = 0ull;
+#pragma unroll
+    for (int i = 0; i < NP; i += 8) {
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(xs + i);
+        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(xs + i + 4);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            a[s][0] = ffma2(x0.x, M.c[s][i / 2 + 0], a[s][0]);
+            a[s][1] = ffma2(x0.y, M.c[s][i / 2 + 1], a[s][1]);
+            a[s][2] = ffma2(x1.x, M.c[s][i / 2 + 2], a[s][2]);
+            a[s][3] = ffma2(x1.y, M.c[s][i / 2 + 3], a[s][3]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const u64 t = fadd2(fadd2(a[s][0], a[s][1]), fadd2(a[s][2], a[s][3]));
+        y[s] = lo2(t) + hi2(t);
+    }
+}
+template <int NS>
+__device__ __forceinline__ void matvec_sum(const double *xs, const MatSlice<double, NS> &M, double (&y)[NS])
+{
+    matvec_sum<double, NS>(xs, M.c, y);
+}
+
+// same, keeping the broadcast vector in registers (packed for float) for a second use
+template <int NS>
+__device__ __forceinline__ void matvec_sum_keep(const float *xs, const MatSlice<float, NS> &M,
+                                                float (&y)[NS], u64 (&xv)[16 * NS])
+{
+    constexpr int NP = 32 * NS;
+    u64 a[NS][4];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s][0] = a[s][1] = a[s][2] = a[s][3] = 0ull;
+#pragma unroll
+    for (int i = 0; i < NP; i += 8) {
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(xs + i);
+        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(xs + i + 4);
+        xv[i / 2] = x0.x; xv[i / 2 + 1] = x0.y; xv[i / 2 + 2] = x1.x; xv[i / 2 + 3] = x1.y;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            a[s][0] = ffma2(x0.x, M.c[s][i / 2 + 0], a[s][0]);
+            a[s][1] = ffma2(x0.y, M.c[s][i / 2 + 1], a[s][1]);
+            a[s][2] = ffma2(x1.x, M.c[s][i / 2 + 2], a[s][2]);
+            a[s][3] = ffma2(x1.y, M.c[s][i / 2 + 3], a[s][3]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const u64 t = fadd2(fadd2(a[s][0], a[s][1]), fadd2(a[s][2], a[s][3]));
+        y[s] = lo2(t) + hi2(t);
+    }
+}
+
+// m[s] = max_i (xs[i] + M[s][i])   ((max,+) semiring, value only)
+template <int NS>
+__device__ __forceinline__ void matvec_maxval(const float *xs, const MatSlice<float, NS> &M, float (&m)[NS])
+{
+    constexpr int NP = 32 * NS;
+    float a[NS][2];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a[s][0] = a[s][1] = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NP; i += 4) {
+        const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(xs + i);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const u64 c0 = fadd2(x.x, M.c[s][i / 2]), c1 = fadd2(x.y, M.c[s][i / 2 + 1]);
+            a[s][0] = fmax3(a[s][0], lo2(c0), hi2(c0));
+            a[s][1] = fmax3(a[s][1], lo2(c1), hi2(c1));
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) m[s] = fmaxf(a[s][0], a[s][1]);
+}
+template <int NS>
+__device__ __forceinline__ void matvec_maxval(const double *xs, const MatSlice<double, NS> &M, double (&m)[NS])
+{
+    constexpr int NP = 32 * NS;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) m[s] = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NP; i += 4) {
+        Vec4<double> x;
+        x.load(xs + i);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[s] = fmax(m[s], x.v[q] + M.c[s][i + q]);
+        }
+    }
+}
+
 // (max,+) semiring with the reference's tie rule: strict '>' scanning the
 // from-state upward, so the lowest from-state wins (_hmm.pyx:232-247).
 // extra0[s] is added to the from-state-0 candidate only (segment quirk).
@@ -125,28 +267,35 @@ __device__ __forceinline__ void matvec_max(const T *xs, const T (&c)[NS][32 * NS
 
 // Scale a non-negative vector by a power of two so that its largest element
 // lies in [1,2).  Exact (no rounding), hence independent of scaling history.
-// Returns the exponent taken out: raw = canonical * 2^shift.
+// Returns the exponent taken out: raw = scaled * 2^shift.
+template <typename T, int NS> __device__ __noinline__ int canonicalise_rare(T (&x)[NS], bool any_pos)
+{
+    // all zero (impossible data), subnormal, inf or nan
+    if (!any_pos) return 0;
+    T m = x[0];
+#pragma unroll
+    for (int s = 1; s < NS; ++s) m = x[s] > m ? x[s] : m;
+    const bool big = __any_sync(TEHMM_FULL, !(m < (T)INFINITY));
+    if (big) return 0;
+    // subnormal maximum: lift by 2^64 and let the next step finish the job
+    const T up = TehmmNum<T>::inv_scale(TehmmNum<T>::BIAS - 64);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) x[s] *= up;
+    return -64;
+}
 template <typename T, int NS> __device__ __forceinline__ int canonicalise(T (&x)[NS])
 {
     T m = x[0];
 #pragma unroll
     for (int s = 1; s < NS; ++s) m = x[s] > m ? x[s] : m;
-    unsigned mb = __reduce_max_sync(TEHMM_FULL, TehmmNum<T>::order_bits(m));
-    int e = sizeof(T) == 4 ? (int)(mb >> 23) : (int)(mb >> 20);
-    if (e == 0) {
-        // all zero (impossible data) or subnormal: lift by 2^64 and let the
-        // next step finish the job
-        if (!__any_sync(TEHMM_FULL, m > (T)0)) return 0;
-        T up = TehmmNum<T>::inv_scale(TehmmNum<T>::BIAS - 64);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) x[s] *= up;
-        return -64;
-    }
-    if (e > TehmmNum<T>::EMAX) return 0;   // inf / nan: leave alone
-    T sc = TehmmNum<T>::inv_scale(e);
+    const unsigned mb = __reduce_max_sync(TEHMM_FULL, TehmmNum<T>::order_bits(m));
+    const unsigned e = sizeof(T) == 4 ? (mb >> 23) : (mb >> 20);
+    if (__builtin_expect(e - 1u >= (unsigned)TehmmNum<T>::EMAX, 0))
+        return canonicalise_rare<T, NS>(x, __any_sync(TEHMM_FULL, m > (T)0));
+    const T sc = TehmmNum<T>::inv_scale((int)e);
 #pragma unroll
     for (int s = 0; s < NS; ++s) x[s] *= sc;
-    return e - TehmmNum<T>::BIAS;
+    return (int)e - TehmmNum<T>::BIAS;
 }
 
 // warp-wide maximum of arbitrary-sign values

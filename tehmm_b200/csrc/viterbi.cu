@@ -24,7 +24,7 @@
 #define VIT_U 4
 
 template <typename T, int NS, bool RATIO>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
 viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
                const double *__restrict__ ratios, uint8_t *__restrict__ bp,
                uint8_t *__restrict__ tilemap, T *__restrict__ start_vec,
