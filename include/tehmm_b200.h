@@ -182,13 +182,16 @@ int tehmm_run_emission_stats(tehmm_ctx *ctx, int prec, const void *d_post,
                              int stats_S, void *d_scratch);
 
 /* Viterbi with traceback (hmm.py:668-676 -> _hmm.pyx:201-259).
- * d_states total uint8 (or d_states64 total int64, either may be NULL),
- * d_logprob nseq float64 (fp64 re-score of the returned path).
- * d_bp: workspace of tehmm_viterbi_bp_bytes().                              */
-int64_t tehmm_viterbi_bp_bytes(tehmm_ctx *ctx);
+ * d_states total uint8 (required), d_states64 total int64 (optional, NULL to
+ * skip), d_logprob nseq float64 (fp64 re-score of the returned path).
+ * d_lattice: workspace of tehmm_viterbi_workspace_bytes() for the delta lattice.
+ * d_ratios_emission: the ratios the emission was computed with (only used by
+ * the re-score); d_ratios_dp: the ratios the DP applies (basehmm.py:327 vs
+ * hmm.py:674 use different ones).                                            */
+int64_t tehmm_viterbi_workspace_bytes(tehmm_ctx *ctx, int prec);
 int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
                       const double *d_ratios_emission, const double *d_ratios_dp,
-                      void *d_bp, uint8_t *d_states, int64_t *d_states64,
+                      void *d_lattice, uint8_t *d_states, int64_t *d_states64,
                       double *d_logprob, void *d_scratch);
 
 /* widen / convert on the device before a D2H copy */

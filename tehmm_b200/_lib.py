@@ -54,7 +54,7 @@ SIGNATURES = {
     "tehmm_run_forward": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_run_backward": (_c_int, [_c_void, _c_int, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_run_emission_stats": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_int, _c_void]),
-    "tehmm_viterbi_bp_bytes": (_c_i64, [_c_void]),
+    "tehmm_viterbi_workspace_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_widen_states": (_c_int, [_c_void, _c_void, _c_void, _c_i64]),
     "tehmm_convert_lattice": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_i64]),

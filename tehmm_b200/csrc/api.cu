@@ -25,8 +25,10 @@ cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, in
 cudaError_t tehmm_launch_backward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, int, const void *, const void *, const double *, void *, uint8_t *, double *, void *, void *, void *, void *, void *, const int *, int, int);
 cudaError_t tehmm_launch_trans_reduce(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const void *, const void *, double *);
 cudaError_t tehmm_launch_map_reduce(cudaStream_t, const TehmmBatchDev &, const double *, double *);
-cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, uint8_t *, uint8_t *, void *, void *, const int *, int, int);
-cudaError_t tehmm_launch_traceback(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const uint8_t *, const uint8_t *, uint8_t *, uint8_t *, uint8_t *, int64_t *, const double *, const double *, double *, double *, int, int);
+cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, void *, void *, void *, const int *, int, int);
+cudaError_t tehmm_launch_traceback(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, uint8_t *, int64_t *, uint8_t *, uint8_t *, const uint8_t *, const int *, int, int);
+cudaError_t tehmm_launch_tb_verify(cudaStream_t, const TehmmBatchDev &, uint8_t *, const uint8_t *, uint8_t *, int *, int *);
+cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const uint8_t *, const double *, const double *, double *, double *);
 cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, double *, double *, int, int);
 size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
 cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
@@ -67,7 +69,7 @@ struct tehmm_ctx {
     int64_t launches = 0;
     int64_t opt_chunk_tiles = 0, opt_warmup = 0, opt_max_repair = 0;
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
-    int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0;
+    int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0, stat_bad_tb = 0, stat_repair_tb = 0;
     int *h_nbad = nullptr;            // pinned
     // model
     bool has_model = false;
@@ -167,6 +169,8 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "repaired_chunks_forward")) return c->stat_bad_fwd;
     if (!strcmp(name, "repaired_chunks_backward")) return c->stat_bad_bwd;
     if (!strcmp(name, "repaired_chunks_viterbi")) return c->stat_bad_vit;
+    if (!strcmp(name, "repaired_chunks_traceback")) return c->stat_bad_tb;
+    if (!strcmp(name, "repair_passes_traceback")) return c->stat_repair_tb;
     if (!strcmp(name, "sms")) return c->sms;
     if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
     if (!strcmp(name, "warmup")) return c->has_batch ? c->b.warmup : 0;
@@ -471,10 +475,10 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
 
 int64_t tehmm_batch_total(tehmm_ctx *c) { return c && c->has_batch ? c->b.total : 0; }
 int64_t tehmm_batch_chunks(tehmm_ctx *c) { return c && c->has_batch ? c->b.nchunks : 0; }
-int64_t tehmm_viterbi_bp_bytes(tehmm_ctx *c)
+int64_t tehmm_viterbi_workspace_bytes(tehmm_ctx *c, int prec)
 {
     if (!c || !c->has_batch || !c->has_model) return 0;
-    return c->b.total * (int64_t)c->m.NP;
+    return c->b.total * (int64_t)c->m.N * (prec == TEHMM_F32 ? 4 : 8);   // the delta lattice
 }
 
 // scratch carving shared by tehmm_scratch_bytes and the run_* entry points
@@ -665,23 +669,23 @@ int tehmm_run_emission_stats(tehmm_ctx *c, int prec, const void *d_post, const d
 }
 
 int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *d_ratios_emission,
-                      const double *d_ratios_dp, void *d_bp, uint8_t *d_states,
+                      const double *d_ratios_dp, void *d_lattice, uint8_t *d_states,
                       int64_t *d_states64, double *d_logprob, void *d_scratch)
 {
     RUN_PROLOGUE();
-    if (!d_elog || !d_bp || !d_states || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument (d_states is required; d_states64 is optional)");
+    if (!d_elog || !d_lattice || !d_states || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument (d_states is required; d_states64 is optional)");
     const Scratch s = carve(c, prec);
     char *w = (char *)d_scratch;
     void *sv = w + s.start_vec, *ev = w + s.end_vec;
     double *sp = (double *)(w + s.part_a);
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
-    uint8_t *tilemap = (uint8_t *)(w + s.tilemap), *cmap = (uint8_t *)(w + s.cmap), *cend = (uint8_t *)(w + s.chunk_end);
+    uint8_t *spec_end = (uint8_t *)(w + s.cmap), *pred = spec_end + c->b.nchunks, *forced = pred + c->b.nchunks;
     const int grid = scan_grid(c);
-    CU(cudaMemsetAsync(tilemap, 0, (size_t)c->b.ntiles * c->m.NP, st));
-    CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, (uint8_t *)d_bp, tilemap, sv, ev, bad, 0, grid));
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    // ---- DP: delta lattice, chunk starts speculated / verified / repaired
+    CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid));
     c->launches += 1;
     const double tol = tolerance(prec, true);
-    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, +1, 0, bad, nbad, nullptr));
         c->launches += 1;
@@ -691,12 +695,27 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
         c->stat_repair_vit += 1; c->stat_bad_vit += nb;
-        CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, (uint8_t *)d_bp, tilemap, sv, ev, bad, 1, grid));
+        CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 1, grid));
         c->launches += 1;
     }
-    CU(tehmm_launch_traceback(st, c->m, c->b, prec, ev, (const uint8_t *)d_bp, tilemap, cmap, cend, d_states, d_states64,
-                              d_ratios_emission, d_ratios_dp, sp, d_logprob, (int)c->max_tiles_per_chunk, grid));
-    c->launches += 5;
+    // ---- traceback: chunk end states speculated / verified / repaired
+    CU(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)c->b.nchunks, st));
+    CU(tehmm_launch_traceback(st, c->m, c->b, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 0, grid));
+    c->launches += 1;
+    for (int64_t pass = 0;; ++pass) {
+        CU(tehmm_launch_tb_verify(st, c->b, spec_end, pred, forced, bad, nbad));
+        c->launches += 1;
+        int nb = 0;
+        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (pass == 0) adapt_warmup(c, nb);
+        if (nb == 0) break;
+        if (pass >= max_pass) return fail(TEHMM_ESTATE, "traceback repair did not converge (%d chunks left)", nb);
+        c->stat_repair_tb += 1; c->stat_bad_tb += nb;
+        CU(tehmm_launch_traceback(st, c->m, c->b, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, grid));
+        c->launches += 1;
+    }
+    CU(tehmm_launch_rescore(st, c->m, c->b, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));
+    c->launches += 2;
     return TEHMM_OK;
 }
 

@@ -16,8 +16,66 @@
 // Algorithmic HBM bytes per step (fp32): 4N (b) + 4N (alpha) read,
 // + 4N written when posteriors are requested, + 1 for MAP states.
 #include "scan.cuh"
+#include <type_traits>
 
 #define BWD_U 4
+
+// xi accumulators: NP per owned state; packed pairs for float
+template <typename T, int NS> struct XiAcc {
+    T a[NS][32 * NS];
+    T w[32 * NS];       // broadcast vector kept from the mat-vec
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int j = 0; j < 32 * NS; ++j) a[s][j] = (T)0;
+    }
+    __device__ __forceinline__ void matvec(const T *ws, const MatSlice<T, NS> &A, T (&bp)[NS])
+    {
+        matvec_sum_keep<T, NS>(ws, A.c, bp, w);
+    }
+    __device__ __forceinline__ void add(int s, T q)
+    {
+#pragma unroll
+        for (int j = 0; j < 32 * NS; ++j) a[s][j] = fma(q, w[j], a[s][j]);
+    }
+    __device__ __forceinline__ void store(int s, T *dst) const
+    {
+#pragma unroll
+        for (int j = 0; j < 32 * NS; ++j) dst[j] = a[s][j];
+    }
+};
+template <int NS> struct XiAcc<float, NS> {
+    u64 a[NS][16 * NS];
+    u64 w[16 * NS];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int j = 0; j < 16 * NS; ++j) a[s][j] = 0ull;
+    }
+    __device__ __forceinline__ void matvec(const float *ws, const MatSlice<float, NS> &A, float (&bp)[NS])
+    {
+        matvec_sum_keep<NS>(ws, A, bp, w);
+    }
+    __device__ __forceinline__ void add(int s, float q)
+    {
+        const u64 q2 = pk2(q, q);
+#pragma unroll
+        for (int j = 0; j < 16 * NS; ++j) a[s][j] = ffma2(q2, w[j], a[s][j]);
+    }
+    __device__ __forceinline__ void store(int s, float *dst) const
+    {
+#pragma unroll
+        for (int j = 0; j < 16 * NS; j += 2)
+            *reinterpret_cast<ulonglong2 *>(dst + 2 * j) = make_ulonglong2(a[s][j], a[s][j + 1]);
+    }
+};
+template <typename T, int NS> struct XiNone {
+    __device__ __forceinline__ void zero() {}
+};
 
 template <typename T, int NS, bool RATIO, bool TRANS>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1 && !TRANS) ? 3 : 1)
@@ -33,48 +91,54 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*ws)[NP] = ws_all[warp];
     const int N = m.N;
+    const unsigned Nu = (unsigned)N;
     const bool want_post = (flags & TEHMM_BWD_POSTERIORS) != 0;
     const bool want_map = (flags & TEHMM_BWD_MAP) != 0;
     const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
     const double eps32 = 1.1920928955078125e-07;
     const double renorm_den = 1.0 + (double)N * eps32;
 
-    // row i of the transition matrix for each owned state
-    T c[NS][NP];
+    // row i of the transition matrix for each owned state (zero beyond N)
+    MatSlice<T, NS> A;
     double dg[NS];
+    unsigned jc[NS];
+    bool own[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        int i = lane + 32 * s;
+        const int i = lane + 32 * s;
 #pragma unroll
-        for (int j = 0; j < NP; ++j) c[s][j] = (T)m.lin_trans[(int64_t)i * NP + j];
+        for (int j = 0; j < NP; ++j) A.set(s, j, (T)m.lin_trans[(int64_t)i * NP + j]);
         dg[s] = RATIO ? m.cut_trans[(int64_t)i * NP + i] : 0.0;
+        own[s] = i < N;
+        jc[s] = (unsigned)min(i, N - 1);
     }
 
     for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
          ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
         if (mode == 1 && !bad[ci]) continue;
         const TehmmChunk ch = b.chunks[ci];
-        T u[NS];                 // canonical beta_hat at the step last processed
+        T u[NS];                 // scaled beta_hat at the step last processed
         int buf = 0;
-        T xi[TRANS ? NS : 1][TRANS ? NP : 1];
+        typename std::conditional<TRANS, XiAcc<T, NS>, XiNone<T, NS>>::type xi;
+        xi.zero();
         T xd[NS];
-        if (TRANS) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                xd[s] = (T)0;
-#pragma unroll
-                for (int j = 0; j < NP; ++j) xi[s][j] = (T)0;
-            }
-        }
+        for (int s = 0; s < NS; ++s) xd[s] = (T)0;
         double mapsum = 0.0;
 
-        // w_{t+1} = b_{t+1} .* u [.* g_{t+1}] -> smem ; returns beta'_t (unnormalised)
-        auto beta_step = [&](int64_t t, const T (&bt1)[NS], T (&bp)[NS], T (&wv)[NP], bool keep) {
+        // rows are addressed relative to t0 with 32-bit offsets
+        const T *__restrict__ bb = blin + ch.t0 * N;
+        const T *__restrict__ aa = alpha + ch.t0 * N;
+        const double *__restrict__ rr = RATIO ? ratios + ch.t0 : nullptr;
+
+        // w_{t+1} = b_{t+1} .* u [.* g_{t+1}] -> smem ; bp = beta'_t (unscaled).
+        // `row1` is the row of t+1 relative to t0.
+        auto beta_step = [&](unsigned row1, const T (&bt1)[NS], T (&bp)[NS]) {
             T w[NS];
 #pragma unroll
             for (int s = 0; s < NS; ++s) w[s] = bt1[s] * u[s];
             if (RATIO) {
-                double r = ratios[t + 1];
+                const double r = rr[row1];
                 if (r > 1.0) {
                     double lg[NS], mg = -INFINITY;
 #pragma unroll
@@ -87,29 +151,50 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
 #pragma unroll
             for (int s = 0; s < NS; ++s) ws[buf][lane + 32 * s] = w[s];
             __syncwarp();
-            if (keep) matvec_sum_keep<T, NS>(ws[buf], c, bp, wv);
-            else matvec_sum<T, NS>(ws[buf], c, bp);
+            if constexpr (TRANS) xi.matvec(ws[buf], A, bp);
+            else matvec_sum<NS>(ws[buf], A, bp);
             buf ^= 1;
         };
-        auto load_row = [&](const T *src, int64_t t, T (&v)[NS]) {
+        auto load_row = [&](const T *base, unsigned row, T (&v)[NS]) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                int j = lane + 32 * s;
-                v[s] = j < N ? src[t * N + j] : (T)0;
-            }
+            for (int s = 0; s < NS; ++s) v[s] = base[row * Nu + jc[s]];
         };
+
+        const unsigned nrows = (unsigned)(ch.t1 - ch.t0);
+        const unsigned last_row = (unsigned)(ch.s1 - 1 - ch.t0);    // row of the sequence's last step
 
         // ---- phase A: beta_hat at t1 (speculated), unless the chunk ends its sequence
         if (ch.t1 < ch.s1) {
             if (mode == 0) {
-                int64_t tq = ch.t1 + b.warmup;
-                if (tq > ch.s1 - 1) tq = ch.s1 - 1;
+                unsigned rq = nrows + (unsigned)b.warmup;           // row of tq = t1 + warmup
+                if (rq > last_row) rq = last_row;
 #pragma unroll
-                for (int s = 0; s < NS; ++s) u[s] = (lane + 32 * s) < N ? (T)1 : (T)0;
-                for (int64_t t = tq - 1; t >= ch.t1; --t) {
-                    T bt1[NS], bp[NS], dummy[NP];
-                    load_row(blin, t + 1, bt1);
-                    beta_step(t, bt1, bp, dummy, false);
+                for (int s = 0; s < NS; ++s) u[s] = own[s] ? (T)1 : (T)0;
+                for (unsigned r1 = rq; r1 > nrows; --r1) {          // computes beta at row r1-1 >= nrows
+                    T bt1[NS], bp[NS];
+                    load_row(bb, r1, bt1);
+                    // warm-up never accumulates statistics: plain mat-vec
+                    {
+                        T w[NS];
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) w[s] = bt1[s] * u[s];
+                        if (RATIO) {
+                            const double r = rr[r1];
+                            if (r > 1.0) {
+                                double lg[NS], mg = -INFINITY;
+#pragma unroll
+                                for (int s = 0; s < NS; ++s) { lg[s] = dg[s] * (r - 1.0); mg = fmax(mg, lg[s]); }
+                                mg = warp_max(mg);
+#pragma unroll
+                                for (int s = 0; s < NS; ++s) w[s] = mg > -INFINITY ? w[s] * (T)exp(lg[s] - mg) : (T)0;
+                            }
+                        }
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) ws[buf][lane + 32 * s] = w[s];
+                        __syncwarp();
+                        matvec_sum<NS>(ws[buf], A, bp);
+                        buf ^= 1;
+                    }
                     canonicalise<T, NS>(bp);
 #pragma unroll
                     for (int s = 0; s < NS; ++s) u[s] = bp[s];
@@ -122,135 +207,130 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
             }
         }
 
-        // ---- phase B: t = t1-1 ... t0 with outputs
-        T an[BWD_U][NS], bn[BWD_U][NS];
-        int64_t t = ch.t1 - 1;
+        // one output step at row r (t = t0 + r): posterior, statistics, then u <- scaled beta_t
+        auto out_step = [&](unsigned r, const T (&at)[NS], const T (&bt1)[NS]) {
+            T bp[NS];
+            const bool last = (r == last_row);
+            if (last) {
 #pragma unroll
-        for (int q = 0; q < BWD_U; ++q) {
-            int64_t tt = max(t - q, ch.t0);
-            load_row(alpha, tt, an[q]);
-            load_row(blin, min(tt + 1, ch.s1 - 1), bn[q]);
-        }
-        for (; t >= ch.t0; t -= BWD_U) {
+                for (int s = 0; s < NS; ++s) bp[s] = own[s] ? (T)1 : (T)0;
+            } else {
+                beta_step(r + 1, bt1, bp);
+            }
+            T p[NS], zl = (T)0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) { p[s] = at[s] * bp[s]; zl += p[s]; }
+            const T Z = warp_sum(zl);
+            const T invZ = (T)1 / Z;
+            T g[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) g[s] = p[s] * invZ;
+            if constexpr (TRANS) {
+                if (!last) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) xi.add(s, at[s] * invZ);
+                }
+                if (RATIO && ch.t0 + r > ch.s0) {
+                    // implied self transitions of a long segment (_hmm.pyx:89-96,106-111)
+                    const double rt = rr[r];
+                    if (rt > 1.0) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) xd[s] += (T)(rt - 1.0) * g[s];
+                    }
+                }
+                if (ch.t0 + r == ch.s0) {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) gamma0[(int64_t)ch.seq * NP + lane + 32 * s] = g[s];
+                }
+            }
+            if (want_post) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    if (own[s]) {
+                        T gv = g[s];
+                        if (renorm) gv = (T)(((double)gv + eps32) / renorm_den);
+                        post[(ch.t0 + r) * N + lane + 32 * s] = gv;
+                    }
+                }
+            }
+            if (want_map) {
+                // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
+                T best;
+                int arg;
+                if (sizeof(T) == 4 && NS == 1) {
+                    // posteriors are >= 0: their bit patterns order like the values
+                    const unsigned bits = own[0] ? __float_as_uint((float)g[0]) : 0u;
+                    const unsigned mx = __reduce_max_sync(TEHMM_FULL, bits);
+                    arg = __ffs(__ballot_sync(TEHMM_FULL, bits == mx)) - 1;
+                    best = (T)__uint_as_float(mx);
+                } else {
+                    best = g[0];
+                    arg = lane;
+#pragma unroll
+                    for (int s = 1; s < NS; ++s)
+                        if (g[s] > best) { best = g[s]; arg = lane + 32 * s; }
+                    if (arg >= N) best = (T)-1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        T ob = __shfl_xor_sync(TEHMM_FULL, best, o);
+                        int oa = __shfl_xor_sync(TEHMM_FULL, arg, o);
+                        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+                    }
+                }
+                if (lane == 0) {
+                    map_states[ch.t0 + r] = (uint8_t)arg;
+                    mapsum += renorm ? ((double)best + eps32) / renorm_den : (double)best;
+                }
+            }
+            canonicalise<T, NS>(bp);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) u[s] = bp[s];
+        };
+
+        // ---- phase B: rows nrows-1 ... 0, groups of BWD_U with the next group in flight.
+        // For row r the step needs alpha[r] and b[r+1]; b of the row after the
+        // sequence's last step does not exist and is not used (clamped load).
+        T an[BWD_U][NS], bn[BWD_U][NS];
+        unsigned left = nrows;            // rows still to do: [0, left)
+        auto load_group = [&](unsigned top, T (&a4)[BWD_U][NS], T (&b4)[BWD_U][NS]) {
+#pragma unroll
+            for (int q = 0; q < BWD_U; ++q) {
+                const unsigned r = top - 1 - (unsigned)q;
+                load_row(aa, r, a4[q]);
+                load_row(bb, min(r + 1, last_row), b4[q]);
+            }
+        };
+        if (left >= BWD_U) load_group(left, an, bn);
+        while (left >= 2 * BWD_U) {
             T ac[BWD_U][NS], bc[BWD_U][NS];
 #pragma unroll
             for (int q = 0; q < BWD_U; ++q) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) { ac[q][s] = an[q][s]; bc[q][s] = bn[q][s]; }
             }
+            load_group(left - BWD_U, an, bn);
 #pragma unroll
-            for (int q = 0; q < BWD_U; ++q) {
-                int64_t tt = max(t - BWD_U - q, ch.t0);
-                load_row(alpha, tt, an[q]);
-                load_row(blin, min(tt + 1, ch.s1 - 1), bn[q]);
-            }
+            for (int q = 0; q < BWD_U; ++q) out_step(left - 1 - (unsigned)q, ac[q], bc[q]);
+            left -= BWD_U;
+        }
+        if (left >= BWD_U) {
 #pragma unroll
-            for (int q = 0; q < BWD_U; ++q) {
-                const int64_t tc = t - q;
-                if (tc < ch.t0) continue;
-                T bp[NS];
-                T wv[TRANS ? NP : 1];
-                const bool last = (tc == ch.s1 - 1);
-                if (last) {
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) bp[s] = (lane + 32 * s) < N ? (T)1 : (T)0;
-                } else if (TRANS) {
-                    T(&wref)[NP] = reinterpret_cast<T(&)[NP]>(wv);
-                    beta_step(tc, bc[q], bp, wref, true);
-                } else {
-                    T dummy[NP];
-                    beta_step(tc, bc[q], bp, dummy, false);
-                }
-                // posterior
-                T p[NS], zl = (T)0;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) { p[s] = ac[q][s] * bp[s]; zl += p[s]; }
-                const T Z = warp_sum(zl);
-                const T invZ = (T)1 / Z;
-                T g[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) g[s] = p[s] * invZ;
-                if (TRANS) {
-                    if (!last) {
-                        T(&wref)[NP] = reinterpret_cast<T(&)[NP]>(wv);
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) {
-                            const T qv = ac[q][s] * invZ;
-#pragma unroll
-                            for (int j = 0; j < NP; ++j) xi[s][j] = fma(qv, wref[j], xi[s][j]);
-                        }
-                    }
-                    if (RATIO && tc > ch.s0) {
-                        // implied self transitions of a long segment (_hmm.pyx:89-96,106-111)
-                        double r = ratios[tc];
-                        if (r > 1.0) {
-#pragma unroll
-                            for (int s = 0; s < NS; ++s) xd[s] += (T)(r - 1.0) * g[s];
-                        }
-                    }
-                    if (tc == ch.s0) {
-#pragma unroll
-                        for (int s = 0; s < NS; ++s) gamma0[(int64_t)ch.seq * NP + lane + 32 * s] = g[s];
-                    }
-                }
-                if (want_post) {
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) {
-                        int j = lane + 32 * s;
-                        if (j < N) {
-                            T gv = g[s];
-                            if (renorm) gv = (T)(((double)gv + eps32) / renorm_den);
-                            post[tc * N + j] = gv;
-                        }
-                    }
-                }
-                if (want_map) {
-                    // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
-                    T best;
-                    int arg;
-                    if (sizeof(T) == 4 && NS == 1) {
-                        // posteriors are >= 0: their bit patterns order like the values
-                        const unsigned bits = lane < N ? __float_as_uint((float)g[0]) : 0u;
-                        const unsigned mx = __reduce_max_sync(TEHMM_FULL, bits);
-                        arg = __ffs(__ballot_sync(TEHMM_FULL, bits == mx)) - 1;
-                        best = (T)__uint_as_float(mx);
-                    } else {
-                        best = g[0];
-                        arg = lane;
-#pragma unroll
-                        for (int s = 1; s < NS; ++s)
-                            if (g[s] > best) { best = g[s]; arg = lane + 32 * s; }
-                        if (arg >= N) best = (T)-1;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            T ob = __shfl_xor_sync(TEHMM_FULL, best, o);
-                            int oa = __shfl_xor_sync(TEHMM_FULL, arg, o);
-                            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-                        }
-                    }
-                    if (lane == 0) {
-                        map_states[tc] = (uint8_t)arg;
-                        mapsum += renorm ? ((double)best + eps32) / renorm_den : (double)best;
-                    }
-                }
-                canonicalise<T, NS>(bp);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) u[s] = bp[s];
-            }
+            for (int q = 0; q < BWD_U; ++q) out_step(left - 1 - (unsigned)q, an[q], bn[q]);
+            left -= BWD_U;
+        }
+        for (; left > 0; --left) {
+            T at[NS], bt1[NS];
+            load_row(aa, left - 1, at);
+            load_row(bb, min(left, last_row), bt1);
+            out_step(left - 1, at, bt1);
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) end_vec[ci * NP + lane + 32 * s] = u[s];
         if (want_map && lane == 0) map_part[ci] = mapsum;
-        if (TRANS) {
+        if constexpr (TRANS) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                T *dst = xi_part + ((int64_t)ci * NP + lane + 32 * s) * NP;
-#pragma unroll
-                for (int j = 0; j < NP; j += 4) {
-                    if (sizeof(T) == 4)
-                        *reinterpret_cast<float4 *>(dst + j) = make_float4(xi[s][j], xi[s][j + 1], xi[s][j + 2], xi[s][j + 3]);
-                    else { dst[j] = xi[s][j]; dst[j + 1] = xi[s][j + 1]; dst[j + 2] = xi[s][j + 2]; dst[j + 3] = xi[s][j + 3]; }
-                }
+                xi.store(s, xi_part + ((int64_t)ci * NP + lane + 32 * s) * NP);
                 xdiag_part[(int64_t)ci * NP + lane + 32 * s] = xd[s];
             }
         }

@@ -30,32 +30,49 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
     __shared__ __align__(16) T xs_all[TEHMM_WARPS_PER_CTA][2][NP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*xs)[NP] = xs_all[warp];
+    const int N = m.N;
 
-    // column j of the transition matrix for each owned state
-    T c[NS][NP];
+    // column j of the transition matrix for each owned state (zero beyond N, so
+    // lanes without a state compute exact zeros and need no predicates)
+    MatSlice<T, NS> A;
     T pi[NS];
     double dg[NS];
+    unsigned jc[NS];      // clamped column for loads
+    bool own[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        int j = lane + 32 * s;
+        const int j = lane + 32 * s;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) c[s][i] = (T)m.lin_trans[(int64_t)i * NP + j];
+        for (int i = 0; i < NP; ++i) A.set(s, i, (T)m.lin_trans[(int64_t)i * NP + j]);
         pi[s] = (T)m.lin_start[j];
         dg[s] = RATIO ? m.cut_trans[(int64_t)j * NP + j] : 0.0;
+        own[s] = j < N;
+        jc[s] = (unsigned)min(j, N - 1);
     }
-    const int N = m.N;
 
     for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
          ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
         if (mode == 1 && !bad[ci]) continue;
         const TehmmChunk ch = b.chunks[ci];
         T x[NS];
-        int64_t esum = 0;
+        int esum = 0;
         double lsum = 0.0;
         int buf = 0;
 
-        // one recursion step: x <- canonical( (x A) .* b_t [.* g_t] ); returns the exponent
-        auto step = [&](int64_t t, const T (&bt)[NS], bool first) -> int {
+        // where this warp starts reading: the warm-up start (speculative pass) or t0
+        int64_t tw = ch.t0;
+        bool from_start = ch.t0 == ch.s0;
+        if (mode == 0 && ch.t0 > ch.s0) {
+            tw = ch.t0 - b.warmup;
+            if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
+        }
+        // everything below addresses rows relative to tw with 32-bit offsets
+        const T *__restrict__ bb = blin + tw * N;
+        T *__restrict__ aa = alpha ? alpha + tw * N : nullptr;
+        const double *__restrict__ rr = RATIO ? ratios + tw : nullptr;
+
+        // one recursion step: x <- scaled( (x A) .* b_t [.* g_t] ); returns the exponent
+        auto step = [&](unsigned row, const T (&bt)[NS], bool first) -> int {
             T raw[NS];
             if (first) {
 #pragma unroll
@@ -65,13 +82,13 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
                 for (int s = 0; s < NS; ++s) xs[buf][lane + 32 * s] = x[s];
                 __syncwarp();
                 T y[NS];
-                matvec_sum<T, NS>(xs[buf], c, y);
+                matvec_sum<NS>(xs[buf], A, y);
                 buf ^= 1;
 #pragma unroll
                 for (int s = 0; s < NS; ++s) raw[s] = y[s] * bt[s];
             }
             if (RATIO) {
-                double r = ratios[t];
+                const double r = rr[row];
                 if (r > 1.0) {
                     double lg[NS], mg = -INFINITY;
 #pragma unroll
@@ -87,61 +104,74 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
                     }
                 }
             }
-            int e = canonicalise<T, NS>(raw);
+            const int e = canonicalise<T, NS>(raw);
 #pragma unroll
             for (int s = 0; s < NS; ++s) x[s] = raw[s];
             return e;
         };
-        auto load_b = [&](int64_t t, T (&bt)[NS]) {
+        // running pointers of this lane's element in the current row (bumped by N per row)
+        const T *__restrict__ bp[NS];
+        T *__restrict__ ap[NS];
+        bool wr[NS];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                int j = lane + 32 * s;
-                bt[s] = j < N ? blin[t * N + j] : (T)0;
-            }
+        for (int s = 0; s < NS; ++s) {
+            bp[s] = bb + jc[s];
+            ap[s] = aa + lane + 32 * s;
+            wr[s] = own[s] && aa != nullptr;
+        }
+        const unsigned Nu = (unsigned)N;
+        // b of the row `ahead` rows after the current one
+        auto load_b = [&](unsigned ahead, T (&bt)[NS]) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) bt[s] = bp[s][ahead * Nu];
+        };
+        auto store_a = [&]() {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (wr[s]) *ap[s] = x[s];
+        };
+        auto advance = [&](unsigned rows) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) { bp[s] += rows * Nu; ap[s] += rows * Nu; }
         };
 
-        int64_t t = ch.t0;
-        if (ch.t0 > ch.s0) {
-            if (mode == 0) {
-                int64_t tw = ch.t0 - b.warmup;
-                T bt[NS];
-                if (tw <= ch.s0) {
-                    tw = ch.s0;
-                    load_b(tw, bt);
-                    step(tw, bt, true);
-                    ++tw;
-                } else {
+        unsigned row = 0;                                   // current row, relative to tw
+        const unsigned row0 = (unsigned)(ch.t0 - tw);       // first row with output
+        const unsigned row1 = (unsigned)(ch.t1 - tw);       // one past the last row
+        if (mode == 1) {
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) x[s] = (lane + 32 * s) < N ? (T)1 : (T)0;
-                }
-                for (; tw < ch.t0; ++tw) {
-                    load_b(tw, bt);
-                    step(tw, bt, false);
-                }
-                lsum = 0.0;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = x[s];
-            } else {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) x[s] = start_vec[ci * NP + lane + 32 * s];
-            }
-        } else {
+            for (int s = 0; s < NS; ++s) x[s] = start_vec[ci * NP + lane + 32 * s];
+        } else if (from_start) {
             T bt[NS];
-            load_b(t, bt);
-            esum += step(t, bt, true);
-            if (alpha) {
+            load_b(0, bt);
+            const int e = step(0, bt, true);
+            if (row0 == 0) { esum += e; store_a(); }
+            row = 1;
+            advance(1);
+        } else {
 #pragma unroll
-                for (int s = 0; s < NS; ++s)
-                    if (lane + 32 * s < N) alpha[t * N + lane + 32 * s] = x[s];
+            for (int s = 0; s < NS; ++s) x[s] = own[s] ? (T)1 : (T)0;
+        }
+        if (mode == 0 && row0 > 0) {
+            // speculative warm-up: no output, scale discarded
+            for (; row < row0; ++row) {
+                T bt[NS];
+                load_b(0, bt);
+                step(row, bt, false);
+                advance(1);
             }
-            ++t;
+            lsum = 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = x[s];
         }
 
-        // main loop with a FWD_U-deep register prefetch of b
+        // main loop: groups of FWD_U steps, the next group's b rows already in flight
         T bn[FWD_U][NS];
+        if (row + FWD_U <= row1) {
 #pragma unroll
-        for (int u = 0; u < FWD_U; ++u) load_b(min(t + u, ch.t1 - 1), bn[u]);
-        for (; t < ch.t1; t += FWD_U) {
+            for (int u = 0; u < FWD_U; ++u) load_b(u, bn[u]);
+        }
+        while (row + 2 * FWD_U <= row1) {
             T bc[FWD_U][NS];
 #pragma unroll
             for (int u = 0; u < FWD_U; ++u) {
@@ -149,18 +179,30 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
                 for (int s = 0; s < NS; ++s) bc[u][s] = bn[u][s];
             }
 #pragma unroll
-            for (int u = 0; u < FWD_U; ++u) load_b(min(t + FWD_U + u, ch.t1 - 1), bn[u]);
+            for (int u = 0; u < FWD_U; ++u) load_b(FWD_U + u, bn[u]);
 #pragma unroll
             for (int u = 0; u < FWD_U; ++u) {
-                if (t + u < ch.t1) {
-                    esum += step(t + u, bc[u], false);
-                    if (alpha) {
-#pragma unroll
-                        for (int s = 0; s < NS; ++s)
-                            if (lane + 32 * s < N) alpha[(t + u) * N + lane + 32 * s] = x[s];
-                    }
-                }
+                esum += step(row + u, bc[u], false);
+                store_a();
+                advance(1);
             }
+            row += FWD_U;
+        }
+        if (row + FWD_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u) {
+                esum += step(row + u, bn[u], false);
+                store_a();
+                advance(1);
+            }
+            row += FWD_U;
+        }
+        for (; row < row1; ++row) {
+            T bt[NS];
+            load_b(0, bt);
+            esum += step(row, bt, false);
+            store_a();
+            advance(1);
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) end_vec[ci * NP + lane + 32 * s] = x[s];

@@ -268,20 +268,20 @@ __device__ __forceinline__ void matvec_max(const T *xs, const T (&c)[NS][32 * NS
 // Scale a non-negative vector by a power of two so that its largest element
 // lies in [1,2).  Exact (no rounding), hence independent of scaling history.
 // Returns the exponent taken out: raw = scaled * 2^shift.
-template <typename T, int NS> __device__ __noinline__ int canonicalise_rare(T (&x)[NS], bool any_pos)
+template <typename T> struct ScaleShift { T sc; int shift; };
+template <typename T> __device__ __noinline__ ScaleShift<T> canonicalise_rare(T m)
 {
-    // all zero (impossible data), subnormal, inf or nan
-    if (!any_pos) return 0;
-    T m = x[0];
-#pragma unroll
-    for (int s = 1; s < NS; ++s) m = x[s] > m ? x[s] : m;
-    const bool big = __any_sync(TEHMM_FULL, !(m < (T)INFINITY));
-    if (big) return 0;
+    // called warp-uniformly: the largest element is zero (impossible data),
+    // subnormal, inf or nan
+    ScaleShift<T> r;
+    r.sc = (T)1;
+    r.shift = 0;
+    if (!__any_sync(TEHMM_FULL, m > (T)0)) return r;
+    if (__any_sync(TEHMM_FULL, !(m < (T)INFINITY))) return r;
     // subnormal maximum: lift by 2^64 and let the next step finish the job
-    const T up = TehmmNum<T>::inv_scale(TehmmNum<T>::BIAS - 64);
-#pragma unroll
-    for (int s = 0; s < NS; ++s) x[s] *= up;
-    return -64;
+    r.shift = -64;
+    r.sc = TehmmNum<T>::inv_scale(TehmmNum<T>::BIAS - 64);
+    return r;
 }
 template <typename T, int NS> __device__ __forceinline__ int canonicalise(T (&x)[NS])
 {
@@ -290,12 +290,16 @@ template <typename T, int NS> __device__ __forceinline__ int canonicalise(T (&x)
     for (int s = 1; s < NS; ++s) m = x[s] > m ? x[s] : m;
     const unsigned mb = __reduce_max_sync(TEHMM_FULL, TehmmNum<T>::order_bits(m));
     const unsigned e = sizeof(T) == 4 ? (mb >> 23) : (mb >> 20);
-    if (__builtin_expect(e - 1u >= (unsigned)TehmmNum<T>::EMAX, 0))
-        return canonicalise_rare<T, NS>(x, __any_sync(TEHMM_FULL, m > (T)0));
-    const T sc = TehmmNum<T>::inv_scale((int)e);
+    ScaleShift<T> r;
+    if (__builtin_expect(e - 1u >= (unsigned)TehmmNum<T>::EMAX, 0)) {
+        r = canonicalise_rare<T>(m);
+    } else {
+        r.sc = TehmmNum<T>::inv_scale((int)e);
+        r.shift = (int)e - TehmmNum<T>::BIAS;
+    }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) x[s] *= sc;
-    return (int)e - TehmmNum<T>::BIAS;
+    for (int s = 0; s < NS; ++s) x[s] *= r.sc;
+    return r.shift;
 }
 
 // warp-wide maximum of arbitrary-sign values

@@ -1,24 +1,31 @@
 // Chunked parallel-in-time Viterbi with on-device parallel traceback
 // (hmm.py:668-676 -> _hmm.pyx:201-259).
 //
-// DP: one warp per chunk, lane j owns column j of log A in registers, delta is
-// kept max-normalised (max = 0) and broadcast through shared memory; the
-// strict-'>' / lowest-from-state tie rule of the reference is kept.  Chunks
-// that do not begin a sequence speculate their start vector with `warmup`
-// steps from a flat vector and are verified / repaired like forward.cu.
+// DP (viterbi_kernel): one warp per chunk, lane j owns column j of log A in
+// registers, delta is kept max-normalised (max = 0) and broadcast through
+// shared memory.  The kernel is issue-bound, so it computes VALUES only:
+//     delta_t[j] = max_i(delta_{t-1}[i] + logA[i][j]) + e_t[j]
+// with packed FADD2 + 3-input FMNMX3 (one instruction per candidate instead of
+// four with an explicit arg-max) and writes the normalised delta lattice.
+// Chunks that do not begin a sequence speculate their start vector with
+// `warmup` steps from a flat vector and are verified / repaired like forward.cu.
 //
-// Traceback without a serial walk over T: while the DP runs, each lane also
-// carries, per traceback tile of 64 steps, the state at the end of the
-// PREVIOUS tile that its best path comes from (one SHFL per step).  Those
-// tile maps are composed per chunk, the per-chunk maps are walked once per
-// sequence out of shared memory, and then every tile is traced independently
-// (one lane per tile) through the uint8 back-pointers.
+// Traceback (vit_traceback_kernel): back-pointers are needed only ALONG the
+// best path, so they are recomputed there: with state s at time t,
+//     s_{t-1} = lowest i maximising delta_{t-1}[i] + logA[i][s]
+// from the stored lattice, lane i evaluating candidate i with exactly the
+// operands the DP used (so ties fall as in the reference: strict '>' scanning
+// from-states upward = lowest from-state, _hmm.pyx:232-247).  One warp per
+// chunk walks its chunk right to left.  The chunk's END state depends on the
+// chunk to its right, so it is speculated too (walk in from `warmup` steps
+// beyond the chunk end, best paths coalesce), then verified against the state
+// the right neighbour really reaches, and repaired where different.
 //
 // The returned log-probability is a float64 re-score of the returned path
 // against the float64 tables, so it does not carry fp32 DP rounding.
 //
-// Algorithmic HBM bytes per step: 4N (elog) read, NP (back-pointers) written,
-// then ~NP read + 1 written by the traceback.
+// Algorithmic HBM bytes per step (fp32): DP 4N read (e) + 4N written (delta);
+// traceback 4N read + 1 written; re-score K + 1 read.
 #include "scan.cuh"
 
 #define VIT_U 4
@@ -26,26 +33,31 @@
 template <typename T, int NS, bool RATIO>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
 viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
-               const double *__restrict__ ratios, uint8_t *__restrict__ bp,
-               uint8_t *__restrict__ tilemap, T *__restrict__ start_vec,
-               T *__restrict__ end_vec, const int *__restrict__ bad, int mode)
+               const double *__restrict__ ratios, T *__restrict__ lattice,
+               T *__restrict__ start_vec, T *__restrict__ end_vec,
+               const int *__restrict__ bad, int mode)
 {
     constexpr int NP = 32 * NS;
     __shared__ __align__(16) T ds_all[TEHMM_WARPS_PER_CTA][2][NP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*ds)[NP] = ds_all[warp];
     const int N = m.N;
+    const unsigned Nu = (unsigned)N;
     const T NEG = (T)-INFINITY;
 
-    T c[NS][NP];
+    MatSlice<T, NS> A;       // column j of log A (-inf beyond N and for zero transitions)
     T ls[NS], dg[NS];
+    unsigned jc[NS];
+    bool own[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        int j = lane + 32 * s;
+        const int j = lane + 32 * s;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) c[s][i] = (T)m.cut_trans[(int64_t)i * NP + j];
+        for (int i = 0; i < NP; ++i) A.set(s, i, (T)m.cut_trans[(int64_t)i * NP + j]);
         ls[s] = (T)m.cut_start[j];
         dg[s] = (T)m.cut_trans[(int64_t)j * NP + j];
+        own[s] = j < N;
+        jc[s] = (unsigned)min(j, N - 1);
     }
     const T a00 = (T)m.cut_trans[0];
 
@@ -54,95 +66,110 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
         if (mode == 1 && !bad[ci]) continue;
         const TehmmChunk ch = b.chunks[ci];
         T d[NS];
-        int orig[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) orig[s] = 0;
         int buf = 0;
 
-        auto load_e = [&](int64_t t, T (&et)[NS]) {
+        int64_t tw = ch.t0;
+        bool from_start = ch.t0 == ch.s0;
+        if (mode == 0 && ch.t0 > ch.s0) {
+            tw = ch.t0 - b.warmup;
+            if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
+        }
+        const T *__restrict__ ee = elog + tw * N;
+        T *__restrict__ ll = lattice + tw * N;
+        const double *__restrict__ rr = RATIO ? ratios + tw : nullptr;
+
+        auto load_e = [&](unsigned row, T (&et)[NS]) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                int j = lane + 32 * s;
-                et[s] = j < N ? elog[t * N + j] : NEG;
+                const T v = ee[row * Nu + jc[s]];
+                et[s] = own[s] ? v : NEG;
             }
         };
-        auto init = [&](int64_t t, const T (&et)[NS]) {
+        auto store_d = [&](unsigned row) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (own[s]) ll[row * Nu + (unsigned)(lane + 32 * s)] = d[s];
+        };
+        auto init = [&](unsigned row, const T (&et)[NS]) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 d[s] = ls[s] + et[s];
                 if (RATIO) {
-                    double r = ratios[t];
+                    const double r = rr[row];
                     if (r > 1.0) d[s] += dg[s] * (T)(r - 1.0);
                 }
             }
             log_normalise<T, NS>(d);
         };
-        // one DP step; arg[] receives the back-pointers
-        auto step = [&](int64_t t, const T (&et)[NS], int (&arg)[NS]) {
+        auto step = [&](unsigned row, const T (&et)[NS]) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) ds[buf][lane + 32 * s] = d[s];
             __syncwarp();
-            T extra0[NS], add[NS];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) { extra0[s] = (T)0; add[s] = et[s]; }
-            if (RATIO) {
-                // _hmm.pyx:234-237 vs 243-244: from-state 0 always gets A_jj*r
-                // (minus A_00 when j==0); the others get A_jj*(r-1) only if r>1
-                const T r = (T)ratios[t];
+            T y[NS];
+            if (!RATIO) {
+                matvec_maxval<NS>(ds[buf], A, y);
+            } else {
+                // _hmm.pyx:234-237 vs 243-244: from-state 0 always gets A_jj*r (minus A_00
+                // when j==0); the other from-states get A_jj*(r-1), and only if r>1.
+                const T r = (T)rr[row];
+                const T x0 = ds[buf][0];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     const T common = r > (T)1 ? dg[s] * (r - (T)1) : (T)0;
-                    add[s] += common;
                     // (a zero-probability self transition would give inf-inf here; the
                     //  reference's finite -1e100 sentinel has no fp32 twin)
-                    extra0[s] = dg[s] > NEG ? dg[s] * r - common : (T)0;
-                    if (lane + 32 * s == 0 && a00 > NEG) extra0[s] -= a00;
+                    T extra0 = dg[s] > NEG ? dg[s] * r - common : (T)0;
+                    if (lane + 32 * s == 0 && a00 > NEG) extra0 -= a00;
+                    T rest = NEG;      // max over from-states >= 1
+                    T c0 = NEG;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        T c;
+                        if constexpr (sizeof(T) == 4) c = (i & 1) ? hi2(A.c[s][i >> 1]) : lo2(A.c[s][i >> 1]);
+                        else c = A.c[s][i];
+                        if (i == 0) c0 = c;
+                        else rest = fmax(rest, ds[buf][i] + c);
+                    }
+                    y[s] = fmax(rest, x0 + c0 + extra0) + common;
                 }
             }
-            T y[NS];
-            matvec_max<T, NS>(ds[buf], c, extra0, y, arg);
             buf ^= 1;
 #pragma unroll
-            for (int s = 0; s < NS; ++s) d[s] = y[s] + add[s];
+            for (int s = 0; s < NS; ++s) d[s] = y[s] + et[s];
             log_normalise<T, NS>(d);
         };
 
-        int64_t t = ch.t0;
-        if (ch.t0 > ch.s0) {
-            if (mode == 0) {
-                int64_t tw = ch.t0 - b.warmup;
-                T et[NS];
-                int arg[NS];
-                if (tw <= ch.s0) {
-                    tw = ch.s0;
-                    load_e(tw, et);
-                    init(tw, et);
-                    ++tw;
-                } else {
+        unsigned row = 0;
+        const unsigned row0 = (unsigned)(ch.t0 - tw), row1 = (unsigned)(ch.t1 - tw);
+        if (mode == 1) {
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) d[s] = (lane + 32 * s) < N ? (T)0 : NEG;
-                }
-                for (; tw < ch.t0; ++tw) {
-                    load_e(tw, et);
-                    step(tw, et, arg);
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = d[s];
-            } else {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) d[s] = start_vec[ci * NP + lane + 32 * s];
-            }
-        } else {
+            for (int s = 0; s < NS; ++s) d[s] = start_vec[ci * NP + lane + 32 * s];
+        } else if (from_start) {
             T et[NS];
-            load_e(t, et);
-            init(t, et);
-            ++t;
+            load_e(0, et);
+            init(0, et);
+            if (row0 == 0) store_d(0);
+            row = 1;
+        } else {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) d[s] = own[s] ? (T)0 : NEG;
+        }
+        if (mode == 0 && row0 > 0) {
+            for (; row < row0; ++row) {
+                T et[NS];
+                load_e(row, et);
+                step(row, et);
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = d[s];
         }
 
         T en[VIT_U][NS];
+        if (row + VIT_U <= row1) {
 #pragma unroll
-        for (int u = 0; u < VIT_U; ++u) load_e(min(t + u, ch.t1 - 1), en[u]);
-        for (; t < ch.t1; t += VIT_U) {
+            for (int u = 0; u < VIT_U; ++u) load_e(row + u, en[u]);
+        }
+        while (row + 2 * VIT_U <= row1) {
             T ec[VIT_U][NS];
 #pragma unroll
             for (int u = 0; u < VIT_U; ++u) {
@@ -150,135 +177,202 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
                 for (int s = 0; s < NS; ++s) ec[u][s] = en[u][s];
             }
 #pragma unroll
-            for (int u = 0; u < VIT_U; ++u) load_e(min(t + VIT_U + u, ch.t1 - 1), en[u]);
+            for (int u = 0; u < VIT_U; ++u) load_e(row + VIT_U + u, en[u]);
 #pragma unroll
             for (int u = 0; u < VIT_U; ++u) {
-                const int64_t tc = t + u;
-                if (tc >= ch.t1) continue;
-                int arg[NS];
-                step(tc, ec[u], arg);
-                const int rel = (int)((tc - ch.s0) & (TEHMM_TILE - 1));
-#pragma unroll
-                for (int s = 0; s < NS; ++s) bp[tc * NP + lane + 32 * s] = (uint8_t)arg[s];
-                // carry "state at the end of the previous tile" along the best paths
-                int no[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    if (rel == 0) {
-                        no[s] = arg[s];
-                    } else if (NS == 1) {
-                        no[s] = __shfl_sync(TEHMM_FULL, orig[0], arg[s]);
-                    } else {
-                        int lo = __shfl_sync(TEHMM_FULL, orig[0], arg[s] & 31);
-                        int hi = __shfl_sync(TEHMM_FULL, orig[NS - 1], arg[s] & 31);
-                        no[s] = arg[s] < 32 ? lo : hi;
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) orig[s] = no[s];
-                if (rel == TEHMM_TILE - 1 || tc == ch.t1 - 1) {
-                    const int64_t tile = ch.tile0 + ((tc - ch.t0) >> 6);
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) tilemap[tile * NP + lane + 32 * s] = (uint8_t)orig[s];
-                }
+                step(row + u, ec[u]);
+                store_d(row + u);
             }
+            row += VIT_U;
+        }
+        if (row + VIT_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) {
+                step(row + u, en[u]);
+                store_d(row + u);
+            }
+            row += VIT_U;
+        }
+        for (; row < row1; ++row) {
+            T et[NS];
+            load_e(row, et);
+            step(row, et);
+            store_d(row);
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) end_vec[ci * NP + lane + 32 * s] = d[s];
     }
 }
 
-// cmap[c][j] = state at t0-1 on the best path that ends chunk c in state j
-__global__ void vit_compose_kernel(TehmmBatchDev b, int NP, const uint8_t *__restrict__ tilemap,
-                                   uint8_t *__restrict__ cmap)
+// order-preserving key of a float for REDUX (larger value -> larger key)
+__device__ __forceinline__ unsigned order_key(float v)
 {
-    int64_t ci = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (ci >= b.nchunks) return;
-    const TehmmChunk ch = b.chunks[ci];
-    for (int j = lane; j < NP; j += 32) {
-        int x = j;
-        for (int k = ch.ntiles - 1; k >= 0; --k) x = tilemap[(ch.tile0 + k) * NP + x];
-        cmap[ci * NP + j] = (uint8_t)x;
+    const unsigned bts = __float_as_uint(v);
+    return bts ^ ((unsigned)((int)bts >> 31) | 0x80000000u);
+}
+
+// lowest state index among the maxima of a warp-distributed vector
+template <typename T, int NS>
+__device__ __forceinline__ int warp_argmax_first(const T (&v)[NS], int lane)
+{
+    if constexpr (sizeof(T) == 4 && NS == 1) {
+        const unsigned key = order_key((float)v[0]);
+        const unsigned mx = __reduce_max_sync(TEHMM_FULL, key);
+        return __ffs(__ballot_sync(TEHMM_FULL, key == mx)) - 1;
+    } else {
+        T best = v[0];
+        int arg = lane;
+#pragma unroll
+        for (int s = 1; s < NS; ++s)
+            if (v[s] > best) { best = v[s]; arg = lane + 32 * s; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(TEHMM_FULL, best, o);
+            const int oa = __shfl_xor_sync(TEHMM_FULL, arg, o);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        return arg;
     }
 }
 
-// One CTA per sequence: end state of the last chunk = first maximum of its
-// final delta (np.argmax, _hmm.pyx:252); then walk the chunk maps backwards out
-// of shared memory to get every chunk's end state.
-template <typename T>
-__global__ void vit_seqscan_kernel(TehmmBatchDev b, int NP, const T *__restrict__ end_vec,
-                                   const uint8_t *__restrict__ cmap, uint8_t *__restrict__ chunk_end,
-                                   int smem_chunks)
+// One warp per chunk.  mode 0: speculate the chunk's end state, walk the chunk,
+// record the state it implies for the left neighbour (pred).  mode 1: redo the
+// chunks whose end state was wrong, from the forced end state.
+template <typename T, int NS, bool RATIO>
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lattice,
+                     const double *__restrict__ ratios, uint8_t *__restrict__ states,
+                     int64_t *__restrict__ states64, uint8_t *__restrict__ spec_end,
+                     uint8_t *__restrict__ pred, const uint8_t *__restrict__ forced_end,
+                     const int *__restrict__ bad, int mode)
 {
-    extern __shared__ uint8_t cm[];
-    __shared__ int cur;
-    int64_t s = blockIdx.x;
-    int64_t c0 = b.seq_chunk0[s], c1 = b.seq_chunk0[s + 1];
-    if (c1 <= c0) return;
-    if (threadIdx.x == 0) {
-        const T *dv = end_vec + (c1 - 1) * NP;
-        int best = 0;
-        for (int j = 1; j < NP; ++j)
-            if (dv[j] > dv[best]) best = j;
-        cur = best;
-        chunk_end[c1 - 1] = (uint8_t)best;
+    constexpr int NP = 32 * NS;
+    extern __shared__ __align__(16) unsigned char tb_smem[];
+    T *AT = reinterpret_cast<T *>(tb_smem);               // AT[s*NP + i] = logA[i][s]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = m.N;
+    const unsigned Nu = (unsigned)N;
+    const T NEG = (T)-INFINITY;
+    for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
+        const int s = e / NP, i = e - s * NP;
+        AT[e] = (T)m.cut_trans[(int64_t)i * NP + s];
     }
     __syncthreads();
-    for (int64_t hi = c1; hi > c0 + 1; hi -= smem_chunks) {
-        int64_t lo = hi - smem_chunks;
-        if (lo < c0 + 1) lo = c0 + 1;
-        // stage cmap[lo..hi)
-        int64_t bytes = (hi - lo) * NP;
-        for (int64_t e = threadIdx.x * 16; e < bytes; e += (int64_t)blockDim.x * 16)
-            *reinterpret_cast<uint4 *>(cm + e) = *reinterpret_cast<const uint4 *>(cmap + lo * NP + e);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int st = cur;
-            for (int64_t c = hi - 1; c >= lo; --c) {
-                st = cm[(c - lo) * NP + st];
-                chunk_end[c - 1] = (uint8_t)st;
+    const T a00 = (T)m.cut_trans[0];
+    unsigned jc[NS];
+    bool own[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        own[s] = lane + 32 * s < N;
+        jc[s] = (unsigned)min(lane + 32 * s, N - 1);
+    }
+
+    for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
+         ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
+        if (mode == 1 && !bad[ci]) continue;
+        const TehmmChunk ch = b.chunks[ci];
+        // rows relative to t0 - 1 (row 0 = the left neighbour's last step, if any)
+        const int64_t tbase = ch.t0 > ch.s0 ? ch.t0 - 1 : ch.t0;
+        const T *__restrict__ ll = lattice + tbase * N;
+        const double *__restrict__ rr = RATIO ? ratios + tbase : nullptr;
+        const unsigned rfirst = (unsigned)(ch.t0 - tbase);            // row of t0 (0 or 1)
+        const unsigned rlast = (unsigned)(ch.t1 - 1 - tbase);         // row of t1-1
+
+        auto load_d = [&](unsigned row, T (&dv)[NS]) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const T v = ll[row * Nu + jc[s]];
+                dv[s] = own[s] ? v : NEG;
             }
-            cur = st;
+        };
+        // state at row-1 given state st at `row`, from delta[row-1] (already loaded)
+        auto back = [&](unsigned row, int st, const T (&dprev)[NS]) -> int {
+            T cand[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cand[s] = dprev[s] + AT[st * NP + lane + 32 * s];
+            if (RATIO) {
+                // only the from-state-0 candidate differs between from-states (see viterbi_kernel)
+                if (lane == 0) {
+                    const T r = (T)rr[row];
+                    const T dgs = AT[st * NP + st];
+                    const T common = r > (T)1 ? dgs * (r - (T)1) : (T)0;
+                    T extra0 = dgs > NEG ? dgs * r - common : (T)0;
+                    if (st == 0 && a00 > NEG) extra0 -= a00;
+                    cand[0] += extra0;
+                }
+            }
+            return warp_argmax_first<T, NS>(cand, lane);
+        };
+
+        int st;
+        if (mode == 1) {
+            st = forced_end[ci];
+        } else if (ch.t1 == ch.s1) {
+            T dv[NS];
+            load_d(rlast, dv);
+            st = warp_argmax_first<T, NS>(dv, lane);        // np.argmax of the last row
+        } else {
+            // speculate: enter from `warmup` steps to the right (or the sequence end)
+            unsigned rq = rlast + (unsigned)b.warmup;
+            const unsigned rseq = (unsigned)(ch.s1 - 1 - tbase);
+            if (rq > rseq) rq = rseq;
+            T dv[NS];
+            load_d(rq, dv);
+            st = warp_argmax_first<T, NS>(dv, lane);
+            T dn[NS];
+            load_d(rq - 1, dn);
+            for (unsigned row = rq; row > rlast; --row) {
+                T dc[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) dc[s] = dn[s];
+                if (row >= 2) load_d(row - 2, dn);
+                st = back(row, st, dc);
+            }
         }
-        __syncthreads();
+        if (lane == 0) spec_end[ci] = (uint8_t)st;
+
+        // walk the chunk: rows rlast ... rfirst, then the predecessor of row rfirst
+        {
+            T dn[NS];
+            if (rlast >= 1) load_d(rlast - 1, dn);
+            for (unsigned row = rlast;; --row) {
+                if (lane == 0) {
+                    if (states) states[tbase + row] = (uint8_t)st;
+                    if (states64) states64[tbase + row] = st;
+                }
+                if (row == 0) break;                       // chunk starts its sequence
+                T dc[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) dc[s] = dn[s];
+                if (row >= 2) load_d(row - 2, dn);
+                st = back(row, st, dc);
+                if (row == rfirst) {                       // st is now the state at t0-1
+                    if (lane == 0) pred[ci] = (uint8_t)st;
+                    break;
+                }
+            }
+        }
     }
 }
 
-// One warp per chunk: lane 0 resolves the end state of every tile, then the
-// lanes trace the tiles in parallel.
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
-vit_traceback_kernel(TehmmBatchDev b, int NP, const uint8_t *__restrict__ bp,
-                     const uint8_t *__restrict__ tilemap, const uint8_t *__restrict__ chunk_end,
-                     uint8_t *__restrict__ states, int64_t *__restrict__ states64, int max_tiles)
+// bad[c-1] = the end state chunk c-1 assumed differs from the state its right
+// neighbour c really reaches at t0-1; the true state is handed to the repair pass.
+__global__ void vit_tb_verify_kernel(TehmmBatchDev b, uint8_t *spec_end, const uint8_t *pred,
+                                     uint8_t *forced_end, int *bad, int *nbad)
 {
-    extern __shared__ uint8_t tile_end_all[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *tile_end = tile_end_all + (size_t)warp * max_tiles;
-    for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
-         ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
-        const TehmmChunk ch = b.chunks[ci];
-        __syncwarp();
-        if (lane == 0) {
-            int st = chunk_end[ci];
-            for (int k = ch.ntiles - 1; k >= 0; --k) {
-                tile_end[k] = (uint8_t)st;
-                st = tilemap[(ch.tile0 + k) * NP + st];
-            }
-        }
-        __syncwarp();
-        for (int k = lane; k < ch.ntiles; k += 32) {
-            const int64_t ta = ch.t0 + (int64_t)k * TEHMM_TILE;
-            int64_t tz = ta + TEHMM_TILE;
-            if (tz > ch.t1) tz = ch.t1;
-            int st = tile_end[k];
-            for (int64_t t = tz - 1; t >= ta; --t) {
-                if (states) states[t] = (uint8_t)st;
-                if (states64) states64[t] = st;
-                if (t > ta) st = bp[t * NP + st];
-            }
+    int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= b.nchunks) return;
+    const TehmmChunk ch = b.chunks[ci];
+    if (ch.t0 > ch.s0) {
+        const int flag = spec_end[ci - 1] != pred[ci];
+        bad[ci - 1] = flag;
+        if (flag) {
+            forced_end[ci - 1] = pred[ci];
+            spec_end[ci - 1] = pred[ci];
+            atomicAdd(nbad, 1);
         }
     }
+    if (ch.t1 == ch.s1) bad[ci] = 0;      // last chunk of a sequence: exact by construction
 }
 
 // float64 score of the returned path, in the reference's terms
@@ -341,51 +435,76 @@ __global__ void vit_score_reduce_kernel(TehmmBatchDev b, const double *__restric
 
 template <typename T, int NS>
 static cudaError_t launch_vit(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
-                              const T *elog, const double *ratios, uint8_t *bp, uint8_t *tilemap,
-                              T *start_vec, T *end_vec, const int *bad, int mode, int grid)
+                              const T *elog, const double *ratios, T *lattice, T *start_vec,
+                              T *end_vec, const int *bad, int mode, int grid)
 {
     if (ratios)
-        viterbi_kernel<T, NS, true><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, bp, tilemap, start_vec, end_vec, bad, mode);
+        viterbi_kernel<T, NS, true><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, lattice, start_vec, end_vec, bad, mode);
     else
-        viterbi_kernel<T, NS, false><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, bp, tilemap, start_vec, end_vec, bad, mode);
+        viterbi_kernel<T, NS, false><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, lattice, start_vec, end_vec, bad, mode);
     return cudaGetLastError();
 }
 
 cudaError_t tehmm_launch_viterbi(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
-                                 int prec, const void *elog, const double *ratios, uint8_t *bp,
-                                 uint8_t *tilemap, void *start_vec, void *end_vec, const int *bad,
-                                 int mode, int grid)
+                                 int prec, const void *elog, const double *ratios, void *lattice,
+                                 void *start_vec, void *end_vec, const int *bad, int mode, int grid)
 {
     if (prec == TEHMM_F32) {
-        if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, bp, tilemap, (float *)start_vec, (float *)end_vec, bad, mode, grid);
-        return launch_vit<float, 2>(st, m, b, (const float *)elog, ratios, bp, tilemap, (float *)start_vec, (float *)end_vec, bad, mode, grid);
+        if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
+        return launch_vit<float, 2>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
     }
-    if (m.NS == 1) return launch_vit<double, 1>(st, m, b, (const double *)elog, ratios, bp, tilemap, (double *)start_vec, (double *)end_vec, bad, mode, grid);
-    return launch_vit<double, 2>(st, m, b, (const double *)elog, ratios, bp, tilemap, (double *)start_vec, (double *)end_vec, bad, mode, grid);
+    if (m.NS == 1) return launch_vit<double, 1>(st, m, b, (const double *)elog, ratios, (double *)lattice, (double *)start_vec, (double *)end_vec, bad, mode, grid);
+    return launch_vit<double, 2>(st, m, b, (const double *)elog, ratios, (double *)lattice, (double *)start_vec, (double *)end_vec, bad, mode, grid);
 }
 
-// compose + per-sequence scan + per-tile traceback + fp64 re-score: 5 launches
-cudaError_t tehmm_launch_traceback(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
-                                   int prec, const void *end_vec, const uint8_t *bp,
-                                   const uint8_t *tilemap, uint8_t *cmap, uint8_t *chunk_end,
-                                   uint8_t *states, int64_t *states64,
-                                   const double *ratios_em, const double *ratios_dp,
-                                   double *score_part, double *logprob, int max_tiles, int grid)
+template <typename T, int NS>
+static cudaError_t launch_tb(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                             const T *lattice, const double *ratios, uint8_t *states,
+                             int64_t *states64, uint8_t *spec_end, uint8_t *pred,
+                             const uint8_t *forced_end, const int *bad, int mode, int grid)
 {
-    const int NP = m.NP;
-    int warps = 4;
-    vit_compose_kernel<<<(int)((b.nchunks + warps - 1) / warps), warps * 32, 0, st>>>(b, NP, tilemap, cmap);
-    int smem_chunks = (160 * 1024) / NP;
-    size_t smem = (size_t)smem_chunks * NP;
-    if (prec == TEHMM_F32) {
-        cudaFuncSetAttribute(vit_seqscan_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vit_seqscan_kernel<float><<<(int)b.nseq, 256, smem, st>>>(b, NP, (const float *)end_vec, cmap, chunk_end, smem_chunks);
+    const size_t smem = (size_t)m.NP * m.NP * sizeof(T);
+    if (ratios) {
+        auto k = vit_traceback_kernel<T, NS, true>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TEHMM_WARPS_PER_CTA * 32, smem, st>>>(m, b, lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode);
     } else {
-        cudaFuncSetAttribute(vit_seqscan_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        vit_seqscan_kernel<double><<<(int)b.nseq, 256, smem, st>>>(b, NP, (const double *)end_vec, cmap, chunk_end, smem_chunks);
+        auto k = vit_traceback_kernel<T, NS, false>;
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, TEHMM_WARPS_PER_CTA * 32, smem, st>>>(m, b, lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode);
     }
-    size_t tsm = (size_t)TEHMM_WARPS_PER_CTA * max_tiles;
-    vit_traceback_kernel<<<grid, TEHMM_WARPS_PER_CTA * 32, tsm, st>>>(b, NP, bp, tilemap, chunk_end, states, states64, max_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t tehmm_launch_traceback(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                   int prec, const void *lattice, const double *ratios,
+                                   uint8_t *states, int64_t *states64, uint8_t *spec_end,
+                                   uint8_t *pred, const uint8_t *forced_end, const int *bad,
+                                   int mode, int grid)
+{
+    if (prec == TEHMM_F32) {
+        if (m.NS == 1) return launch_tb<float, 1>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
+        return launch_tb<float, 2>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
+    }
+    if (m.NS == 1) return launch_tb<double, 1>(st, m, b, (const double *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
+    return launch_tb<double, 2>(st, m, b, (const double *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
+}
+
+cudaError_t tehmm_launch_tb_verify(cudaStream_t st, const TehmmBatchDev &b, uint8_t *spec_end,
+                                   const uint8_t *pred, uint8_t *forced_end, int *bad, int *nbad)
+{
+    cudaError_t e = cudaMemsetAsync(nbad, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    vit_tb_verify_kernel<<<(int)((b.nchunks + 127) / 128), 128, 0, st>>>(b, spec_end, pred, forced_end, bad, nbad);
+    return cudaGetLastError();
+}
+
+// float64 re-score of the path: 2 launches
+cudaError_t tehmm_launch_rescore(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                 const uint8_t *states, const double *ratios_em,
+                                 const double *ratios_dp, double *score_part, double *logprob)
+{
+    int warps = 4;
     int rgrid = (int)((b.nchunks + warps - 1) / warps);
     if (b.obs_bytes == 1) vit_rescore_kernel<uint8_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint8_t *)b.obs, states, ratios_em, ratios_dp, score_part);
     else if (b.obs_bytes == 2) vit_rescore_kernel<uint16_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint16_t *)b.obs, states, ratios_em, ratios_dp, score_part);

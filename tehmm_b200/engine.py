@@ -195,7 +195,7 @@ class Engine(object):
 
     def run_viterbi(self, prec, elog, d_ratios_em, d_ratios_dp, want64=True):
         torch = self.torch
-        bp = self.empty(int(self.lib.tehmm_viterbi_bp_bytes(self.ctx.handle)), torch.uint8)
+        bp = self.empty(int(self.lib.tehmm_viterbi_workspace_bytes(self.ctx.handle, prec)), torch.uint8)
         states = self.empty(self.total, torch.uint8)
         states64 = self.empty(self.total, torch.int64) if want64 else None
         logprob = self.empty(self.nseq, torch.float64)
