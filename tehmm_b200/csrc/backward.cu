@@ -77,8 +77,9 @@ template <typename T, int NS> struct XiNone {
     __device__ __forceinline__ void zero() {}
 };
 
-template <typename T, int NS, bool RATIO, bool TRANS>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1 && !TRANS) ? 3 : 1)
+// OUT = compile-time output selection (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP | TEHMM_BWD_TRANS)
+template <typename T, int NS, bool RATIO, int OUT>
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1 && !(OUT & TEHMM_BWD_TRANS)) ? 3 : 1)
 backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict__ blin,
                 const T *__restrict__ alpha, const double *__restrict__ ratios,
                 T *__restrict__ post, uint8_t *__restrict__ map_states,
@@ -92,11 +93,12 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
     T(*ws)[NP] = ws_all[warp];
     const int N = m.N;
     const unsigned Nu = (unsigned)N;
-    const bool want_post = (flags & TEHMM_BWD_POSTERIORS) != 0;
-    const bool want_map = (flags & TEHMM_BWD_MAP) != 0;
+    constexpr bool TRANS = (OUT & TEHMM_BWD_TRANS) != 0;
+    constexpr bool want_post = (OUT & TEHMM_BWD_POSTERIORS) != 0;
+    constexpr bool want_map = (OUT & TEHMM_BWD_MAP) != 0;
     const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
     const double eps32 = 1.1920928955078125e-07;
-    const double renorm_den = 1.0 + (double)N * eps32;
+    const double renorm_inv = 1.0 / (1.0 + (double)N * eps32);
 
     // row i of the transition matrix for each owned state (zero beyond N)
     MatSlice<T, NS> A;
@@ -129,6 +131,8 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
         // rows are addressed relative to t0 with 32-bit offsets
         const T *__restrict__ bb = blin + ch.t0 * N;
         const T *__restrict__ aa = alpha + ch.t0 * N;
+        T *__restrict__ pp = want_post ? post + ch.t0 * N : nullptr;
+        uint8_t *__restrict__ mm = want_map ? map_states + ch.t0 : nullptr;
         const double *__restrict__ rr = RATIO ? ratios + ch.t0 : nullptr;
 
         // w_{t+1} = b_{t+1} .* u [.* g_{t+1}] -> smem ; bp = beta'_t (unscaled).
@@ -221,7 +225,9 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
 #pragma unroll
             for (int s = 0; s < NS; ++s) { p[s] = at[s] * bp[s]; zl += p[s]; }
             const T Z = warp_sum(zl);
-            const T invZ = (T)1 / Z;
+            T invZ;
+            if constexpr (sizeof(T) == 4) invZ = __frcp_rn(Z);
+            else invZ = (T)1 / Z;
             T g[NS];
 #pragma unroll
             for (int s = 0; s < NS; ++s) g[s] = p[s] * invZ;
@@ -243,17 +249,17 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
                     for (int s = 0; s < NS; ++s) gamma0[(int64_t)ch.seq * NP + lane + 32 * s] = g[s];
                 }
             }
-            if (want_post) {
+            if constexpr (want_post) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     if (own[s]) {
                         T gv = g[s];
-                        if (renorm) gv = (T)(((double)gv + eps32) / renorm_den);
-                        post[(ch.t0 + r) * N + lane + 32 * s] = gv;
+                        if (renorm) gv = (T)(((double)gv + eps32) * renorm_inv);
+                        pp[r * Nu + (unsigned)(lane + 32 * s)] = gv;
                     }
                 }
             }
-            if (want_map) {
+            if constexpr (want_map) {
                 // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
                 T best;
                 int arg;
@@ -278,8 +284,8 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
                     }
                 }
                 if (lane == 0) {
-                    map_states[ch.t0 + r] = (uint8_t)arg;
-                    mapsum += renorm ? ((double)best + eps32) / renorm_den : (double)best;
+                    mm[r] = (uint8_t)arg;
+                    mapsum += renorm ? ((double)best + eps32) * renorm_inv : (double)best;
                 }
             }
             canonicalise<T, NS>(bp);
@@ -385,10 +391,20 @@ static cudaError_t launch_bwd(cudaStream_t st, const TehmmModelDev &m, const Teh
                               int mode, int grid)
 {
     const int th = TEHMM_WARPS_PER_CTA * 32;
-    const bool tr = (flags & TEHMM_BWD_TRANS) != 0;
-#define BWD_GO(R, TR) backward_kernel<T, NS, R, TR><<<grid, th, 0, st>>>(m, b, flags, blin, alpha, ratios, post, map_states, map_part, xi_part, xdiag_part, gamma0, start_vec, end_vec, bad, mode)
-    if (ratios) { if (tr) BWD_GO(true, true); else BWD_GO(true, false); }
-    else { if (tr) BWD_GO(false, true); else BWD_GO(false, false); }
+    const int out = flags & (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP | TEHMM_BWD_TRANS);
+#define BWD_GO(R, O) backward_kernel<T, NS, R, O><<<grid, th, 0, st>>>(m, b, flags, blin, alpha, ratios, post, map_states, map_part, xi_part, xdiag_part, gamma0, start_vec, end_vec, bad, mode)
+#define BWD_OUT(O) do { if (ratios) BWD_GO(true, O); else BWD_GO(false, O); } while (0)
+    switch (out) {
+    case 0: BWD_OUT(0); break;
+    case 1: BWD_OUT(1); break;
+    case 2: BWD_OUT(2); break;
+    case 3: BWD_OUT(3); break;
+    case 4: BWD_OUT(4); break;
+    case 5: BWD_OUT(5); break;
+    case 6: BWD_OUT(6); break;
+    default: BWD_OUT(7); break;
+    }
+#undef BWD_OUT
 #undef BWD_GO
     return cudaGetLastError();
 }

@@ -53,13 +53,21 @@ __device__ __forceinline__ void em_finish_row(const TehmmModelDev &m, int64_t t,
         return;
     }
     if (lane == 0) rowmax[t] = M;
+    const int64_t o = t * N + lane;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        const int j = lane + 32 * s;
-        if (j < N) {
+        if (lane + 32 * s < N) {
             const double d = (M > -INFINITY) ? v[s] - M : 0.0;
-            if (elog) elog[t * N + j] = (T)d;
-            if (blin) blin[t * N + j] = (sizeof(T) == 4) ? (T)expf((float)d) : (T)exp(d);
+            if (sizeof(T) == 4) {
+                // d <= 0 and the entries that matter are within a few units of 0, where
+                // ex2.approx(d*log2e) is good to ~1e-7 relative
+                const float df = (float)d;
+                if (elog) elog[o + 32 * s] = (T)df;
+                if (blin) blin[o + 32 * s] = (T)__expf(df);
+            } else {
+                if (elog) elog[o + 32 * s] = (T)d;
+                if (blin) blin[o + 32 * s] = (T)exp(d);
+            }
         }
     }
 }

@@ -29,6 +29,7 @@
 #include "scan.cuh"
 
 #define VIT_U 4
+#define TB_PF 12   // delta rows in flight ahead of the traceback walk
 
 template <typename T, int NS, bool RATIO>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
@@ -304,6 +305,56 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
             return warp_argmax_first<T, NS>(cand, lane);
         };
 
+        // Walk rows hi, hi-1, ..., lo+1 (state at `hi` known), calling emit(row, st)
+        // for every visited row and finishing with st = state at row `lo`.
+        // delta rows are prefetched TB_PF rows ahead of the (latency-bound) walk.
+        auto walk = [&](unsigned hi, unsigned lo, int st, bool emit_rows) -> int {
+            auto emit = [&](unsigned row, int state) {
+                if (emit_rows && lane == 0) {
+                    if (states) states[tbase + row] = (uint8_t)state;
+                    if (states64) states64[tbase + row] = state;
+                }
+            };
+            unsigned row = hi;
+            // full groups of TB_PF rows, unconditional so the ring stays in registers:
+            // cur[q] = delta[row-1-q]; the next group's rows are in flight meanwhile
+            if (row >= lo + 2 * TB_PF) {
+                T nxt[TB_PF][NS];
+#pragma unroll
+                for (int q = 0; q < TB_PF; ++q) load_d(row - 1 - (unsigned)q, nxt[q]);
+                while (row >= lo + 2 * TB_PF) {
+                    T cur[TB_PF][NS];
+#pragma unroll
+                    for (int q = 0; q < TB_PF; ++q) {
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) cur[q][s] = nxt[q][s];
+                    }
+#pragma unroll
+                    for (int q = 0; q < TB_PF; ++q) load_d(row - 1 - TB_PF - (unsigned)q, nxt[q]);
+#pragma unroll
+                    for (int q = 0; q < TB_PF; ++q) {
+                        emit(row - (unsigned)q, st);
+                        st = back(row - (unsigned)q, st, cur[q]);
+                    }
+                    row -= TB_PF;
+                }
+                // nxt holds the rows of one more full group
+#pragma unroll
+                for (int q = 0; q < TB_PF; ++q) {
+                    emit(row - (unsigned)q, st);
+                    st = back(row - (unsigned)q, st, nxt[q]);
+                }
+                row -= TB_PF;
+            }
+            for (; row > lo; --row) {
+                T dc[NS];
+                load_d(row - 1, dc);
+                emit(row, st);
+                st = back(row, st, dc);
+            }
+            return st;
+        };
+
         int st;
         if (mode == 1) {
             st = forced_end[ci];
@@ -319,38 +370,18 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
             T dv[NS];
             load_d(rq, dv);
             st = warp_argmax_first<T, NS>(dv, lane);
-            T dn[NS];
-            load_d(rq - 1, dn);
-            for (unsigned row = rq; row > rlast; --row) {
-                T dc[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) dc[s] = dn[s];
-                if (row >= 2) load_d(row - 2, dn);
-                st = back(row, st, dc);
-            }
+            st = walk(rq, rlast, st, false);
         }
         if (lane == 0) spec_end[ci] = (uint8_t)st;
 
-        // walk the chunk: rows rlast ... rfirst, then the predecessor of row rfirst
-        {
-            T dn[NS];
-            if (rlast >= 1) load_d(rlast - 1, dn);
-            for (unsigned row = rlast;; --row) {
-                if (lane == 0) {
-                    if (states) states[tbase + row] = (uint8_t)st;
-                    if (states64) states64[tbase + row] = st;
-                }
-                if (row == 0) break;                       // chunk starts its sequence
-                T dc[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) dc[s] = dn[s];
-                if (row >= 2) load_d(row - 2, dn);
-                st = back(row, st, dc);
-                if (row == rfirst) {                       // st is now the state at t0-1
-                    if (lane == 0) pred[ci] = (uint8_t)st;
-                    break;
-                }
-            }
+        // walk the chunk: rows rlast ... rfirst; when the chunk has a left neighbour
+        // (rfirst == 1) the walk ends on row 0 = t0-1, whose state goes to `pred`
+        st = walk(rlast, 0, st, true);
+        if (rfirst == 1) {
+            if (lane == 0) pred[ci] = (uint8_t)st;
+        } else if (lane == 0) {
+            if (states) states[tbase] = (uint8_t)st;
+            if (states64) states64[tbase] = st;
         }
     }
 }
