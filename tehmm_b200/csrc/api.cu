@@ -32,6 +32,9 @@ cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const Tehm
 cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, double *, double *, int, int);
 size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
 cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
+cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int);
+cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int);
+int tehmm_tile_warps(void);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
 
 // ---------------------------------------------------------------- errors
@@ -68,7 +71,9 @@ struct tehmm_ctx {
     cudaStream_t own_stream = nullptr;
     int64_t launches = 0;
     int64_t opt_chunk_tiles = 0, opt_warmup = 0, opt_max_repair = 0;
+    int64_t opt_tile = 1, opt_fine_len = 0;   // tensor-core tile kernels on / fine chunk length (0 = auto)
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
+    int64_t stat_tile_passes = 0;
     int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0, stat_bad_tb = 0, stat_repair_tb = 0;
     int *h_nbad = nullptr;            // pinned
     // model
@@ -77,7 +82,8 @@ struct tehmm_ctx {
     void *model_blob = nullptr;
     // batch
     bool has_batch = false;
-    TehmmBatchDev b{};
+    TehmmBatchDev b{};            // coarse partition: one chunk per warp (forward.cu, backward.cu, viterbi.cu)
+    TehmmBatchDev bf{};           // fine partition: sixteen chunks per warp (tile.cu)
     void *batch_blob = nullptr;
     int *d_seq_flag = nullptr;
     int64_t max_tiles_per_chunk = 1;
@@ -155,6 +161,8 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     if (!strcmp(name, "chunk_tiles")) c->opt_chunk_tiles = v;
     else if (!strcmp(name, "warmup")) c->opt_warmup = v;
     else if (!strcmp(name, "max_repair")) c->opt_max_repair = v;
+    else if (!strcmp(name, "tile")) c->opt_tile = v;
+    else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -173,6 +181,8 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "repair_passes_traceback")) return c->stat_repair_tb;
     if (!strcmp(name, "sms")) return c->sms;
     if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
+    if (!strcmp(name, "fine_chunks")) return c->has_batch ? c->bf.nchunks : 0;
+    if (!strcmp(name, "tile_passes")) return c->stat_tile_passes;
     if (!strcmp(name, "warmup")) return c->has_batch ? c->b.warmup : 0;
     return -1;
 }
@@ -431,11 +441,18 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
         tpc = std::max<int64_t>(4, std::min<int64_t>(tpc, 2048));
     }
     const int64_t L = tpc * TEHMM_TILE;
-    std::vector<TehmmChunk> chunks;
-    std::vector<int64_t> seq_chunk0(nseq + 1);
+    // fine partition for the tile kernels: one 16-chunk tile per resident warp
+    int64_t Lf = c->opt_fine_len;
+    if (Lf <= 0) {
+        const int64_t target = (int64_t)c->sms * tehmm_tile_warps() * 16;
+        Lf = std::max<int64_t>(64, (total + target - 1) / target);
+    }
+    std::vector<TehmmChunk> chunks, fchunks;
+    std::vector<int64_t> seq_chunk0(nseq + 1), seq_fchunk0(nseq + 1);
     int64_t tile_base = 0;
     for (int64_t s = 0; s < nseq; ++s) {
         seq_chunk0[s] = (int64_t)chunks.size();
+        seq_fchunk0[s] = (int64_t)fchunks.size();
         const int64_t s0 = h_offsets[s], s1 = h_offsets[s + 1];
         for (int64_t t0 = s0; t0 < s1; t0 += L) {
             TehmmChunk ch;
@@ -446,15 +463,27 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
             tile_base += ch.ntiles;
             chunks.push_back(ch);
         }
+        for (int64_t t0 = s0; t0 < s1; t0 += Lf) {
+            TehmmChunk ch;
+            ch.t0 = t0; ch.t1 = std::min(s1, t0 + Lf); ch.s0 = s0; ch.s1 = s1;
+            ch.seq = (int32_t)s;
+            ch.ntiles = 0; ch.tile0 = 0;
+            fchunks.push_back(ch);
+        }
     }
     seq_chunk0[nseq] = (int64_t)chunks.size();
-    const int64_t nchunks = (int64_t)chunks.size();
+    seq_fchunk0[nseq] = (int64_t)fchunks.size();
+    const int64_t nchunks = (int64_t)chunks.size(), nfchunks = (int64_t)fchunks.size();
     size_t o_off = 0, o_sc = align_up(o_off + (size_t)(nseq + 1) * 8), o_ch = align_up(o_sc + (size_t)(nseq + 1) * 8);
-    size_t bytes = align_up(o_ch + (size_t)nchunks * sizeof(TehmmChunk));
+    size_t o_fsc = align_up(o_ch + (size_t)nchunks * sizeof(TehmmChunk));
+    size_t o_fch = align_up(o_fsc + (size_t)(nseq + 1) * 8);
+    size_t bytes = align_up(o_fch + (size_t)nfchunks * sizeof(TehmmChunk));
     std::vector<unsigned char> h(bytes, 0);
     memcpy(&h[o_off], h_offsets, (size_t)(nseq + 1) * 8);
     memcpy(&h[o_sc], seq_chunk0.data(), (size_t)(nseq + 1) * 8);
     memcpy(&h[o_ch], chunks.data(), (size_t)nchunks * sizeof(TehmmChunk));
+    memcpy(&h[o_fsc], seq_fchunk0.data(), (size_t)(nseq + 1) * 8);
+    memcpy(&h[o_fch], fchunks.data(), (size_t)nfchunks * sizeof(TehmmChunk));
     CU(cudaStreamSynchronize(c->stream));
     if (c->batch_blob) { cudaFree(c->batch_blob); c->batch_blob = nullptr; }
     if (c->d_seq_flag) { cudaFree(c->d_seq_flag); c->d_seq_flag = nullptr; }
@@ -468,6 +497,10 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
     b.seq_off = (const int64_t *)(d + o_off); b.seq_chunk0 = (const int64_t *)(d + o_sc);
     b.chunks = (const TehmmChunk *)(d + o_ch);
     b.warmup = (int)(c->opt_warmup > 0 ? c->opt_warmup : 64);
+    c->bf = b;
+    c->bf.nchunks = nfchunks;
+    c->bf.seq_chunk0 = (const int64_t *)(d + o_fsc);
+    c->bf.chunks = (const TehmmChunk *)(d + o_fch);
     c->max_tiles_per_chunk = tpc;
     c->has_batch = true;
     return TEHMM_OK;
@@ -490,13 +523,14 @@ static Scratch carve(const tehmm_ctx *c, int prec)
 {
     const size_t ts = prec == TEHMM_F32 ? 4 : 8;
     const size_t NP = (size_t)c->m.NP, nc = (size_t)c->b.nchunks;
+    const size_t nb = (size_t)std::max(c->b.nchunks, c->bf.nchunks);   // either partition
     Scratch s;
     size_t o = 0;
-    s.start_vec = o; o = align_up(o + nc * NP * ts);
-    s.end_vec = o; o = align_up(o + nc * NP * ts);
-    s.cscale = o; o = align_up(o + nc * 8);
-    s.part_a = o; o = align_up(o + nc * 8);
-    s.bad = o; o = align_up(o + nc * 4);
+    s.start_vec = o; o = align_up(o + nb * NP * ts);
+    s.end_vec = o; o = align_up(o + nb * NP * ts);
+    s.cscale = o; o = align_up(o + nb * 8);
+    s.part_a = o; o = align_up(o + nb * 8);
+    s.bad = o; o = align_up(o + nb * 4);
     s.nbad = o; o = align_up(o + 4);
     s.xi = o; o = align_up(o + nc * NP * NP * ts);
     s.xdiag = o; o = align_up(o + nc * NP * ts);
@@ -580,10 +614,20 @@ static double tolerance(int prec, bool log_space)
 
 // The warm-up length adapts: if more than 2% of the chunks of a pass had to be
 // repaired, later passes of this context speculate twice as far back.
-static void adapt_warmup(tehmm_ctx *c, int first_pass_bad)
+static void adapt_warmup(tehmm_ctx *c, int first_pass_bad, int64_t nchunks)
 {
     if (c->opt_warmup > 0) return;
-    if ((int64_t)first_pass_bad * 50 > c->b.nchunks && c->b.warmup < 4096) c->b.warmup *= 2;
+    if ((int64_t)first_pass_bad * 50 > nchunks && c->b.warmup < 4096) {
+        c->b.warmup *= 2;
+        c->bf.warmup = c->b.warmup;
+    }
+}
+
+// The tensor-core tile kernels (tile.cu) take the fp32, N <= 32, N even, no
+// segment-ratio case; everything else runs one chunk per warp.
+static bool use_tile(const tehmm_ctx *c, int prec, const double *d_ratios)
+{
+    return c->opt_tile != 0 && prec == TEHMM_F32 && c->m.NS == 1 && (c->m.N & 1) == 0 && d_ratios == nullptr;
 }
 
 int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *d_rowmax,
@@ -597,23 +641,32 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     double *cs = (double *)(w + s.cscale), *lkap = (double *)(w + s.part_a);
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     const int grid = scan_grid(c);
-    CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 0, grid));
+    const bool tile = use_tile(c, prec, d_ratios);
+    const TehmmBatchDev &PB = tile ? c->bf : c->b;       // the partition this pass runs on
+    auto launch = [&](int mode) -> cudaError_t {
+        if (tile) {
+            c->stat_tile_passes += 1;
+            return tehmm_launch_forward_tile(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha, (float *)sv, (float *)ev, cs, bad, mode, c->sms);
+        }
+        return tehmm_launch_forward(st, c->m, PB, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, mode, grid);
+    };
+    CU(launch(0));
     c->launches += 1;
     const double tol = tolerance(prec, false);
-    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, +1, 1, bad, nbad, lkap));
+        CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, +1, 1, bad, nbad, lkap));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
-        if (pass == 0) adapt_warmup(c, nb);
+        if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "forward repair did not converge (%d chunks left)", nb);
         c->stat_repair_fwd += 1; c->stat_bad_fwd += nb;
-        CU(tehmm_launch_forward(st, c->m, c->b, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, 1, grid));
+        CU(launch(1));
         c->launches += 1;
     }
-    CU(tehmm_launch_forward_logprob(st, c->b, prec, c->m.NP, ev, cs, lkap, d_logprob));
+    CU(tehmm_launch_forward_logprob(st, PB, prec, c->m.NP, ev, cs, lkap, d_logprob));
     c->launches += 1;
     return TEHMM_OK;
 }
@@ -634,23 +687,32 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     void *xi = w + s.xi, *xd = w + s.xdiag, *g0 = w + s.gamma0;
     const int grid = scan_grid(c);
-    CU(tehmm_launch_backward(st, c->m, c->b, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, 0, grid));
+    const bool tile = use_tile(c, prec, d_ratios) && !(flags & TEHMM_BWD_TRANS);
+    const TehmmBatchDev &PB = tile ? c->bf : c->b;
+    auto launch = [&](int mode) -> cudaError_t {
+        if (tile) {
+            c->stat_tile_passes += 1;
+            return tehmm_launch_backward_tile(st, c->m, PB, flags, (const float *)d_blin, (const float *)d_alpha, (float *)d_post, d_map_states, mp, (float *)sv, (float *)ev, bad, mode, c->sms);
+        }
+        return tehmm_launch_backward(st, c->m, PB, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, mode, grid);
+    };
+    CU(launch(0));
     c->launches += 1;
     const double tol = tolerance(prec, false);
-    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, -1, 1, bad, nbad, nullptr));
+        CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, -1, 1, bad, nbad, nullptr));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
-        if (pass == 0) adapt_warmup(c, nb);
+        if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "backward repair did not converge (%d chunks left)", nb);
         c->stat_repair_bwd += 1; c->stat_bad_bwd += nb;
-        CU(tehmm_launch_backward(st, c->m, c->b, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, 1, grid));
+        CU(launch(1));
         c->launches += 1;
     }
-    if (flags & TEHMM_BWD_MAP) { CU(tehmm_launch_map_reduce(st, c->b, mp, d_map_score)); c->launches += 1; }
+    if (flags & TEHMM_BWD_MAP) { CU(tehmm_launch_map_reduce(st, PB, mp, d_map_score)); c->launches += 1; }
     if (flags & TEHMM_BWD_TRANS) { CU(tehmm_launch_trans_reduce(st, c->m, c->b, prec, xi, xd, g0, d_start_trans)); c->launches += 1; }
     return TEHMM_OK;
 }
@@ -681,6 +743,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     uint8_t *spec_end = (uint8_t *)(w + s.cmap), *pred = spec_end + c->b.nchunks, *forced = pred + c->b.nchunks;
     const int grid = scan_grid(c);
+    const TehmmBatchDev &PB = c->b;
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     // ---- DP: delta lattice, chunk starts speculated / verified / repaired
     CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid));
@@ -691,7 +754,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
-        if (pass == 0) adapt_warmup(c, nb);
+        if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
         c->stat_repair_vit += 1; c->stat_bad_vit += nb;
@@ -707,7 +770,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
-        if (pass == 0) adapt_warmup(c, nb);
+        if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "traceback repair did not converge (%d chunks left)", nb);
         c->stat_repair_tb += 1; c->stat_bad_tb += nb;

@@ -374,13 +374,12 @@ __global__ void trans_reduce_kernel(TehmmModelDev m, TehmmBatchDev b, const T *_
 __global__ void map_reduce_kernel(TehmmBatchDev b, const double *__restrict__ map_part,
                                   double *__restrict__ map_score)
 {
-    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (s >= b.nseq) return;
+    // one block per sequence
+    const int64_t s = blockIdx.x;
     double acc = 0.0;
-    for (int64_t c = b.seq_chunk0[s] + lane; c < b.seq_chunk0[s + 1]; c += 32) acc += map_part[c];
-    acc = warp_sum(acc);
-    if (lane == 0) map_score[s] = acc;
+    for (int64_t c = b.seq_chunk0[s] + threadIdx.x; c < b.seq_chunk0[s + 1]; c += blockDim.x) acc += map_part[c];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) map_score[s] = acc;
 }
 
 template <typename T, int NS>
@@ -439,8 +438,7 @@ cudaError_t tehmm_launch_trans_reduce(cudaStream_t st, const TehmmModelDev &m, c
 cudaError_t tehmm_launch_map_reduce(cudaStream_t st, const TehmmBatchDev &b, const double *map_part,
                                     double *map_score)
 {
-    int warps = 4;
-    int grid = (int)((b.nseq + warps - 1) / warps);
-    map_reduce_kernel<<<grid, warps * 32, 0, st>>>(b, map_part, map_score);
+    const int th = b.nchunks / b.nseq >= 256 ? 256 : 64;
+    map_reduce_kernel<<<(int)b.nseq, th, 0, st>>>(b, map_part, map_score);
     return cudaGetLastError();
 }

@@ -292,18 +292,16 @@ __global__ void forward_logprob_kernel(TehmmBatchDev b, int NP, const T *__restr
                                        const double *__restrict__ logkappa,
                                        double *__restrict__ logprob)
 {
-    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (s >= b.nseq) return;
-    int64_t c0 = b.seq_chunk0[s], c1 = b.seq_chunk0[s + 1];
-    if (c1 <= c0) { if (lane == 0) logprob[s] = 0.0; return; }
+    // one block per sequence
+    const int64_t s = blockIdx.x;
+    const int64_t c0 = b.seq_chunk0[s], c1 = b.seq_chunk0[s + 1];
+    if (c1 <= c0) { if (threadIdx.x == 0) logprob[s] = 0.0; return; }
     double acc = 0.0;
-    for (int64_t c = c0 + lane; c < c1; c += 32) acc += cscale[c] - logkappa[c];
-    acc = warp_sum(acc);
-    double tail = 0.0;
-    for (int j = lane; j < NP; j += 32) tail += (double)end_vec[(c1 - 1) * NP + j];
-    tail = warp_sum(tail);
-    if (lane == 0) logprob[s] = acc + log(tail);
+    for (int64_t c = c0 + threadIdx.x; c < c1; c += blockDim.x) acc += cscale[c] - logkappa[c];
+    acc = block_sum(acc);
+    double tail = threadIdx.x < NP ? (double)end_vec[(c1 - 1) * NP + threadIdx.x] : 0.0;
+    tail = block_sum(tail);
+    if (threadIdx.x == 0) logprob[s] = acc + log(tail);
 }
 
 template <typename T, int NS>
@@ -350,11 +348,10 @@ cudaError_t tehmm_launch_forward_logprob(cudaStream_t st, const TehmmBatchDev &b
                                          const void *end_vec, const double *cscale,
                                          const double *logkappa, double *logprob)
 {
-    int warps = 4;
-    int grid = (int)((b.nseq + warps - 1) / warps);
+    const int th = b.nchunks / b.nseq >= 256 ? 256 : 64;
     if (prec == TEHMM_F32)
-        forward_logprob_kernel<float><<<grid, warps * 32, 0, st>>>(b, NP, (const float *)end_vec, cscale, logkappa, logprob);
+        forward_logprob_kernel<float><<<(int)b.nseq, th, 0, st>>>(b, NP, (const float *)end_vec, cscale, logkappa, logprob);
     else
-        forward_logprob_kernel<double><<<grid, warps * 32, 0, st>>>(b, NP, (const double *)end_vec, cscale, logkappa, logprob);
+        forward_logprob_kernel<double><<<(int)b.nseq, th, 0, st>>>(b, NP, (const double *)end_vec, cscale, logkappa, logprob);
     return cudaGetLastError();
 }

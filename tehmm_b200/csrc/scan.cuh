@@ -44,6 +44,20 @@ template <typename T> __device__ __forceinline__ T warp_max(T v)
     return v;
 }
 
+// block-wide sum (blockDim.x a multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v)
+{
+    __shared__ double part[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) part[w] = v;
+    __syncthreads();
+    v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
 // y[s] = sum_i xs[i] * c[s][i]   (sum-product semiring)
 template <typename T, int NS>
 __device__ __forceinline__ void matvec_sum(const T *xs, const T (&c)[NS][32 * NS], T (&y)[NS])

@@ -1,0 +1,575 @@
+// Tensor-core forward / backward passes: SIXTEEN chunks per warp.
+// (hmm.py:678-729 -> _hmm.pyx:120-198; basehmm.py:265-272,357-358)
+//
+// forward.cu / backward.cu give one chunk of the time axis to one warp and do
+// the N x N mat-vec with 16 FFMA2 + 8 LDS.128 per step: ~70-100 issue slots per
+// time step, which is what bounds them.  Here a warp owns a TILE of 16 chunks
+// and advances all of them one time step with one 16 x 32 x 32 matrix product
+//     X'[chunk][j] = sum_i X[chunk][i] A[i][j]
+// on the tensor cores (mma.sync.m16n8k8 TF32, fp32 accumulate).  TF32 alone
+// (10-bit mantissa) is far outside the 1e-5 contract, so every product is the
+// usual three-term split  x_hi A_hi + x_lo A_hi + x_hi A_lo  (x = x_hi + x_lo
+// exactly, each part a TF32 number): 48 MMAs per tile step = 3 per chunk step,
+// ~2^-21 relative error per step, and the filter does not accumulate it.
+//
+// Register layout (g = lane/4, q = lane%4): the lane holds, for tile rows g and
+// g+8, the EIGHT CONSECUTIVE states 8q .. 8q+7.  The accumulator fragment of
+// n-tile nt (columns n = 2q, 2q+1) is mapped to states 8q+2nt, 8q+2nt+1, so
+//   * a row of b / alpha / posteriors is read and written as four 8-byte
+//     accesses per lane, a quad covering the whole 4N-byte row;
+//   * the accumulator fragment of n-tile kt IS the A-operand fragment of
+//     k-tile kt of the next step (k-slot q <-> state 8q+2kt, slot q+4 <-> state
+//     8q+2kt+1): the recursion never leaves registers, no shuffles, no smem.
+// The transition matrix lives in registers as B-operand fragments permuted
+// accordingly (64 registers: hi and lo parts).
+//
+// Chunks of one tile run in lock step on a common clock k: row r processes
+// time t0_r - W + k (forward) or t1_r - 1 + W - k (backward), W = warm-up
+// length, so the speculative warm-up is k < W for every row and outputs start
+// at k = W.  Rows that start late (sequence start inside the warm-up window),
+// end early (ragged chunks) or are not selected by a repair pass are masked:
+// their loads return zeros and their stores are predicated off.
+//
+// Speculate / verify / repair, canonical power-of-two scaling, start_vec /
+// end_vec / cscale conventions: exactly those of forward.cu and backward.cu,
+// so verify_kernel, forward_logprob_kernel and map_reduce_kernel are shared and
+// either implementation can consume the other's alpha lattice.
+//
+// Requires fp32, N <= 32 and N even (8-byte aligned rows), no segment ratios;
+// everything else takes the one-chunk-per-warp kernels.
+// Algorithmic HBM bytes per step: forward 4N read + 4N written, backward 8N read
+// (+4N posteriors, +1 MAP state).
+#include "scan.cuh"
+
+#define TILE_WARPS 8
+#define FWD_RING 4     // rows of b in flight per tile row (time steps)
+#define BWD_RING 2     // rows of b and alpha in flight per tile row
+
+struct TransFrag {
+    uint32_t hi[4][4][2];   // [k-tile][n-tile][b0,b1]
+    uint32_t lo[4][4][2];
+};
+
+__device__ __forceinline__ uint32_t tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                         uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// B-operand fragments of the (zero padded, 32 x 32) linear transition matrix.
+// forward:  D[r][j] = sum_i X[r][i] A[i][j]   -> B[k = i][n = j] = A[i][j]
+// backward: D[r][i] = sum_j W[r][j] A[i][j]   -> B[k = j][n = i] = A[i][j]
+template <bool BACKWARD>
+__device__ __forceinline__ void load_trans(const TehmmModelDev &m, int g, int q, TransFrag &A)
+{
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int sn = 8 * (g >> 1) + 2 * nt + (g & 1);   // state of output column n = g
+            const int sk = 8 * q + 2 * kt;                    // state of k-slot q (slot q+4: sk+1)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double v = BACKWARD ? m.lin_trans[(int64_t)sn * 32 + sk + e]
+                                          : m.lin_trans[(int64_t)(sk + e) * 32 + sn];
+                const uint32_t h = tf32_rna((float)v);
+                A.hi[kt][nt][e] = h;
+                A.lo[kt][nt][e] = tf32_rna((float)(v - (double)__uint_as_float(h)));
+            }
+        }
+    }
+}
+
+// d = x * A for the 16 x 32 tile; x[r][i] / d[r][i] <-> tile row g + 8r, state 8q + i
+__device__ __forceinline__ void tile_matmul(const float (&x)[2][8], const TransFrag &A, float (&d)[2][8])
+{
+    // x = xh + xl exactly: xh = x truncated to TF32 (the tensor core reads only the
+    // top 19 bits, so x itself is passed), xl = the remainder rounded to TF32.
+    // (cvt.rna.tf32.f32 expands to four instructions on sm_100a; this is three per value.)
+    uint32_t xh[2][8], xl[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            xh[r][i] = __float_as_uint(x[r][i]);
+            const float rem = x[r][i] - __uint_as_float(xh[r][i] & 0xffffe000u);
+            xl[r][i] = __float_as_uint(rem) + 0x1000u;
+        }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+    // small terms first, the n-tiles interleaved (four independent accumulator chains)
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            mma_tf32(acc[nt], xl[0][2 * kt], xl[1][2 * kt], xl[0][2 * kt + 1], xl[1][2 * kt + 1],
+                     A.hi[kt][nt][0], A.hi[kt][nt][1]);
+    }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            mma_tf32(acc[nt], xh[0][2 * kt], xh[1][2 * kt], xh[0][2 * kt + 1], xh[1][2 * kt + 1],
+                     A.lo[kt][nt][0], A.lo[kt][nt][1]);
+    }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            mma_tf32(acc[nt], xh[0][2 * kt], xh[1][2 * kt], xh[0][2 * kt + 1], xh[1][2 * kt + 1],
+                     A.hi[kt][nt][0], A.hi[kt][nt][1]);
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        d[0][2 * nt] = acc[nt][0]; d[0][2 * nt + 1] = acc[nt][1];
+        d[1][2 * nt] = acc[nt][2]; d[1][2 * nt + 1] = acc[nt][3];
+    }
+}
+
+// maximum / sum over the 32 states of a tile row (the four lanes of a quad)
+__device__ __forceinline__ float quad_max(float v)
+{
+    v = fmaxf(v, __shfl_xor_sync(TEHMM_FULL, v, 1));
+    return fmaxf(v, __shfl_xor_sync(TEHMM_FULL, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v)
+{
+    v += __shfl_xor_sync(TEHMM_FULL, v, 1);
+    return v + __shfl_xor_sync(TEHMM_FULL, v, 2);
+}
+__device__ __forceinline__ float max8(const float (&v)[8])
+{
+    return fmaxf(fmax3(fmax3(v[0], v[1], v[2]), v[3], v[4]), fmax3(v[5], v[6], v[7]));
+}
+
+// canonicalise (scan.cuh) for a tile row: exact power-of-two scaling that puts
+// the row maximum into [1,2).  Returns the exponent taken out.
+__device__ __forceinline__ int row_scale(float (&v)[8])
+{
+    const unsigned mb = __float_as_uint(quad_max(max8(v)));
+    const unsigned e = mb >> 23;
+    float sc;
+    int sh;
+    if (__builtin_expect(e - 1u < 253u, 1)) {
+        sc = __uint_as_float((254u - e) << 23);
+        sh = (int)e - 127;
+    } else if (mb == 0u || e >= 254u) {          // dead / masked row, inf, nan
+        sc = 1.f;
+        sh = 0;
+    } else {                                     // subnormal maximum: lift, finish next step
+        sc = 18446744073709551616.f;             // 2^64
+        sh = -64;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= sc;
+    return sh;
+}
+
+__device__ __forceinline__ void load_vec32(const float *p, float (&v)[8])
+{
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    const float4 c = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+}
+__device__ __forceinline__ void store_vec32(float *p, const float (&v)[8])
+{
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// One lattice row slice (states 8q..8q+7) as 8-byte accesses.  p points at the
+// ROW; coff[pp] is the column of pair pp, or an existing column of the row for
+// pairs beyond N: whatever finite value they read is multiplied by the exact
+// zero the padded states carry, so loads need no column predicate.
+__device__ __forceinline__ void load_row8(const float *p, bool on, const int (&coff)[4], float (&v)[8])
+{
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+        float2 t = make_float2(0.f, 0.f);
+        if (on) t = __ldg(reinterpret_cast<const float2 *>(p + coff[pp]));
+        v[2 * pp] = t.x;
+        v[2 * pp + 1] = t.y;
+    }
+}
+__device__ __forceinline__ void store_row8(float *p, bool on, const bool (&colok)[4], const float (&v)[8])
+{
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp)
+        if (on && colok[pp]) *reinterpret_cast<float2 *>(p + 2 * pp) = make_float2(v[2 * pp], v[2 * pp + 1]);
+}
+
+#define TILE_NEVER 0x7fffffff
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
+                const double *__restrict__ rowmax, float *__restrict__ alpha,
+                float *__restrict__ start_vec, float *__restrict__ end_vec,
+                double *__restrict__ cscale, const int *__restrict__ bad, int mode)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int N = m.N, W = b.warmup;
+
+    TransFrag A;
+    load_trans<false>(m, g, q, A);
+    float pi[8], ones[8];
+    bool colok[4];
+    int coff[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        pi[i] = (float)m.lin_start[8 * q + i];
+        ones[i] = 8 * q + i < N ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+        colok[pp] = 8 * q + 2 * pp < N;
+        coff[pp] = colok[pp] ? 8 * q + 2 * pp : 0;
+    }
+
+    const int64_t ngroups = (b.nchunks + 15) / 16;
+    for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
+         gi += (int64_t)gridDim.x * TILE_WARPS) {
+        // ---- schedule of the lane's two tile rows
+        int ks[2], ke[2];
+        int64_t off[2], cid[2];
+        bool first[2], pred[2];
+        int kb = TILE_NEVER, kmax = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t c = gi * 16 + g + 8 * r;
+            cid[r] = c;
+            bool valid = c < b.nchunks;
+            if (valid && mode == 1) valid = bad[c] != 0;
+            ks[r] = TILE_NEVER; ke[r] = 0; off[r] = 0; first[r] = false; pred[r] = false;
+            if (valid) {
+                const TehmmChunk ch = b.chunks[c];
+                const int64_t dist = ch.t0 - ch.s0;
+                pred[r] = dist > 0;
+                if (dist == 0) { ks[r] = W; first[r] = true; }
+                else if (mode == 1) ks[r] = W;                       // from the true vector at t0-1
+                else if (dist <= W) { ks[r] = W - (int)dist; first[r] = true; }
+                else ks[r] = 0;                                      // speculate from a flat vector
+                ke[r] = W + (int)(ch.t1 - ch.t0);
+                off[r] = (ch.t0 - W) * N + 8 * q;
+                kb = min(kb, ks[r]);
+                kmax = max(kmax, ke[r]);
+            }
+        }
+        kb = __reduce_min_sync(TEHMM_FULL, kb);
+        kmax = __reduce_max_sync(TEHMM_FULL, kmax);
+        if (kmax <= 0) continue;
+
+        float x[2][8];
+        int esum[2] = {0, 0};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[r][i] = 0.f;
+
+        auto load_b = [&](int k, float (&bt)[2][8]) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                load_row8(blin + off[r] - 8 * q + (int64_t)k * N, k >= ks[r] && k < ke[r], coff, bt[r]);
+        };
+        auto step = [&](int k, const float (&bt)[2][8]) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (k == ks[r]) {                                    // the row starts here
+                    if (mode == 1 && !first[r]) load_vec32(start_vec + cid[r] * 32 + 8 * q, x[r]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[r][i] = ones[i];
+                    }
+                }
+            }
+            float d[2][8];
+            tile_matmul(x, A, d);
+            int sh[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (k == ks[r] && first[r]) {                        // alpha_0 = pi .* b_0
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[r][i] = pi[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[r][i] = d[r][i] * bt[r][i];
+                sh[r] = row_scale(x[r]);
+            }
+            if (k >= W) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    esum[r] += sh[r];
+                    if (alpha) store_row8(alpha + off[r] + (int64_t)k * N, k >= ks[r] && k < ke[r], colok, x[r]);
+                }
+            } else if (k == W - 1 && mode == 0) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (pred[r] && k >= ks[r] && k < ke[r]) store_vec32(start_vec + cid[r] * 32 + 8 * q, x[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, x[r]);
+        };
+
+        float ring[FWD_RING][2][8];
+#pragma unroll
+        for (int u = 0; u < FWD_RING; ++u) load_b(kb + u, ring[u]);
+        for (int k0 = kb; k0 < kmax; k0 += FWD_RING) {
+#pragma unroll
+            for (int u = 0; u < FWD_RING; ++u) {
+                float bt[2][8];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bt[r][i] = ring[u][r][i];
+                load_b(k0 + u + FWD_RING, ring[u]);
+                step(k0 + u, bt);
+            }
+        }
+
+        // log of everything taken out of each chunk: exponents and row maxima
+        for (int rr = 0; rr < 16; ++rr) {
+            const int64_t c = gi * 16 + rr;
+            if (c >= b.nchunks) break;
+            if (mode == 1 && !bad[c]) continue;
+            const TehmmChunk ch = b.chunks[c];
+            double ms = 0.0;
+            for (int64_t tt = ch.t0 + lane; tt < ch.t1; tt += 32) ms += rowmax[tt];
+            ms = warp_sum(ms);
+            const int e = __shfl_sync(TEHMM_FULL, (rr & 8) ? esum[1] : esum[0], (rr & 7) * 4);
+            if (lane == 0) cscale[c] = (double)e * 0.6931471805599453094 + ms;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward
+// OUT = TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP (compile time)
+template <int OUT>
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__restrict__ blin,
+                const float *__restrict__ alpha, float *__restrict__ post,
+                uint8_t *__restrict__ map_states, double *__restrict__ map_part,
+                float *__restrict__ start_vec, float *__restrict__ end_vec,
+                const int *__restrict__ bad, int mode)
+{
+    constexpr bool want_post = (OUT & TEHMM_BWD_POSTERIORS) != 0;
+    constexpr bool want_map = (OUT & TEHMM_BWD_MAP) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int N = m.N, W = b.warmup;
+    const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
+    const float eps32 = 1.1920928955078125e-07f;
+    const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
+    const float renorm_invf = (float)renorm_inv;
+
+    TransFrag A;
+    load_trans<true>(m, g, q, A);
+    float ones[8];
+    bool colok[4];
+    int coff[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ones[i] = 8 * q + i < N ? 1.f : 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp) {
+        colok[pp] = 8 * q + 2 * pp < N;
+        coff[pp] = colok[pp] ? 8 * q + 2 * pp : 0;
+    }
+
+    const int64_t ngroups = (b.nchunks + 15) / 16;
+    for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
+         gi += (int64_t)gridDim.x * TILE_WARPS) {
+        // ---- schedule: at clock k the row is at time t1 - 1 + W - k
+        int ks[2], ke[2], kbv[2];      // kbv: first clock whose b_{t+1} exists
+        int64_t off[2], trow[2], cid[2];
+        bool exact[2], succ[2];
+        int kb = TILE_NEVER, kmax = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t c = gi * 16 + g + 8 * r;
+            cid[r] = c;
+            bool valid = c < b.nchunks;
+            if (valid && mode == 1) valid = bad[c] != 0;
+            ks[r] = TILE_NEVER; ke[r] = 0; kbv[r] = TILE_NEVER; off[r] = 0; trow[r] = 0;
+            exact[r] = false; succ[r] = false;
+            if (valid) {
+                const TehmmChunk ch = b.chunks[c];
+                const int64_t rem = ch.s1 - ch.t1;                   // steps of the sequence after the chunk
+                succ[r] = rem > 0;
+                if (rem == 0) { ks[r] = W; exact[r] = true; }        // beta_{T-1}: _hmm.pyx:179 (1/N applied later)
+                else if (mode == 1) ks[r] = W;                       // from the true vector at t1
+                else if (rem <= W) { ks[r] = W - (int)rem; exact[r] = true; }
+                else ks[r] = 0;                                      // speculate from a flat vector
+                kbv[r] = exact[r] ? ks[r] + 1 : ks[r];
+                ke[r] = W + (int)(ch.t1 - ch.t0);
+                trow[r] = ch.t1 - 1 + W;
+                off[r] = trow[r] * N + 8 * q;
+                kb = min(kb, ks[r]);
+                kmax = max(kmax, ke[r]);
+            }
+        }
+        kb = __reduce_min_sync(TEHMM_FULL, kb);
+        kmax = __reduce_max_sync(TEHMM_FULL, kmax);
+        if (kmax <= 0) continue;
+
+        float u[2][8];
+        double mapsum[2] = {0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[r][i] = 0.f;
+
+        // at[r] = alpha_t (outputs only), bt[r] = b_{t+1}
+        auto load_ab = [&](int k, float (&at)[2][8], float (&bt)[2][8]) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t o = off[r] - (int64_t)k * N;
+                load_row8(blin + o - 8 * q + N, k >= kbv[r] && k < ke[r], coff, bt[r]);
+                load_row8(alpha + o - 8 * q, k >= W && k >= ks[r] && k < ke[r], coff, at[r]);
+            }
+        };
+        auto step = [&](int k, const float (&at)[2][8], const float (&bt)[2][8]) {
+            float w[2][8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (k == ks[r] && !exact[r]) {
+                    if (mode == 1) load_vec32(start_vec + cid[r] * 32 + 8 * q, u[r]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) u[r][i] = ones[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[r][i] = bt[r][i] * u[r][i];
+            }
+            float bp[2][8];
+            tile_matmul(w, A, bp);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (k == ks[r] && exact[r]) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bp[r][i] = ones[i];
+                }
+            }
+            if (k >= W) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool act = k >= ks[r] && k < ke[r];
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) p[i] = at[r][i] * bp[r][i];
+                    const float Z = quad_sum(((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7])));
+                    const float invZ = __frcp_rn(Z);
+                    if constexpr (want_map) {
+                        // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
+                        const float best = quad_max(max8(p));
+                        int idx = 99;
+#pragma unroll
+                        for (int i = 7; i >= 0; --i)
+                            if (p[i] == best) idx = 8 * q + i;
+                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
+                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
+                        if (act && q == 0) {
+                            map_states[trow[r] - k] = (uint8_t)(idx < N ? idx : 0);
+                            const float bg = best * invZ;
+                            mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
+                        }
+                    }
+                    if constexpr (want_post) {
+                        float gv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            gv[i] = p[i] * invZ;
+                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf;
+                        }
+                        store_row8(post + off[r] - (int64_t)k * N, act, colok, gv);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                row_scale(bp[r]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[r][i] = bp[r][i];
+            }
+            if (k == W - 1 && mode == 0) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (succ[r] && k >= ks[r] && k < ke[r]) store_vec32(start_vec + cid[r] * 32 + 8 * q, u[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, u[r]);
+        };
+
+        float ra[BWD_RING][2][8], rb[BWD_RING][2][8];
+#pragma unroll
+        for (int v = 0; v < BWD_RING; ++v) load_ab(kb + v, ra[v], rb[v]);
+        for (int k0 = kb; k0 < kmax; k0 += BWD_RING) {
+#pragma unroll
+            for (int v = 0; v < BWD_RING; ++v) {
+                float at[2][8], bt[2][8];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { at[r][i] = ra[v][r][i]; bt[r][i] = rb[v][r][i]; }
+                load_ab(k0 + v + BWD_RING, ra[v], rb[v]);
+                step(k0 + v, at, bt);
+            }
+        }
+        if constexpr (want_map) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (q == 0 && ke[r] > 0) map_part[cid[r]] = mapsum[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static int tile_grid(const TehmmBatchDev &b, int sms)
+{
+    const int64_t ngroups = (b.nchunks + 15) / 16;
+    const int64_t need = (ngroups + TILE_WARPS - 1) / TILE_WARPS;
+    return (int)(need < 1 ? 1 : (need < sms ? need : sms));
+}
+
+cudaError_t tehmm_launch_forward_tile(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                      const float *blin, const double *rowmax, float *alpha,
+                                      float *start_vec, float *end_vec, double *cscale,
+                                      const int *bad, int mode, int sms)
+{
+    fwd_tile_kernel<<<tile_grid(b, sms), TILE_WARPS * 32, 0, st>>>(m, b, blin, rowmax, alpha, start_vec,
+                                                                   end_vec, cscale, bad, mode);
+    return cudaGetLastError();
+}
+
+cudaError_t tehmm_launch_backward_tile(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                       int flags, const float *blin, const float *alpha, float *post,
+                                       uint8_t *map_states, double *map_part, float *start_vec,
+                                       float *end_vec, const int *bad, int mode, int sms)
+{
+    const int grid = tile_grid(b, sms), th = TILE_WARPS * 32;
+#define BWD_TILE(O) bwd_tile_kernel<O><<<grid, th, 0, st>>>(m, b, flags, blin, alpha, post, map_states, map_part, start_vec, end_vec, bad, mode)
+    switch (flags & (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP)) {
+    case 0: BWD_TILE(0); break;
+    case TEHMM_BWD_POSTERIORS: BWD_TILE(TEHMM_BWD_POSTERIORS); break;
+    case TEHMM_BWD_MAP: BWD_TILE(TEHMM_BWD_MAP); break;
+    default: BWD_TILE(TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP); break;
+    }
+#undef BWD_TILE
+    return cudaGetLastError();
+}
+
+int tehmm_tile_warps(void) { return TILE_WARPS; }

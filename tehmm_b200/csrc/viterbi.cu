@@ -455,13 +455,12 @@ __global__ void vit_rescore_kernel(TehmmModelDev m, TehmmBatchDev b, const OBS *
 __global__ void vit_score_reduce_kernel(TehmmBatchDev b, const double *__restrict__ score_part,
                                         double *__restrict__ logprob)
 {
-    int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int lane = threadIdx.x & 31;
-    if (s >= b.nseq) return;
+    // one block per sequence
+    const int64_t s = blockIdx.x;
     double acc = 0.0;
-    for (int64_t c = b.seq_chunk0[s] + lane; c < b.seq_chunk0[s + 1]; c += 32) acc += score_part[c];
-    acc = warp_sum(acc);
-    if (lane == 0) logprob[s] = acc;
+    for (int64_t c = b.seq_chunk0[s] + threadIdx.x; c < b.seq_chunk0[s + 1]; c += blockDim.x) acc += score_part[c];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) logprob[s] = acc;
 }
 
 template <typename T, int NS>
@@ -540,6 +539,6 @@ cudaError_t tehmm_launch_rescore(cudaStream_t st, const TehmmModelDev &m, const 
     if (b.obs_bytes == 1) vit_rescore_kernel<uint8_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint8_t *)b.obs, states, ratios_em, ratios_dp, score_part);
     else if (b.obs_bytes == 2) vit_rescore_kernel<uint16_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint16_t *)b.obs, states, ratios_em, ratios_dp, score_part);
     else vit_rescore_kernel<int32_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const int32_t *)b.obs, states, ratios_em, ratios_dp, score_part);
-    vit_score_reduce_kernel<<<(int)((b.nseq + warps - 1) / warps), warps * 32, 0, st>>>(b, score_part, logprob);
+    vit_score_reduce_kernel<<<(int)b.nseq, b.nchunks / b.nseq >= 256 ? 256 : 64, 0, st>>>(b, score_part, logprob);
     return cudaGetLastError();
 }

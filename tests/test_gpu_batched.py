@@ -20,11 +20,15 @@ TOL = {"f32": 1e-5, "f64": 1e-10}
 ATOL = {"f32": 2e-6, "f64": 1e-12}
 
 
-def engine(chunk_tiles=0, warmup=0):
+def engine(chunk_tiles=0, warmup=0, fine_len=0, tile=1):
+    """chunk_tiles / warmup: the one-chunk-per-warp partition; fine_len / tile: the
+    sixteen-chunks-per-warp tensor-core kernels (csrc/tile.cu), on by default"""
     from tehmm_b200.engine import get_engine
     eng = get_engine(0)
     eng.ctx.set_option("chunk_tiles", chunk_tiles)
     eng.ctx.set_option("warmup", warmup)
+    eng.ctx.set_option("fine_len", fine_len)
+    eng.ctx.set_option("tile", tile)
     return eng
 
 
@@ -220,3 +224,64 @@ def test_f32_vs_f64_at_scale():
     nchunks = eng.ctx.stat("chunks")
     for k in before:
         assert eng.ctx.stat("repaired_chunks_" + k) - before[k] <= 0.02 * nchunks, k
+
+
+# ---------------------------------------------------------------- tensor-core tile kernels
+@pytest.mark.parametrize("N", [2, 6, 30, 32])
+@pytest.mark.parametrize("warmup,fine_len", [(8, 16), (1, 24), (64, 0)])
+def test_tile_kernels_ragged(oracle, N, warmup, fine_len):
+    """csrc/tile.cu (fp32, 16 chunks per warp on the tensor cores) against the oracle:
+    ragged batch, chunks shorter / longer than the warm-up, sequence starts and ends
+    inside the warm-up window, partial tiles, the repair path (warmup=1)."""
+    from tehmm_b200 import synth
+    syms = (4, 8, 2) if N < 30 else synth.BENCH_SYMS
+    m = synth.make_model(N=N, syms=syms, seed=100 + N)
+    lens = [1, 2, 700, 65, 17, 1300, 129, 3, 40]
+    obs = [synth.sample_obs(m, T, seed=130 + i)[0] for i, T in enumerate(lens)]
+    eng = engine(chunk_tiles=2, warmup=warmup, fine_len=fine_len, tile=1)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    before = eng.ctx.stat("tile_passes")
+    out = eng.posteriors(renorm_eps=True, want_map=True, precision="f32")
+    assert eng.ctx.stat("tile_passes") >= before + 2          # the tile kernels really ran
+    for i, o in enumerate(obs):
+        ref = oracle_all(oracle, o, m["table"], 1.0, m["log_start"], m["log_trans"])
+        assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=TOL["f32"])
+        post = oracle.posteriors(ref["fwd"], ref["bwd"], renorm_eps=True)
+        assert_allclose(out["post"][i], post, rtol=TOL["f32"], atol=ATOL["f32"])
+        ref_map = np.argmax(post, axis=1)
+        assert np.mean(out["map_states"][i] == ref_map) >= 0.995
+        assert out["map_score"][i] == pytest.approx(np.max(post, axis=1).sum(), rel=TOL["f32"])
+    if warmup == 1 and N >= 6:
+        assert eng.ctx.stat("repair_passes_forward") > 0
+    # score-only (no alpha lattice) and MAP-only variants
+    lp = eng.score(precision="f32")
+    assert_allclose(lp, out["logprob"], rtol=1e-12)
+    mo = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f32")
+    for i in range(len(obs)):
+        assert np.mean(mo["map_states"][i] == out["map_states"][i]) >= 0.995
+
+
+def test_tile_and_warp_kernels_interoperate(oracle):
+    """forward by one implementation, backward by the other: same alpha lattice
+    conventions (canonical power-of-two scaling), same posteriors."""
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=151)
+    obs = [synth.sample_obs(m, T, seed=160 + i)[0] for i, T in enumerate([900, 2100, 77])]
+    res = {}
+    for fwd_tile in (0, 1):
+        for bwd_tile in (0, 1):
+            eng = engine(chunk_tiles=2, warmup=32, fine_len=48, tile=fwd_tile)
+            eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+            eng.upload_batch(obs)
+            prec, tdt = eng._prec("f32")
+            _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
+            alpha, logprob = eng.run_forward(prec, tdt, blin, rowmax, None)
+            eng.ctx.set_option("tile", bwd_tile)
+            post, _, _ = eng.run_backward(prec, tdt, _lib.BWD_POSTERIORS, blin, alpha, None)
+            res[(fwd_tile, bwd_tile)] = (logprob.cpu().numpy(), post.cpu().numpy())
+    eng.ctx.set_option("tile", 1)
+    base = res[(0, 0)]
+    for key, (lp, post) in res.items():
+        assert_allclose(lp, base[0], rtol=1e-7)
+        assert_allclose(post, base[1], rtol=TOL["f32"], atol=ATOL["f32"])
