@@ -42,8 +42,8 @@
 #include "scan.cuh"
 
 #define TILE_WARPS 8
-#define FWD_RING 4     // rows of b in flight per tile row (time steps)
-#define BWD_RING 2     // rows of b and alpha in flight per tile row
+#define FWD_STAGES 6    // time steps of b staged ahead in shared memory
+#define BWD_STAGES 5    // time steps of b and alpha staged ahead
 
 struct TransFrag {
     uint32_t hi[4][4][2];   // [k-tile][n-tile][b0,b1]
@@ -189,19 +189,38 @@ __device__ __forceinline__ void store_vec32(float *p, const float (&v)[8])
     *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-// One lattice row slice (states 8q..8q+7) as 8-byte accesses.  p points at the
-// ROW; coff[pp] is the column of pair pp, or an existing column of the row for
-// pairs beyond N: whatever finite value they read is multiplied by the exact
-// zero the padded states carry, so loads need no column predicate.
-__device__ __forceinline__ void load_row8(const float *p, bool on, const int (&coff)[4], float (&v)[8])
+// Row staging: global -> shared with cp.async (LDGSTS), STAGES time steps ahead of
+// the recursion.  Register prefetch rings do not work here: the loads of several
+// steps end up on the same hardware scoreboard, so waiting for the oldest waits
+// for the newest (ncu: 70% of the stall samples were long-scoreboard on the first
+// use).  cp.async completion is tracked per commit group instead.
+// Each lane stages and reads back only its own values (tile rows g and g+8,
+// states 8q..8q+7), so no barrier is needed; the slot layout [row][half][lane]
+// x 16 bytes makes the read-back LDS.128 conflict free.
+// A pair beyond N reads an existing column of the row: whatever finite value it
+// gets is multiplied by the exact zero the padded states carry, so only the
+// row-level predicate is needed; masked rows are zero-filled (src-size 0).
+#define TILE_STAGE_BYTES 2048   // per warp per stage: 16 rows x 128 bytes
+
+__device__ __forceinline__ void stage_row(uint32_t slot, const float *rowp, bool on, const int (&coff)[4],
+                                          const float *safe)
 {
+    const int nbytes = on ? 8 : 0;
 #pragma unroll
     for (int pp = 0; pp < 4; ++pp) {
-        float2 t = make_float2(0.f, 0.f);
-        if (on) t = __ldg(reinterpret_cast<const float2 *>(p + coff[pp]));
-        v[2 * pp] = t.x;
-        v[2 * pp + 1] = t.y;
+        const float *src = on ? rowp + coff[pp] : safe;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+                     :: "r"(slot + (uint32_t)((pp >> 1) * 512 + (pp & 1) * 8)), "l"(src), "r"(nbytes) : "memory");
     }
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
+__device__ __forceinline__ void stage_read(uint32_t slot, float (&v)[8])
+{
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(slot) : "memory");
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(slot + 512u) : "memory");
 }
 __device__ __forceinline__ void store_row8(float *p, bool on, const bool (&colok)[4], const float (&v)[8])
 {
@@ -219,9 +238,13 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 float *__restrict__ start_vec, float *__restrict__ end_vec,
                 double *__restrict__ cscale, const int *__restrict__ bad, int mode)
 {
+    extern __shared__ __align__(16) unsigned char tile_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
+    // this lane's 16-byte slot of (stage 0, row 0, half 0)
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
+                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 16);
 
     TransFrag A;
     load_trans<false>(m, g, q, A);
@@ -279,10 +302,13 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[r][i] = 0.f;
 
-        auto load_b = [&](int k, float (&bt)[2][8]) {
+        // stage the b rows of clock k
+        auto issue = [&](int k, int stage) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
-                load_row8(blin + off[r] - 8 * q + (int64_t)k * N, k >= ks[r] && k < ke[r], coff, bt[r]);
+                stage_row(slot0 + (uint32_t)(stage * TILE_STAGE_BYTES + r * 1024),
+                          blin + off[r] - 8 * q + (int64_t)k * N, k >= ks[r] && k < ke[r], coff, blin);
+            stage_commit();
         };
         auto step = [&](int k, const float (&bt)[2][8]) {
 #pragma unroll
@@ -324,21 +350,20 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, x[r]);
         };
 
-        float ring[FWD_RING][2][8];
 #pragma unroll
-        for (int u = 0; u < FWD_RING; ++u) load_b(kb + u, ring[u]);
-        for (int k0 = kb; k0 < kmax; k0 += FWD_RING) {
-#pragma unroll
-            for (int u = 0; u < FWD_RING; ++u) {
-                float bt[2][8];
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bt[r][i] = ring[u][r][i];
-                load_b(k0 + u + FWD_RING, ring[u]);
-                step(k0 + u, bt);
-            }
+        for (int u = 0; u < FWD_STAGES - 1; ++u) issue(kb + u, u);
+        int rs = 0, ws = FWD_STAGES - 1;          // stage read / written at clock k
+        for (int k = kb; k < kmax; ++k) {
+            issue(k + FWD_STAGES - 1, ws);
+            stage_wait<FWD_STAGES - 1>();         // the group of clock k has landed
+            float bt[2][8];
+            stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES), bt[0]);
+            stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES + 1024), bt[1]);
+            step(k, bt);
+            rs = rs + 1 == FWD_STAGES ? 0 : rs + 1;
+            ws = ws + 1 == FWD_STAGES ? 0 : ws + 1;
         }
+        stage_wait<0>();
 
         // log of everything taken out of each chunk: exponents and row maxima
         for (int rr = 0; rr < 16; ++rr) {
@@ -367,9 +392,13 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
 {
     constexpr bool want_post = (OUT & TEHMM_BWD_POSTERIORS) != 0;
     constexpr bool want_map = (OUT & TEHMM_BWD_MAP) != 0;
+    extern __shared__ __align__(16) unsigned char tile_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
+    // per stage: b rows then alpha rows
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
+                           (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 16);
     const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
     const float eps32 = 1.1920928955078125e-07f;
     const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
@@ -431,14 +460,16 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
 #pragma unroll
             for (int i = 0; i < 8; ++i) u[r][i] = 0.f;
 
-        // at[r] = alpha_t (outputs only), bt[r] = b_{t+1}
-        auto load_ab = [&](int k, float (&at)[2][8], float (&bt)[2][8]) {
+        // stage b_{t+1} and (outputs only) alpha_t of clock k
+        auto issue = [&](int k, int stage) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int64_t o = off[r] - (int64_t)k * N;
-                load_row8(blin + o - 8 * q + N, k >= kbv[r] && k < ke[r], coff, bt[r]);
-                load_row8(alpha + o - 8 * q, k >= W && k >= ks[r] && k < ke[r], coff, at[r]);
+                const int64_t o = off[r] - 8 * q - (int64_t)k * N;
+                const uint32_t sl = slot0 + (uint32_t)(stage * 2 * TILE_STAGE_BYTES + r * 1024);
+                stage_row(sl, blin + o + N, k >= kbv[r] && k < ke[r], coff, blin);
+                stage_row(sl + TILE_STAGE_BYTES, alpha + o, k >= W && k >= ks[r] && k < ke[r], coff, blin);
             }
+            stage_commit();
         };
         auto step = [&](int k, const float (&at)[2][8], const float (&bt)[2][8]) {
             float w[2][8];
@@ -514,21 +545,23 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, u[r]);
         };
 
-        float ra[BWD_RING][2][8], rb[BWD_RING][2][8];
 #pragma unroll
-        for (int v = 0; v < BWD_RING; ++v) load_ab(kb + v, ra[v], rb[v]);
-        for (int k0 = kb; k0 < kmax; k0 += BWD_RING) {
-#pragma unroll
-            for (int v = 0; v < BWD_RING; ++v) {
-                float at[2][8], bt[2][8];
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { at[r][i] = ra[v][r][i]; bt[r][i] = rb[v][r][i]; }
-                load_ab(k0 + v + BWD_RING, ra[v], rb[v]);
-                step(k0 + v, at, bt);
-            }
+        for (int v = 0; v < BWD_STAGES - 1; ++v) issue(kb + v, v);
+        int rs = 0, ws = BWD_STAGES - 1;
+        for (int k = kb; k < kmax; ++k) {
+            issue(k + BWD_STAGES - 1, ws);
+            stage_wait<BWD_STAGES - 1>();
+            float at[2][8], bt[2][8];
+            const uint32_t sl = slot0 + (uint32_t)(rs * 2 * TILE_STAGE_BYTES);
+            stage_read(sl, bt[0]);
+            stage_read(sl + 1024, bt[1]);
+            stage_read(sl + TILE_STAGE_BYTES, at[0]);
+            stage_read(sl + TILE_STAGE_BYTES + 1024, at[1]);
+            step(k, at, bt);
+            rs = rs + 1 == BWD_STAGES ? 0 : rs + 1;
+            ws = ws + 1 == BWD_STAGES ? 0 : ws + 1;
         }
+        stage_wait<0>();
         if constexpr (want_map) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
@@ -550,8 +583,11 @@ cudaError_t tehmm_launch_forward_tile(cudaStream_t st, const TehmmModelDev &m, c
                                       float *start_vec, float *end_vec, double *cscale,
                                       const int *bad, int mode, int sms)
 {
-    fwd_tile_kernel<<<tile_grid(b, sms), TILE_WARPS * 32, 0, st>>>(m, b, blin, rowmax, alpha, start_vec,
-                                                                   end_vec, cscale, bad, mode);
+    const int smem = TILE_WARPS * FWD_STAGES * TILE_STAGE_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fwd_tile_kernel<<<tile_grid(b, sms), TILE_WARPS * 32, smem, st>>>(m, b, blin, rowmax, alpha, start_vec,
+                                                                      end_vec, cscale, bad, mode);
     return cudaGetLastError();
 }
 
@@ -561,7 +597,10 @@ cudaError_t tehmm_launch_backward_tile(cudaStream_t st, const TehmmModelDev &m, 
                                        float *end_vec, const int *bad, int mode, int sms)
 {
     const int grid = tile_grid(b, sms), th = TILE_WARPS * 32;
-#define BWD_TILE(O) bwd_tile_kernel<O><<<grid, th, 0, st>>>(m, b, flags, blin, alpha, post, map_states, map_part, start_vec, end_vec, bad, mode)
+    const int smem = TILE_WARPS * BWD_STAGES * 2 * TILE_STAGE_BYTES;
+#define BWD_TILE(O) do { cudaError_t e = cudaFuncSetAttribute(bwd_tile_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+                         if (e != cudaSuccess) return e; \
+                         bwd_tile_kernel<O><<<grid, th, smem, st>>>(m, b, flags, blin, alpha, post, map_states, map_part, start_vec, end_vec, bad, mode); } while (0)
     switch (flags & (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP)) {
     case 0: BWD_TILE(0); break;
     case TEHMM_BWD_POSTERIORS: BWD_TILE(TEHMM_BWD_POSTERIORS); break;
