@@ -8,9 +8,9 @@
 //     X'[chunk][j] = sum_i X[chunk][i] A[i][j]
 // on the tensor cores (mma.sync.m16n8k8 TF32, fp32 accumulate).  TF32 alone
 // (10-bit mantissa) is far outside the 1e-5 contract, so every product is the
-// usual three-term split  x_hi A_hi + x_lo A_hi + x_hi A_lo  (x = x_hi + x_lo
-// exactly, each part a TF32 number): 48 MMAs per tile step = 3 per chunk step,
-// ~2^-21 relative error per step, and the filter does not accumulate it.
+// usual three-term split  x_hi A_hi + x_lo A_hi + x_hi A_lo  with x = x_hi + x_lo
+// exactly (Veltkamp split, packed fp32): 48 MMAs per tile step = 3 per chunk
+// step, ~2^-21 relative error per step, and the filter does not accumulate it.
 //
 // Register layout (g = lane/4, q = lane%4): the lane holds, for tile rows g and
 // g+8, the EIGHT CONSECUTIVE states 8q .. 8q+7.  The accumulator fragment of
@@ -20,20 +20,33 @@
 //   * the accumulator fragment of n-tile kt IS the A-operand fragment of
 //     k-tile kt of the next step (k-slot q <-> state 8q+2kt, slot q+4 <-> state
 //     8q+2kt+1): the recursion never leaves registers, no shuffles, no smem.
+// The state vector is kept as packed (row g, row g+8) pairs per state, which is
+// both the A-operand register order and the operand shape of FFMA2 / FMUL2.
 // The transition matrix lives in registers as B-operand fragments permuted
 // accordingly (64 registers: hi and lo parts).
+//
+// Rows of b (and alpha) are staged global -> shared with cp.async, several time
+// steps ahead of the recursion; each lane stages and reads back only its own
+// values, so no barrier is involved.
 //
 // Chunks of one tile run in lock step on a common clock k: row r processes
 // time t0_r - W + k (forward) or t1_r - 1 + W - k (backward), W = warm-up
 // length, so the speculative warm-up is k < W for every row and outputs start
 // at k = W.  Rows that start late (sequence start inside the warm-up window),
 // end early (ragged chunks) or are not selected by a repair pass are masked:
-// their loads return zeros and their stores are predicated off.
+// their loads are zero-filled and their stores predicated off.  Row starts and
+// ends are handled as rare, warp-uniform "events" outside the steady-state step.
 //
-// Speculate / verify / repair, canonical power-of-two scaling, start_vec /
-// end_vec / cscale conventions: exactly those of forward.cu and backward.cu,
-// so verify_kernel, forward_logprob_kernel and map_reduce_kernel are shared and
+// Scaling is by exact powers of two like canonicalise() in scan.cuh, but LAGGED
+// by one step: step k multiplies by the scale derived from the row maximum of
+// step k-1 (folded into b), which takes the max-reduction off the critical
+// path.  The stored vectors are then normalised to within one step's shrinkage
+// of [1,2) instead of exactly; everything downstream (posteriors, verify_kernel,
+// forward_logprob_kernel) is scale free or carries the exponent explicitly, so
 // either implementation can consume the other's alpha lattice.
+//
+// Speculate / verify / repair and the start_vec / end_vec / cscale conventions
+// are those of forward.cu and backward.cu.
 //
 // Requires fp32, N <= 32 and N even (8-byte aligned rows), no segment ratios;
 // everything else takes the one-chunk-per-warp kernels.
@@ -44,6 +57,8 @@
 #define TILE_WARPS 8
 #define FWD_STAGES 6    // time steps of b staged ahead in shared memory
 #define BWD_STAGES 5    // time steps of b and alpha staged ahead
+#define TILE_STAGE_BYTES 2048   // per warp per stage: 16 rows x 128 bytes
+#define TILE_NEVER 0x7fffffff
 
 struct TransFrag {
     uint32_t hi[4][4][2];   // [k-tile][n-tile][b0,b1]
@@ -56,6 +71,14 @@ __device__ __forceinline__ uint32_t tf32_rna(float x)
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t lo32(u64 v) { return (uint32_t)v; }
+__device__ __forceinline__ uint32_t hi32(u64 v) { return (uint32_t)(v >> 32); }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1)
@@ -89,51 +112,44 @@ __device__ __forceinline__ void load_trans(const TehmmModelDev &m, int g, int q,
     }
 }
 
-// d = x * A for the 16 x 32 tile; x[r][i] / d[r][i] <-> tile row g + 8r, state 8q + i
-__device__ __forceinline__ void tile_matmul(const float (&x)[2][8], const TransFrag &A, float (&d)[2][8])
+// The tile's state: xp[c] = (row g, row g+8) values of state 8q + c, packed.
+// acc[nt] = accumulator fragment of n-tile nt = (row g: states 8q+2nt, +1; row g+8: same).
+__device__ __forceinline__ void tile_matmul(const u64 (&xp)[8], const TransFrag &A, float (&acc)[4][4])
 {
-    // x = xh + xl exactly: xh = x truncated to TF32 (the tensor core reads only the
-    // top 19 bits, so x itself is passed), xl = the remainder rounded to TF32.
-    // (cvt.rna.tf32.f32 expands to four instructions on sm_100a; this is three per value.)
-    uint32_t xh[2][8], xl[2][8];
+    // Veltkamp split, two rows at a time: hi has 11 significant bits (a TF32
+    // number), lo = x - hi exactly; the tensor core drops lo's last two bits.
+    const u64 C = pk2(8193.f, 8193.f), M1 = pk2(-1.f, -1.f);
+    u64 xh[8], xl[8];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            xh[r][i] = __float_as_uint(x[r][i]);
-            const float rem = x[r][i] - __uint_as_float(xh[r][i] & 0xffffe000u);
-            xl[r][i] = __float_as_uint(rem) + 0x1000u;
-        }
+    for (int c = 0; c < 8; ++c) {
+        const u64 t = fmul2(xp[c], C);
+        const u64 d = ffma2(xp[c], M1, t);      // t - x
+        xh[c] = ffma2(d, M1, t);                // t - (t - x)
+        xl[c] = ffma2(xh[c], M1, xp[c]);        // x - hi
     }
-    float acc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    // small terms first, the n-tiles interleaved (four independent accumulator chains)
+    // small terms first; the four n-tiles are independent accumulator chains
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-            mma_tf32(acc[nt], xl[0][2 * kt], xl[1][2 * kt], xl[0][2 * kt + 1], xl[1][2 * kt + 1],
+            mma_tf32(acc[nt], lo32(xl[2 * kt]), hi32(xl[2 * kt]), lo32(xl[2 * kt + 1]), hi32(xl[2 * kt + 1]),
                      A.hi[kt][nt][0], A.hi[kt][nt][1]);
     }
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-            mma_tf32(acc[nt], xh[0][2 * kt], xh[1][2 * kt], xh[0][2 * kt + 1], xh[1][2 * kt + 1],
+            mma_tf32(acc[nt], lo32(xh[2 * kt]), hi32(xh[2 * kt]), lo32(xh[2 * kt + 1]), hi32(xh[2 * kt + 1]),
                      A.lo[kt][nt][0], A.lo[kt][nt][1]);
     }
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
-            mma_tf32(acc[nt], xh[0][2 * kt], xh[1][2 * kt], xh[0][2 * kt + 1], xh[1][2 * kt + 1],
+            mma_tf32(acc[nt], lo32(xh[2 * kt]), hi32(xh[2 * kt]), lo32(xh[2 * kt + 1]), hi32(xh[2 * kt + 1]),
                      A.hi[kt][nt][0], A.hi[kt][nt][1]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        d[0][2 * nt] = acc[nt][0]; d[0][2 * nt + 1] = acc[nt][1];
-        d[1][2 * nt] = acc[nt][2]; d[1][2 * nt + 1] = acc[nt][3];
     }
 }
 
@@ -148,32 +164,16 @@ __device__ __forceinline__ float quad_sum(float v)
     v += __shfl_xor_sync(TEHMM_FULL, v, 1);
     return v + __shfl_xor_sync(TEHMM_FULL, v, 2);
 }
-__device__ __forceinline__ float max8(const float (&v)[8])
-{
-    return fmaxf(fmax3(fmax3(v[0], v[1], v[2]), v[3], v[4]), fmax3(v[5], v[6], v[7]));
-}
 
-// canonicalise (scan.cuh) for a tile row: exact power-of-two scaling that puts
-// the row maximum into [1,2).  Returns the exponent taken out.
-__device__ __forceinline__ int row_scale(float (&v)[8])
+// Exact power-of-two scale that would put a (positive, finite) row maximum m
+// into [1,2): sc = 2^-(e-127), sh = e-127 with e the biased exponent.  A zero or
+// subnormal maximum gets 2^127 (lifts subnormals, keeps zeros); the exponent of
+// a masked row is never used.
+__device__ __forceinline__ void scale_of(float m, float &sc, int &sh)
 {
-    const unsigned mb = __float_as_uint(quad_max(max8(v)));
-    const unsigned e = mb >> 23;
-    float sc;
-    int sh;
-    if (__builtin_expect(e - 1u < 253u, 1)) {
-        sc = __uint_as_float((254u - e) << 23);
-        sh = (int)e - 127;
-    } else if (mb == 0u || e >= 254u) {          // dead / masked row, inf, nan
-        sc = 1.f;
-        sh = 0;
-    } else {                                     // subnormal maximum: lift, finish next step
-        sc = 18446744073709551616.f;             // 2^64
-        sh = -64;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] *= sc;
-    return sh;
+    const unsigned mb = __float_as_uint(m);
+    sc = __uint_as_float(0x7f000000u - (mb & 0x7f800000u));
+    sh = (int)(mb >> 23) - 127;
 }
 
 __device__ __forceinline__ void load_vec32(const float *p, float (&v)[8])
@@ -183,44 +183,46 @@ __device__ __forceinline__ void load_vec32(const float *p, float (&v)[8])
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
 }
-__device__ __forceinline__ void store_vec32(float *p, const float (&v)[8])
+// row h (0: tile row g, 1: tile row g+8) of the packed state
+__device__ __forceinline__ void store_row_vec32(float *p, const u64 (&xp)[8], int h)
 {
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = h ? hi2(xp[c]) : lo2(xp[c]);
     *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-
-// Row staging: global -> shared with cp.async (LDGSTS), STAGES time steps ahead of
-// the recursion.  Register prefetch rings do not work here: the loads of several
-// steps end up on the same hardware scoreboard, so waiting for the oldest waits
-// for the newest (ncu: 70% of the stall samples were long-scoreboard on the first
-// use).  cp.async completion is tracked per commit group instead.
-// Each lane stages and reads back only its own values (tile rows g and g+8,
-// states 8q..8q+7), so no barrier is needed; the slot layout [row][half][lane]
-// x 16 bytes makes the read-back LDS.128 conflict free.
-// A pair beyond N reads an existing column of the row: whatever finite value it
-// gets is multiplied by the exact zero the padded states carry, so only the
-// row-level predicate is needed; masked rows are zero-filled (src-size 0).
-#define TILE_STAGE_BYTES 2048   // per warp per stage: 16 rows x 128 bytes
-
-__device__ __forceinline__ void stage_row(uint32_t slot, const float *rowp, bool on, const int (&coff)[4],
-                                          const float *safe)
+__device__ __forceinline__ void set_row(u64 (&xp)[8], int h, const float (&v)[8])
 {
-    const int nbytes = on ? 8 : 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) xp[c] = h ? pk2(lo2(xp[c]), v[c]) : pk2(v[c], hi2(xp[c]));
+}
+
+// Row staging: global -> shared with cp.async (LDGSTS).  Register prefetch rings
+// do not work here: the loads of several steps share hardware scoreboards, so
+// waiting for the oldest waits for the newest (ncu: 70% of the stall samples were
+// long-scoreboard on the first use); cp.async completion is tracked per commit
+// group instead.  Slot layout [row][pair][lane] x 8 bytes: every LDGSTS and
+// every read-back LDS.64 covers 256 consecutive bytes (no bank conflicts; the
+// L1 data pipe is the co-limiter of these kernels).  Masked rows and pairs
+// beyond N are zero-filled (src-size 0: the address is not accessed).
+__device__ __forceinline__ void stage_row(uint32_t slot, const float *src, bool on, const bool (&colok)[4])
+{
 #pragma unroll
     for (int pp = 0; pp < 4; ++pp) {
-        const float *src = on ? rowp + coff[pp] : safe;
+        const int nbytes = (on && colok[pp]) ? 8 : 0;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
-                     :: "r"(slot + (uint32_t)((pp >> 1) * 512 + (pp & 1) * 8)), "l"(src), "r"(nbytes) : "memory");
+                     :: "r"(slot + (uint32_t)(pp * 256)), "l"(src + 2 * pp), "r"(nbytes) : "memory");
     }
 }
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
 __device__ __forceinline__ void stage_read(uint32_t slot, float (&v)[8])
 {
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(slot) : "memory");
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(slot + 512u) : "memory");
+#pragma unroll
+    for (int pp = 0; pp < 4; ++pp)
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];"
+                     : "=f"(v[2 * pp]), "=f"(v[2 * pp + 1]) : "r"(slot + (uint32_t)(pp * 256)) : "memory");
 }
 __device__ __forceinline__ void store_row8(float *p, bool on, const bool (&colok)[4], const float (&v)[8])
 {
@@ -228,8 +230,6 @@ __device__ __forceinline__ void store_row8(float *p, bool on, const bool (&colok
     for (int pp = 0; pp < 4; ++pp)
         if (on && colok[pp]) *reinterpret_cast<float2 *>(p + 2 * pp) = make_float2(v[2 * pp], v[2 * pp + 1]);
 }
-
-#define TILE_NEVER 0x7fffffff
 
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
@@ -244,23 +244,19 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     const int N = m.N, W = b.warmup;
     // this lane's 16-byte slot of (stage 0, row 0, half 0)
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
-                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 16);
+                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 8);
 
     TransFrag A;
     load_trans<false>(m, g, q, A);
     float pi[8], ones[8];
     bool colok[4];
-    int coff[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         pi[i] = (float)m.lin_start[8 * q + i];
         ones[i] = 8 * q + i < N ? 1.f : 0.f;
     }
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-        colok[pp] = 8 * q + 2 * pp < N;
-        coff[pp] = colok[pp] ? 8 * q + 2 * pp : 0;
-    }
+    for (int pp = 0; pp < 4; ++pp) colok[pp] = 8 * q + 2 * pp < N;
 
     const int64_t ngroups = (b.nchunks + 15) / 16;
     for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
@@ -295,71 +291,128 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         kmax = __reduce_max_sync(TEHMM_FULL, kmax);
         if (kmax <= 0) continue;
 
-        float x[2][8];
-        int esum[2] = {0, 0};
+        // next clock >= k at which some row of the tile starts or ends
+        auto next_event = [&](int k) -> int {
+            int e = TILE_NEVER;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[r][i] = 0.f;
+            for (int r = 0; r < 2; ++r) {
+                if (ks[r] >= k) e = min(e, ks[r]);
+                if (ke[r] - 1 >= k) e = min(e, ke[r] - 1);
+            }
+            return __reduce_min_sync(TEHMM_FULL, e);
+        };
 
-        // stage the b rows of clock k
+        u64 xp[8];                      // state, packed (row g, row g+8)
+        float scp[2] = {1.f, 1.f};      // scale to apply at the next step
+        int shp[2] = {0, 0}, esum[2] = {0, 0};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xp[c] = 0ull;
+
+        const float *lp[2];             // row of the next clock to stage
+        float *sp[2];                   // alpha row of the current clock
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            lp[r] = blin + off[r] + (int64_t)kb * N;
+            sp[r] = alpha + off[r] + (int64_t)kb * N;
+        }
         auto issue = [&](int k, int stage) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r)
-                stage_row(slot0 + (uint32_t)(stage * TILE_STAGE_BYTES + r * 1024),
-                          blin + off[r] - 8 * q + (int64_t)k * N, k >= ks[r] && k < ke[r], coff, blin);
+            for (int r = 0; r < 2; ++r) {
+                stage_row(slot0 + (uint32_t)(stage * TILE_STAGE_BYTES + r * 1024), lp[r],
+                          k >= ks[r] && k < ke[r], colok);
+                lp[r] += N;
+            }
             stage_commit();
-        };
-        auto step = [&](int k, const float (&bt)[2][8]) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (k == ks[r]) {                                    // the row starts here
-                    if (mode == 1 && !first[r]) load_vec32(start_vec + cid[r] * 32 + 8 * q, x[r]);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x[r][i] = ones[i];
-                    }
-                }
-            }
-            float d[2][8];
-            tile_matmul(x, A, d);
-            int sh[2];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (k == ks[r] && first[r]) {                        // alpha_0 = pi .* b_0
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) d[r][i] = pi[i];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[r][i] = d[r][i] * bt[r][i];
-                sh[r] = row_scale(x[r]);
-            }
-            if (k >= W) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    esum[r] += sh[r];
-                    if (alpha) store_row8(alpha + off[r] + (int64_t)k * N, k >= ks[r] && k < ke[r], colok, x[r]);
-                }
-            } else if (k == W - 1 && mode == 0) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (pred[r] && k >= ks[r] && k < ke[r]) store_vec32(start_vec + cid[r] * 32 + 8 * q, x[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-                if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, x[r]);
         };
 
 #pragma unroll
         for (int u = 0; u < FWD_STAGES - 1; ++u) issue(kb + u, u);
         int rs = 0, ws = FWD_STAGES - 1;          // stage read / written at clock k
+        int kev = next_event(kb);
         for (int k = kb; k < kmax; ++k) {
             issue(k + FWD_STAGES - 1, ws);
             stage_wait<FWD_STAGES - 1>();         // the group of clock k has landed
             float bt[2][8];
             stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES), bt[0]);
             stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES + 1024), bt[1]);
-            step(k, bt);
+            const bool ev = k == kev;             // warp uniform, rare
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (k == ks[r]) {             // the row starts here
+                        float v[8];
+                        if (mode == 1 && !first[r]) load_vec32(start_vec + cid[r] * 32 + 8 * q, v);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = ones[i];
+                        }
+                        set_row(xp, r, v);
+                        scp[r] = 1.f; shp[r] = 0;
+                    }
+                }
+            }
+            // ---- the step: x <- (x A) .* (b * 2^-shp)
+            u64 bs[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const u64 s2 = pk2(scp[r], scp[r]);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) bs[r][p] = fmul2(pk2(bt[r][2 * p], bt[r][2 * p + 1]), s2);
+            }
+            float acc[4][4];
+            tile_matmul(xp, A, acc);
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float a0 = acc[nt][0] * lo2(bs[0][nt]), a1 = acc[nt][1] * hi2(bs[0][nt]);
+                const float c0 = acc[nt][2] * lo2(bs[1][nt]), c1 = acc[nt][3] * hi2(bs[1][nt]);
+                xp[2 * nt] = pk2(a0, c0);
+                xp[2 * nt + 1] = pk2(a1, c1);
+                m0 = fmax3(m0, a0, a1);
+                m1 = fmax3(m1, c0, c1);
+            }
+            int sh_now[2] = {shp[0], shp[1]};     // exponents applied in this step
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (k == ks[r] && first[r]) {  // alpha_0 = pi .* b_0
+                        float v[8];
+                        float mm = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { v[i] = pi[i] * bt[r][i]; mm = fmaxf(mm, v[i]); }
+                        set_row(xp, r, v);
+                        if (r == 0) m0 = mm; else m1 = mm;
+                        sh_now[r] = 0;
+                    }
+                }
+            }
+            scale_of(quad_max(m0), scp[0], shp[0]);
+            scale_of(quad_max(m1), scp[1], shp[1]);
+            if (k >= W) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool act = k < ke[r];
+                    esum[r] += act ? sh_now[r] : 0;
+                    if (alpha) {
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = r ? hi2(xp[c]) : lo2(xp[c]);
+                        store_row8(sp[r], act, colok, v);
+                    }
+                }
+            } else if (k == W - 1 && mode == 0) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (pred[r] && k >= ks[r] && k < ke[r]) store_row_vec32(start_vec + cid[r] * 32 + 8 * q, xp, r);
+            }
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (k + 1 == ke[r]) store_row_vec32(end_vec + cid[r] * 32 + 8 * q, xp, r);
+                kev = next_event(k + 1);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) sp[r] += N;
             rs = rs + 1 == FWD_STAGES ? 0 : rs + 1;
             ws = ws + 1 == FWD_STAGES ? 0 : ws + 1;
         }
@@ -398,7 +451,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     const int N = m.N, W = b.warmup;
     // per stage: b rows then alpha rows
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
-                           (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 16);
+                           (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 8);
     const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
     const float eps32 = 1.1920928955078125e-07f;
     const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
@@ -408,14 +461,10 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     load_trans<true>(m, g, q, A);
     float ones[8];
     bool colok[4];
-    int coff[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) ones[i] = 8 * q + i < N ? 1.f : 0.f;
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-        colok[pp] = 8 * q + 2 * pp < N;
-        coff[pp] = colok[pp] ? 8 * q + 2 * pp : 0;
-    }
+    for (int pp = 0; pp < 4; ++pp) colok[pp] = 8 * q + 2 * pp < N;
 
     const int64_t ngroups = (b.nchunks + 15) / 16;
     for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
@@ -453,101 +502,48 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
         kmax = __reduce_max_sync(TEHMM_FULL, kmax);
         if (kmax <= 0) continue;
 
-        float u[2][8];
+        auto next_event = [&](int k) -> int {
+            int e = TILE_NEVER;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (ks[r] >= k) e = min(e, ks[r]);
+                if (ke[r] - 1 >= k) e = min(e, ke[r] - 1);
+            }
+            return __reduce_min_sync(TEHMM_FULL, e);
+        };
+
+        u64 up[8];                      // beta'_{t+1}, packed (row g, row g+8), scaled with a one-step lag
+        float scp[2] = {1.f, 1.f};
         double mapsum[2] = {0.0, 0.0};
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) u[r][i] = 0.f;
+        for (int c = 0; c < 8; ++c) up[c] = 0ull;
 
-        // stage b_{t+1} and (outputs only) alpha_t of clock k
+        const float *lb[2], *la[2];     // rows b_{t+1} and alpha_t of the next clock to stage
+        float *pp_[2];                  // posterior row of the current clock
+        uint8_t *mp_[2];                // MAP state of the current clock
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            lb[r] = blin + off[r] + N - (int64_t)kb * N;
+            la[r] = alpha + off[r] - (int64_t)kb * N;
+            pp_[r] = want_post ? post + off[r] - (int64_t)kb * N : nullptr;
+            mp_[r] = want_map ? map_states + trow[r] - kb : nullptr;
+        }
         auto issue = [&](int k, int stage) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                const int64_t o = off[r] - 8 * q - (int64_t)k * N;
                 const uint32_t sl = slot0 + (uint32_t)(stage * 2 * TILE_STAGE_BYTES + r * 1024);
-                stage_row(sl, blin + o + N, k >= kbv[r] && k < ke[r], coff, blin);
-                stage_row(sl + TILE_STAGE_BYTES, alpha + o, k >= W && k >= ks[r] && k < ke[r], coff, blin);
+                stage_row(sl, lb[r], k >= kbv[r] && k < ke[r], colok);
+                stage_row(sl + TILE_STAGE_BYTES, la[r], k >= W && k < ke[r], colok);
+                lb[r] -= N;
+                la[r] -= N;
             }
             stage_commit();
-        };
-        auto step = [&](int k, const float (&at)[2][8], const float (&bt)[2][8]) {
-            float w[2][8];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (k == ks[r] && !exact[r]) {
-                    if (mode == 1) load_vec32(start_vec + cid[r] * 32 + 8 * q, u[r]);
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) u[r][i] = ones[i];
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) w[r][i] = bt[r][i] * u[r][i];
-            }
-            float bp[2][8];
-            tile_matmul(w, A, bp);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (k == ks[r] && exact[r]) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bp[r][i] = ones[i];
-                }
-            }
-            if (k >= W) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool act = k >= ks[r] && k < ke[r];
-                    float p[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) p[i] = at[r][i] * bp[r][i];
-                    const float Z = quad_sum(((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7])));
-                    const float invZ = __frcp_rn(Z);
-                    if constexpr (want_map) {
-                        // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
-                        const float best = quad_max(max8(p));
-                        int idx = 99;
-#pragma unroll
-                        for (int i = 7; i >= 0; --i)
-                            if (p[i] == best) idx = 8 * q + i;
-                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
-                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
-                        if (act && q == 0) {
-                            map_states[trow[r] - k] = (uint8_t)(idx < N ? idx : 0);
-                            const float bg = best * invZ;
-                            mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
-                        }
-                    }
-                    if constexpr (want_post) {
-                        float gv[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            gv[i] = p[i] * invZ;
-                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf;
-                        }
-                        store_row8(post + off[r] - (int64_t)k * N, act, colok, gv);
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                row_scale(bp[r]);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) u[r][i] = bp[r][i];
-            }
-            if (k == W - 1 && mode == 0) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (succ[r] && k >= ks[r] && k < ke[r]) store_vec32(start_vec + cid[r] * 32 + 8 * q, u[r]);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-                if (k + 1 == ke[r]) store_vec32(end_vec + cid[r] * 32 + 8 * q, u[r]);
         };
 
 #pragma unroll
         for (int v = 0; v < BWD_STAGES - 1; ++v) issue(kb + v, v);
         int rs = 0, ws = BWD_STAGES - 1;
+        int kev = next_event(kb);
         for (int k = kb; k < kmax; ++k) {
             issue(k + BWD_STAGES - 1, ws);
             stage_wait<BWD_STAGES - 1>();
@@ -557,7 +553,120 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             stage_read(sl + 1024, bt[1]);
             stage_read(sl + TILE_STAGE_BYTES, at[0]);
             stage_read(sl + TILE_STAGE_BYTES + 1024, at[1]);
-            step(k, at, bt);
+            const bool ev = k == kev;
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (k == ks[r] && !exact[r]) {
+                        float v[8];
+                        if (mode == 1) load_vec32(start_vec + cid[r] * 32 + 8 * q, v);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = ones[i];
+                        }
+                        set_row(up, r, v);
+                        scp[r] = 1.f;
+                    }
+                }
+            }
+            // ---- w = (b_{t+1} 2^-sh) .* beta'_{t+1};  beta'_t = w A^T
+            u64 wp[8];
+            {
+                u64 bs[2][4];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const u64 s2 = pk2(scp[r], scp[r]);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) bs[r][p] = fmul2(pk2(bt[r][2 * p], bt[r][2 * p + 1]), s2);
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    wp[2 * p] = fmul2(up[2 * p], pk2(lo2(bs[0][p]), lo2(bs[1][p])));
+                    wp[2 * p + 1] = fmul2(up[2 * p + 1], pk2(hi2(bs[0][p]), hi2(bs[1][p])));
+                }
+            }
+            float acc[4][4];
+            tile_matmul(wp, A, acc);
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                up[2 * nt] = pk2(acc[nt][0], acc[nt][2]);
+                up[2 * nt + 1] = pk2(acc[nt][1], acc[nt][3]);
+                m0 = fmax3(m0, acc[nt][0], acc[nt][1]);
+                m1 = fmax3(m1, acc[nt][2], acc[nt][3]);
+            }
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (k == ks[r] && exact[r]) {    // the sequence's last step: beta = 1
+                        set_row(up, r, ones);
+                        if (r == 0) m0 = 1.f; else m1 = 1.f;
+                    }
+                }
+            }
+            {
+                int dummy;
+                scale_of(quad_max(m0), scp[0], dummy);
+                scale_of(quad_max(m1), scp[1], dummy);
+            }
+            if (k >= W) {
+                // posterior of time t: gamma = alpha_t .* beta'_t / Z
+                u64 pr[8];
+                u64 zs = 0ull;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    pr[c] = fmul2(up[c], pk2(at[0][c], at[1][c]));
+                    zs = fadd2(zs, pr[c]);
+                }
+                const float Z0 = quad_sum(lo2(zs)), Z1 = quad_sum(hi2(zs));
+                const float invZ[2] = {__frcp_rn(Z0), __frcp_rn(Z1)};
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const bool act = k < ke[r];
+                    float p[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) p[c] = r ? hi2(pr[c]) : lo2(pr[c]);
+                    if constexpr (want_map) {
+                        // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
+                        const float best = quad_max(fmaxf(fmax3(fmax3(p[0], p[1], p[2]), p[3], p[4]), fmax3(p[5], p[6], p[7])));
+                        int idx = 99;
+#pragma unroll
+                        for (int i = 7; i >= 0; --i)
+                            if (p[i] == best) idx = 8 * q + i;
+                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
+                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
+                        if (act && q == 0) {
+                            *mp_[r] = (uint8_t)(idx < N ? idx : 0);
+                            const float bg = best * invZ[r];
+                            mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
+                        }
+                    }
+                    if constexpr (want_post) {
+                        float gv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            gv[i] = p[i] * invZ[r];
+                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf;
+                        }
+                        store_row8(pp_[r], act, colok, gv);
+                    }
+                }
+            } else if (k == W - 1 && mode == 0) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (succ[r] && k >= ks[r] && k < ke[r]) store_row_vec32(start_vec + cid[r] * 32 + 8 * q, up, r);
+            }
+            if (ev) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    if (k + 1 == ke[r]) store_row_vec32(end_vec + cid[r] * 32 + 8 * q, up, r);
+                kev = next_event(k + 1);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if constexpr (want_post) pp_[r] -= N;
+                if constexpr (want_map) mp_[r] -= 1;
+            }
             rs = rs + 1 == BWD_STAGES ? 0 : rs + 1;
             ws = ws + 1 == BWD_STAGES ? 0 : ws + 1;
         }
