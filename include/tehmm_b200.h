@@ -141,6 +141,12 @@ int tehmm_set_model(tehmm_ctx *ctx, int N, int K, int S, const double *log_start
 int tehmm_set_batch(tehmm_ctx *ctx, const void *d_obs, int obs_bytes, int64_t nseq,
                     const int64_t *h_offsets);
 int64_t tehmm_batch_total(tehmm_ctx *ctx);  /* total rows */
+/* Row stride LD (in elements) of every batched lattice below -- d_elog, d_blin,
+ * d_alpha, d_post and the Viterbi workspace are (total, LD) row-major with the
+ * states in columns 0..N-1 and zero padding after them.  LD = 32 for N <= 32
+ * (one 128-byte line per float32 row, 16-byte aligned for vector and bulk
+ * copies), N otherwise.  Valid after tehmm_set_model.                         */
+int tehmm_lattice_stride(tehmm_ctx *ctx);
 int64_t tehmm_batch_chunks(tehmm_ctx *ctx); /* chunks in the time partition */
 /* bytes of d_scratch the tehmm_run_* calls need for the current batch+model */
 int64_t tehmm_scratch_bytes(tehmm_ctx *ctx, int prec);
@@ -155,7 +161,7 @@ int tehmm_run_emission(tehmm_ctx *ctx, int prec, const double *d_ratios,
 /* Reference-layout frame: d_frame[t][j] float64 = what fastAllLogProbs writes */
 int tehmm_run_emission_f64(tehmm_ctx *ctx, const double *d_ratios, double *d_frame);
 
-/* Forward (hmm.py:678-713 -> _hmm.pyx:120-158).  d_alpha (total*N, may be NULL
+/* Forward (hmm.py:678-713 -> _hmm.pyx:120-158).  d_alpha (total*LD, may be NULL
  * for score-only) receives the per-step max-normalised forward vector;
  * d_logprob (nseq, float64) the sequence log-likelihoods.                    */
 int tehmm_run_forward(tehmm_ctx *ctx, int prec, const void *d_blin,
@@ -164,7 +170,7 @@ int tehmm_run_forward(tehmm_ctx *ctx, int prec, const void *d_blin,
 
 /* Backward + posterior glue + expected counts (hmm.py:715-729,545-574,
  * basehmm.py:265-272,516-517, _hmm.pyx:62-117,160-198).  flags = TEHMM_BWD_*.
- *   d_post        total*N, element type prec            (POSTERIORS)
+ *   d_post        total*LD, element type prec           (POSTERIORS)
  *   d_map_states  total, uint8;  d_map_score nseq f64   (MAP)
  *   d_start_trans N + N*N float64, ACCUMULATED into     (TRANS)             */
 int tehmm_run_backward(tehmm_ctx *ctx, int prec, int flags, const void *d_blin,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "tehmm_set_batch": (_c_int, [_c_void, _c_void, _c_int, _c_i64, _c_void]),
     "tehmm_batch_total": (_c_i64, [_c_void]),
     "tehmm_batch_chunks": (_c_i64, [_c_void]),
+    "tehmm_lattice_stride": (_c_int, [_c_void]),
     "tehmm_scratch_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_emission": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_run_emission_f64": (_c_int, [_c_void, _c_void, _c_void]),

@@ -411,6 +411,7 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     unsigned char *d = (unsigned char *)c->model_blob;
     TehmmModelDev &m = c->m;
     m.N = N; m.K = K; m.S = S; m.NS = NS; m.NP = NP; m.tab_rows = rows; m.normalize = normalize;
+    m.LD = NS == 1 ? 32 : N;
     m.table_in_smem = (size_t)rows * N * 8 <= tehmm_emission_table_budget(K) ? 1 : 0;
     m.log_start = (const double *)(d + o_ls); m.log_trans = (const double *)(d + o_lt);
     m.table = (const double *)(d + o_tab); m.table_t = (const double *)(d + o_tt);
@@ -507,11 +508,12 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
 }
 
 int64_t tehmm_batch_total(tehmm_ctx *c) { return c && c->has_batch ? c->b.total : 0; }
+int tehmm_lattice_stride(tehmm_ctx *c) { return c && c->has_model ? c->m.LD : 0; }
 int64_t tehmm_batch_chunks(tehmm_ctx *c) { return c && c->has_batch ? c->b.nchunks : 0; }
 int64_t tehmm_viterbi_workspace_bytes(tehmm_ctx *c, int prec)
 {
     if (!c || !c->has_batch || !c->has_model) return 0;
-    return c->b.total * (int64_t)c->m.N * (prec == TEHMM_F32 ? 4 : 8);   // the delta lattice
+    return c->b.total * (int64_t)c->m.LD * (prec == TEHMM_F32 ? 4 : 8);   // the delta lattice
 }
 
 // scratch carving shared by tehmm_scratch_bytes and the run_* entry points
@@ -623,11 +625,11 @@ static void adapt_warmup(tehmm_ctx *c, int first_pass_bad, int64_t nchunks)
     }
 }
 
-// The tensor-core tile kernels (tile.cu) take the fp32, N <= 32, N even, no
+// The tensor-core tile kernels (tile.cu) take the fp32, N <= 32, no
 // segment-ratio case; everything else runs one chunk per warp.
 static bool use_tile(const tehmm_ctx *c, int prec, const double *d_ratios)
 {
-    return c->opt_tile != 0 && prec == TEHMM_F32 && c->m.NS == 1 && (c->m.N & 1) == 0 && d_ratios == nullptr;
+    return c->opt_tile != 0 && prec == TEHMM_F32 && c->m.NS == 1 && c->m.LD == 32 && d_ratios == nullptr;
 }
 
 int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *d_rowmax,

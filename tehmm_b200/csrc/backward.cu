@@ -92,7 +92,7 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*ws)[NP] = ws_all[warp];
     const int N = m.N;
-    const unsigned Nu = (unsigned)N;
+    const unsigned Nu = (unsigned)m.LD;      // lattice row stride
     constexpr bool TRANS = (OUT & TEHMM_BWD_TRANS) != 0;
     constexpr bool want_post = (OUT & TEHMM_BWD_POSTERIORS) != 0;
     constexpr bool want_map = (OUT & TEHMM_BWD_MAP) != 0;
@@ -129,9 +129,9 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
         double mapsum = 0.0;
 
         // rows are addressed relative to t0 with 32-bit offsets
-        const T *__restrict__ bb = blin + ch.t0 * N;
-        const T *__restrict__ aa = alpha + ch.t0 * N;
-        T *__restrict__ pp = want_post ? post + ch.t0 * N : nullptr;
+        const T *__restrict__ bb = blin + ch.t0 * m.LD;
+        const T *__restrict__ aa = alpha + ch.t0 * m.LD;
+        T *__restrict__ pp = want_post ? post + ch.t0 * m.LD : nullptr;
         uint8_t *__restrict__ mm = want_map ? map_states + ch.t0 : nullptr;
         const double *__restrict__ rr = RATIO ? ratios + ch.t0 : nullptr;
 
@@ -256,6 +256,8 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
                         T gv = g[s];
                         if (renorm) gv = (T)(((double)gv + eps32) * renorm_inv);
                         pp[r * Nu + (unsigned)(lane + 32 * s)] = gv;
+                    } else if (lane + 32 * s < m.LD) {
+                        pp[r * Nu + (unsigned)(lane + 32 * s)] = (T)0;     // padding column
                     }
                 }
             }

@@ -28,6 +28,10 @@ struct TehmmChunk {
 // Device-resident model, both spaces, padded to NP = 32*NS states.
 struct TehmmModelDev {
     int N, K, S, NS, NP;
+    int LD;                     // row stride (elements) of every batched lattice: elog, blin, alpha,
+                                // posteriors, delta.  32 for N <= 32 (128-byte rows of float: one
+                                // cache line, 16-byte vector / bulk accesses), N otherwise.  Columns
+                                // N..LD-1 are padding and always hold zeros.
     int tab_rows;               // rows of the compact transposed table
     int table_in_smem;          // compact table fits the emission kernel's smem
     double normalize;

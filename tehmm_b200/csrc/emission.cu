@@ -53,9 +53,13 @@ __device__ __forceinline__ void em_finish_row(const TehmmModelDev &m, int64_t t,
         return;
     }
     if (lane == 0) rowmax[t] = M;
-    const int64_t o = t * N + lane;
+    const int64_t o = t * m.LD + lane;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
+        if (lane + 32 * s >= N && lane + 32 * s < m.LD) {        // padding columns: zeros
+            if (elog) elog[o + 32 * s] = (T)0;
+            if (blin) blin[o + 32 * s] = (T)0;
+        }
         if (lane + 32 * s < N) {
             const double d = (M > -INFINITY) ? v[s] - M : 0.0;
             if (sizeof(T) == 4) {
@@ -173,7 +177,7 @@ emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
 // zeroed only while no earlier row of the sequence had a value > -1e20.
 // One warp per flagged sequence; almost never runs.
 template <typename T>
-__global__ void emission_fix_kernel(int N, const int *__restrict__ seq_flag,
+__global__ void emission_fix_kernel(int N, int LD, const int *__restrict__ seq_flag,
                                     const int64_t *__restrict__ seq_off, int64_t nseq,
                                     T *elog, T *blin, double *rowmax, double *frame)
 {
@@ -193,8 +197,8 @@ __global__ void emission_fix_kernel(int N, const int *__restrict__ seq_flag,
         if (!infeasible) break;
         for (int j = lane; j < N; j += 32) {
             if (frame) frame[t * N + j] = 0.0;
-            if (elog) elog[t * N + j] = (T)0;
-            if (blin) blin[t * N + j] = (T)1;
+            if (elog) elog[t * LD + j] = (T)0;
+            if (blin) blin[t * LD + j] = (T)1;
         }
         if (rowmax && lane == 0) rowmax[t] = 0.0;
         __syncwarp();
@@ -266,9 +270,9 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
         int warps = 4;
         int grid = (int)((b.nseq + warps - 1) / warps);
         if (frame || prec == TEHMM_F32)
-            emission_fix_kernel<float><<<grid, warps * 32, 0, st>>>(m.N, seq_flag, b.seq_off, b.nseq, (float *)elog, (float *)blin, rowmax, frame);
+            emission_fix_kernel<float><<<grid, warps * 32, 0, st>>>(m.N, m.LD, seq_flag, b.seq_off, b.nseq, (float *)elog, (float *)blin, rowmax, frame);
         else
-            emission_fix_kernel<double><<<grid, warps * 32, 0, st>>>(m.N, seq_flag, b.seq_off, b.nseq, (double *)elog, (double *)blin, rowmax, frame);
+            emission_fix_kernel<double><<<grid, warps * 32, 0, st>>>(m.N, m.LD, seq_flag, b.seq_off, b.nseq, (double *)elog, (double *)blin, rowmax, frame);
         e = cudaGetLastError();
     }
     *err = e;

@@ -67,8 +67,8 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
             if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
         }
         // everything below addresses rows relative to tw with 32-bit offsets
-        const T *__restrict__ bb = blin + tw * N;
-        T *__restrict__ aa = alpha ? alpha + tw * N : nullptr;
+        const T *__restrict__ bb = blin + tw * m.LD;
+        T *__restrict__ aa = alpha ? alpha + tw * m.LD : nullptr;
         const double *__restrict__ rr = RATIO ? ratios + tw : nullptr;
 
         // one recursion step: x <- scaled( (x A) .* b_t [.* g_t] ); returns the exponent
@@ -117,9 +117,9 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
         for (int s = 0; s < NS; ++s) {
             bp[s] = bb + jc[s];
             ap[s] = aa + lane + 32 * s;
-            wr[s] = own[s] && aa != nullptr;
+            wr[s] = lane + 32 * s < m.LD && aa != nullptr;   // padding columns get the exact zeros
         }
-        const unsigned Nu = (unsigned)N;
+        const unsigned Nu = (unsigned)m.LD;
         // b of the row `ahead` rows after the current one
         auto load_b = [&](unsigned ahead, T (&bt)[NS]) {
 #pragma unroll

@@ -53,7 +53,7 @@ emission_stats_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tota
     for (int64_t tb = ta; tb < tz; tb += ST_TILE) {
         const int rows = (int)min((int64_t)ST_TILE, tz - tb);
         __syncthreads();
-        for (int e = threadIdx.x; e < rows * N; e += blockDim.x) post_s[e] = post[tb * N + e];
+        for (int e = threadIdx.x; e < rows * N; e += blockDim.x) post_s[e] = post[(tb + e / N) * m.LD + e % N];
         for (int e = threadIdx.x; e < rows * K; e += blockDim.x) sym_s[e] = (int)obs[tb * K + e];
         if (ratios)
             for (int e = threadIdx.x; e < rows; e += blockDim.x) ratio_s[e] = ratios[tb + e];
@@ -97,7 +97,7 @@ __global__ void emission_stats_global_kernel(TehmmModelDev m, const OBS *__restr
         const int sym = (int)obs[e];
         const double r = ratios ? ratios[t] : 1.0;
         for (int j = 0; j < N; ++j)
-            atomicAdd(&dense_stats[((int64_t)k * N + j) * statS + sym], (double)post[t * N + j] * r);
+            atomicAdd(&dense_stats[((int64_t)k * N + j) * statS + sym], (double)post[t * m.LD + j] * r);
     }
 }
 

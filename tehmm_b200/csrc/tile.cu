@@ -15,8 +15,8 @@
 // Register layout (g = lane/4, q = lane%4): the lane holds, for tile rows g and
 // g+8, the EIGHT CONSECUTIVE states 8q .. 8q+7.  The accumulator fragment of
 // n-tile nt (columns n = 2q, 2q+1) is mapped to states 8q+2nt, 8q+2nt+1, so
-//   * a row of b / alpha / posteriors is read and written as four 8-byte
-//     accesses per lane, a quad covering the whole 4N-byte row;
+//   * a row of b / alpha / posteriors (LD = 32 floats = one 128-byte line) is
+//     read and written as two 16-byte accesses per lane, a quad covering the row;
 //   * the accumulator fragment of n-tile kt IS the A-operand fragment of
 //     k-tile kt of the next step (k-slot q <-> state 8q+2kt, slot q+4 <-> state
 //     8q+2kt+1): the recursion never leaves registers, no shuffles, no smem.
@@ -48,7 +48,7 @@
 // Speculate / verify / repair and the start_vec / end_vec / cscale conventions
 // are those of forward.cu and backward.cu.
 //
-// Requires fp32, N <= 32 and N even (8-byte aligned rows), no segment ratios;
+// Requires fp32, N <= 32 (lattice row stride LD = 32), no segment ratios;
 // everything else takes the one-chunk-per-warp kernels.
 // Algorithmic HBM bytes per step: forward 4N read + 4N written, backward 8N read
 // (+4N posteriors, +1 MAP state).
@@ -198,37 +198,40 @@ __device__ __forceinline__ void set_row(u64 (&xp)[8], int h, const float (&v)[8]
     for (int c = 0; c < 8; ++c) xp[c] = h ? pk2(lo2(xp[c]), v[c]) : pk2(v[c], hi2(xp[c]));
 }
 
-// Row staging: global -> shared with cp.async (LDGSTS).  Register prefetch rings
-// do not work here: the loads of several steps share hardware scoreboards, so
-// waiting for the oldest waits for the newest (ncu: 70% of the stall samples were
-// long-scoreboard on the first use); cp.async completion is tracked per commit
-// group instead.  Slot layout [row][pair][lane] x 8 bytes: every LDGSTS and
-// every read-back LDS.64 covers 256 consecutive bytes (no bank conflicts; the
-// L1 data pipe is the co-limiter of these kernels).  Masked rows and pairs
-// beyond N are zero-filled (src-size 0: the address is not accessed).
-__device__ __forceinline__ void stage_row(uint32_t slot, const float *src, bool on, const bool (&colok)[4])
+// Row staging: global -> shared with cp.async (LDGSTS), 16 bytes per lane (rows
+// are LD = 32 floats = one 128-byte line, so a quad reads half a row per
+// instruction).  Register prefetch rings do not work here: the loads of several
+// steps share hardware scoreboards, so waiting for the oldest waits for the
+// newest (ncu: 70% of the stall samples were long-scoreboard on the first use);
+// cp.async completion is tracked per commit group instead.  Slot layout
+// [row][half][lane] x 16 bytes: every LDGSTS.128 and every read-back LDS.128
+// covers 512 consecutive bytes (no bank conflicts).  Masked rows are zero-filled
+// (src-size 0: the address is not accessed); padding columns hold zeros in HBM.
+__device__ __forceinline__ void stage_row(uint32_t slot, const float *src, bool on)
 {
+    const int nbytes = on ? 16 : 0;
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp) {
-        const int nbytes = (on && colok[pp]) ? 8 : 0;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
-                     :: "r"(slot + (uint32_t)(pp * 256)), "l"(src + 2 * pp), "r"(nbytes) : "memory");
-    }
+    for (int h = 0; h < 2; ++h)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     :: "r"(slot + (uint32_t)(h * 512)), "l"(src + 4 * h), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
 __device__ __forceinline__ void stage_read(uint32_t slot, float (&v)[8])
 {
 #pragma unroll
-    for (int pp = 0; pp < 4; ++pp)
-        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];"
-                     : "=f"(v[2 * pp]), "=f"(v[2 * pp + 1]) : "r"(slot + (uint32_t)(pp * 256)) : "memory");
+    for (int h = 0; h < 2; ++h)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v[4 * h]), "=f"(v[4 * h + 1]), "=f"(v[4 * h + 2]), "=f"(v[4 * h + 3])
+                     : "r"(slot + (uint32_t)(h * 512)) : "memory");
 }
-__device__ __forceinline__ void store_row8(float *p, bool on, const bool (&colok)[4], const float (&v)[8])
+// a lattice row slice (states 8q..8q+7, padding included) as two 16-byte stores
+__device__ __forceinline__ void store_row8(float *p, bool on, const float (&v)[8])
 {
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp)
-        if (on && colok[pp]) *reinterpret_cast<float2 *>(p + 2 * pp) = make_float2(v[2 * pp], v[2 * pp + 1]);
+    if (on) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
 }
 
 // ------------------------------------------------------------------ forward
@@ -242,21 +245,19 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
+    constexpr int LD = 32;                        // lattice row stride (TehmmModelDev::LD for N <= 32)
     // this lane's 16-byte slot of (stage 0, row 0, half 0)
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
-                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 8);
+                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 16);
 
     TransFrag A;
     load_trans<false>(m, g, q, A);
     float pi[8], ones[8];
-    bool colok[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         pi[i] = (float)m.lin_start[8 * q + i];
         ones[i] = 8 * q + i < N ? 1.f : 0.f;
     }
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp) colok[pp] = 8 * q + 2 * pp < N;
 
     const int64_t ngroups = (b.nchunks + 15) / 16;
     for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
@@ -282,7 +283,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 else if (dist <= W) { ks[r] = W - (int)dist; first[r] = true; }
                 else ks[r] = 0;                                      // speculate from a flat vector
                 ke[r] = W + (int)(ch.t1 - ch.t0);
-                off[r] = (ch.t0 - W) * N + 8 * q;
+                off[r] = (ch.t0 - W) * LD + 8 * q;
                 kb = min(kb, ks[r]);
                 kmax = max(kmax, ke[r]);
             }
@@ -312,15 +313,15 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         float *sp[2];                   // alpha row of the current clock
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            lp[r] = blin + off[r] + (int64_t)kb * N;
-            sp[r] = alpha + off[r] + (int64_t)kb * N;
+            lp[r] = blin + off[r] + (int64_t)kb * LD;
+            sp[r] = alpha + off[r] + (int64_t)kb * LD;
         }
         auto issue = [&](int k, int stage) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 stage_row(slot0 + (uint32_t)(stage * TILE_STAGE_BYTES + r * 1024), lp[r],
-                          k >= ks[r] && k < ke[r], colok);
-                lp[r] += N;
+                          k >= ks[r] && k < ke[r]);
+                lp[r] += LD;
             }
             stage_commit();
         };
@@ -397,7 +398,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                         float v[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) v[c] = r ? hi2(xp[c]) : lo2(xp[c]);
-                        store_row8(sp[r], act, colok, v);
+                        store_row8(sp[r], act, v);
                     }
                 }
             } else if (k == W - 1 && mode == 0) {
@@ -412,7 +413,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 kev = next_event(k + 1);
             }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) sp[r] += N;
+            for (int r = 0; r < 2; ++r) sp[r] += LD;
             rs = rs + 1 == FWD_STAGES ? 0 : rs + 1;
             ws = ws + 1 == FWD_STAGES ? 0 : ws + 1;
         }
@@ -449,9 +450,10 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
+    constexpr int LD = 32;
     // per stage: b rows then alpha rows
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
-                           (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 8);
+                           (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 16);
     const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
     const float eps32 = 1.1920928955078125e-07f;
     const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
@@ -460,11 +462,8 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     TransFrag A;
     load_trans<true>(m, g, q, A);
     float ones[8];
-    bool colok[4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) ones[i] = 8 * q + i < N ? 1.f : 0.f;
-#pragma unroll
-    for (int pp = 0; pp < 4; ++pp) colok[pp] = 8 * q + 2 * pp < N;
 
     const int64_t ngroups = (b.nchunks + 15) / 16;
     for (int64_t gi = (int64_t)blockIdx.x * TILE_WARPS + warp; gi < ngroups;
@@ -493,7 +492,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 kbv[r] = exact[r] ? ks[r] + 1 : ks[r];
                 ke[r] = W + (int)(ch.t1 - ch.t0);
                 trow[r] = ch.t1 - 1 + W;
-                off[r] = trow[r] * N + 8 * q;
+                off[r] = trow[r] * LD + 8 * q;
                 kb = min(kb, ks[r]);
                 kmax = max(kmax, ke[r]);
             }
@@ -523,19 +522,19 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
         uint8_t *mp_[2];                // MAP state of the current clock
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            lb[r] = blin + off[r] + N - (int64_t)kb * N;
-            la[r] = alpha + off[r] - (int64_t)kb * N;
-            pp_[r] = want_post ? post + off[r] - (int64_t)kb * N : nullptr;
+            lb[r] = blin + off[r] + LD - (int64_t)kb * LD;
+            la[r] = alpha + off[r] - (int64_t)kb * LD;
+            pp_[r] = want_post ? post + off[r] - (int64_t)kb * LD : nullptr;
             mp_[r] = want_map ? map_states + trow[r] - kb : nullptr;
         }
         auto issue = [&](int k, int stage) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const uint32_t sl = slot0 + (uint32_t)(stage * 2 * TILE_STAGE_BYTES + r * 1024);
-                stage_row(sl, lb[r], k >= kbv[r] && k < ke[r], colok);
-                stage_row(sl + TILE_STAGE_BYTES, la[r], k >= W && k < ke[r], colok);
-                lb[r] -= N;
-                la[r] -= N;
+                stage_row(sl, lb[r], k >= kbv[r] && k < ke[r]);
+                stage_row(sl + TILE_STAGE_BYTES, la[r], k >= W && k < ke[r]);
+                lb[r] -= LD;
+                la[r] -= LD;
             }
             stage_commit();
         };
@@ -646,9 +645,9 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             gv[i] = p[i] * invZ[r];
-                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf;
+                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf * ones[i];   // padding stays zero
                         }
-                        store_row8(pp_[r], act, colok, gv);
+                        store_row8(pp_[r], act, gv);
                     }
                 }
             } else if (k == W - 1 && mode == 0) {
@@ -664,7 +663,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             }
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                if constexpr (want_post) pp_[r] -= N;
+                if constexpr (want_post) pp_[r] -= LD;
                 if constexpr (want_map) mp_[r] -= 1;
             }
             rs = rs + 1 == BWD_STAGES ? 0 : rs + 1;

@@ -43,7 +43,7 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*ds)[NP] = ds_all[warp];
     const int N = m.N;
-    const unsigned Nu = (unsigned)N;
+    const unsigned Nu = (unsigned)m.LD;      // lattice row stride
     const T NEG = (T)-INFINITY;
 
     MatSlice<T, NS> A;       // column j of log A (-inf beyond N and for zero transitions)
@@ -75,8 +75,8 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
             tw = ch.t0 - b.warmup;
             if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
         }
-        const T *__restrict__ ee = elog + tw * N;
-        T *__restrict__ ll = lattice + tw * N;
+        const T *__restrict__ ee = elog + tw * m.LD;
+        T *__restrict__ ll = lattice + tw * m.LD;
         const double *__restrict__ rr = RATIO ? ratios + tw : nullptr;
 
         auto load_e = [&](unsigned row, T (&et)[NS]) {
@@ -252,7 +252,7 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
     T *AT = reinterpret_cast<T *>(tb_smem);               // AT[s*NP + i] = logA[i][s]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = m.N;
-    const unsigned Nu = (unsigned)N;
+    const unsigned Nu = (unsigned)m.LD;      // lattice row stride
     const T NEG = (T)-INFINITY;
     for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
         const int s = e / NP, i = e - s * NP;
@@ -274,7 +274,7 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
         const TehmmChunk ch = b.chunks[ci];
         // rows relative to t0 - 1 (row 0 = the left neighbour's last step, if any)
         const int64_t tbase = ch.t0 > ch.s0 ? ch.t0 - 1 : ch.t0;
-        const T *__restrict__ ll = lattice + tbase * N;
+        const T *__restrict__ ll = lattice + tbase * m.LD;
         const double *__restrict__ rr = RATIO ? ratios + tbase : nullptr;
         const unsigned rfirst = (unsigned)(ch.t0 - tbase);            // row of t0 (0 or 1)
         const unsigned rlast = (unsigned)(ch.t1 - 1 - tbase);         // row of t1-1

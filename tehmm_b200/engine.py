@@ -91,6 +91,7 @@ class Engine(object):
         _lib.check(self.lib.tehmm_set_model(self.ctx.handle, N, K, S, _lib.ptr(ls), _lib.ptr(lt), _lib.ptr(tab),
                                             float(normalize), _lib.ptr(ns)))
         self.N, self.K, self.S = N, K, S
+        self.LD = int(self.lib.tehmm_lattice_stride(self.ctx.handle))   # row stride of the device lattices
 
     def upload_batch(self, obs_list, pinned=None):
         """Concatenate, copy to the device and describe to the library.
@@ -161,7 +162,7 @@ class Engine(object):
 
     # ------------------------------------------------------------ device ops
     def run_emission(self, prec, tdt, d_ratios, want_log, want_lin):
-        n = self.total * self.N
+        n = self.total * self.LD
         elog = self.empty(n, tdt) if want_log else None
         blin = self.empty(n, tdt) if want_lin else None
         rowmax = self.empty(self.total, self.torch.float64)
@@ -170,7 +171,7 @@ class Engine(object):
         return elog, blin, rowmax
 
     def run_forward(self, prec, tdt, blin, rowmax, d_ratios, want_alpha=True):
-        alpha = self.empty(self.total * self.N, tdt) if want_alpha else None
+        alpha = self.empty(self.total * self.LD, tdt) if want_alpha else None
         logprob = self.empty(self.nseq, self.torch.float64)
         sc = self.scratch(prec)
         _lib.check(self.lib.tehmm_run_forward(self.ctx.handle, prec, self._p(blin), self._p(rowmax),
@@ -179,7 +180,7 @@ class Engine(object):
 
     def run_backward(self, prec, tdt, flags, blin, alpha, d_ratios, start_trans=None):
         torch = self.torch
-        post = self.empty(self.total * self.N, tdt) if flags & _lib.BWD_POSTERIORS else None
+        post = self.empty(self.total * self.LD, tdt) if flags & _lib.BWD_POSTERIORS else None
         mstates = self.empty(self.total, torch.uint8) if flags & _lib.BWD_MAP else None
         mscore = self.empty(self.nseq, torch.float64) if flags & _lib.BWD_MAP else None
         sc = self.scratch(prec)
@@ -211,6 +212,13 @@ class Engine(object):
         out = self.empty(t.numel(), self.torch.float64)
         _lib.check(self.lib.tehmm_convert_lattice(self.ctx.handle, prec, self._p(t), self._p(out), t.numel()))
         return out
+
+    def lattice_to_host(self, prec, t):
+        """(total, LD) device lattice -> (total, N) float64 host array (padding dropped on the device)."""
+        v = self.to_f64(prec, t).view(self.total, self.LD)
+        if self.LD != self.N:
+            v = v[:, :self.N].contiguous()
+        return v.cpu().numpy()
 
     def split(self, host, width=None):
         """Cut a concatenated host array back into per-sequence views."""
@@ -246,7 +254,7 @@ class Engine(object):
         post, mstates, mscore = self.run_backward(prec, tdt, flags, blin, alpha, d_rd)
         out = {"logprob": logprob.cpu().numpy()}
         if want_post:
-            out["post"] = self.split(self.to_f64(prec, post).cpu().numpy(), self.N)
+            out["post"] = self.split(self.lattice_to_host(prec, post))
         if want_map:
             st64 = self.empty(self.total, self.torch.int64)
             _lib.check(self.lib.tehmm_widen_states(self.ctx.handle, self._p(mstates), self._p(st64), self.total))

@@ -227,7 +227,7 @@ def test_f32_vs_f64_at_scale():
 
 
 # ---------------------------------------------------------------- tensor-core tile kernels
-@pytest.mark.parametrize("N", [2, 6, 30, 32])
+@pytest.mark.parametrize("N", [2, 5, 30, 32])
 @pytest.mark.parametrize("warmup,fine_len", [(8, 16), (1, 24), (64, 0)])
 def test_tile_kernels_ragged(oracle, N, warmup, fine_len):
     """csrc/tile.cu (fp32, 16 chunks per warp on the tensor cores) against the oracle:
@@ -252,7 +252,7 @@ def test_tile_kernels_ragged(oracle, N, warmup, fine_len):
         ref_map = np.argmax(post, axis=1)
         assert np.mean(out["map_states"][i] == ref_map) >= 0.995
         assert out["map_score"][i] == pytest.approx(np.max(post, axis=1).sum(), rel=TOL["f32"])
-    if warmup == 1 and N >= 6:
+    if warmup == 1 and N >= 5:
         assert eng.ctx.stat("repair_passes_forward") > 0
     # score-only (no alpha lattice) and MAP-only variants
     lp = eng.score(precision="f32")

@@ -146,6 +146,7 @@ static void report(const char *name, F launch, int threads, double ops_per_iter_
 int main()
 {
 #define RUN_MMA(K, A, T) report("mma kind" #K " nacc" #A, [](float *o, long long *c) { k_mma<K, A><<<148, T>>>(o, c); }, T, A)
+    RUN_MMA(0, 1, 128); RUN_MMA(0, 2, 128); RUN_MMA(0, 4, 128); RUN_MMA(0, 4, 256); RUN_MMA(0, 4, 384);
     RUN_MMA(0, 8, 128); RUN_MMA(0, 8, 256); RUN_MMA(0, 8, 512); RUN_MMA(0, 16, 256); RUN_MMA(0, 2, 1024);
     RUN_MMA(1, 8, 128); RUN_MMA(1, 8, 256); RUN_MMA(1, 8, 512);
     RUN_MMA(2, 8, 256); RUN_MMA(2, 8, 512);
