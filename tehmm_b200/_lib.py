@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtehmm_b200.so")
+LIB_PATH = os.environ.get("TEHMM_B200_LIB") or os.path.join(_HERE, "libtehmm_b200.so")   # override: kernel experiments only
 
 TEHMM_OK, TEHMM_EINVAL, TEHMM_ECUDA, TEHMM_ENOMEM, TEHMM_ESTATE, TEHMM_ELIMIT = 0, -1, -2, -3, -4, -5
 F32, F64 = 0, 1

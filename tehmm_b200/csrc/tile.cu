@@ -55,7 +55,15 @@
 #include "scan.cuh"
 
 #define TILE_WARPS 8
-#define FWD_STAGES 6    // time steps of b staged ahead in shared memory
+// Measured on B200 (10 M x 30, forward with / without the alpha store, ms):
+//   per-lane LDGSTS + STG.128 0.887 / 0.525;  TB=2,NBL=4,NBS=2 0.845 / 0.738;
+//   TB=4,NBL=2,NBS=1 0.668 / 0.542  -- small bulk copies are TMA issue bound.
+#ifndef FWD_NBL
+#define FWD_NBL 2       // forward: bulk-load block buffers (TB time steps each)
+#endif
+#ifndef FWD_NBS
+#define FWD_NBS 1       // forward: bulk-store block buffers
+#endif
 #define BWD_STAGES 5    // time steps of b and alpha staged ahead
 #define TILE_STAGE_BYTES 2048   // per warp per stage: 16 rows x 128 bytes
 #define TILE_NEVER 0x7fffffff
@@ -234,6 +242,63 @@ __device__ __forceinline__ void store_row8(float *p, bool on, const float (&v)[8
     }
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D) and mbarriers, per warp ----------------
+// A tile row's lattice rows of consecutive time steps are consecutive in HBM
+// (LD = 32 floats = 128 bytes each, 16-byte aligned), so one cp.async.bulk moves
+// a row's next TB steps into shared memory; 16 lanes issue the 16 rows of a
+// block, completion is counted in bytes on a per-warp mbarrier.  Outputs go the
+// other way (st.shared, then cp.async.bulk shared -> global).  Compared with
+// per-lane LDGSTS / STG (8 cache lines per instruction, address registers held
+// until the LSU has read them) this takes the global traffic off the LSU queue:
+// the per-lane path spent two thirds of its time in mio_throttle / scoreboard
+// stalls (profiles/).
+#ifndef TB
+#define TB 4                          // time steps per bulk block
+#endif
+#define TMA_RS (TB * 128 + 16)        // bytes between tile rows of a block (pad: conflict-free LDS.128)
+#define TMA_BUF (16 * TMA_RS)         // bytes of one block buffer
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\t"
+                 "bra WAIT_%=;\n\t"
+                 "DONE_%=:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N_) : "memory"); }
+template <int N_> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N_) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void lds128(uint32_t a, float (&v)[8], int o)
+{
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[o]), "=f"(v[o + 1]), "=f"(v[o + 2]), "=f"(v[o + 3]) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 // ------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
 fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
@@ -241,14 +306,26 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 float *__restrict__ start_vec, float *__restrict__ end_vec,
                 double *__restrict__ cscale, const int *__restrict__ bad, int mode)
 {
-    extern __shared__ __align__(16) unsigned char tile_smem[];
+    extern __shared__ __align__(128) unsigned char tile_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
     constexpr int LD = 32;                        // lattice row stride (TehmmModelDev::LD for N <= 32)
-    // this lane's 16-byte slot of (stage 0, row 0, half 0)
-    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
-                           (uint32_t)(warp * FWD_STAGES * TILE_STAGE_BYTES + lane * 16);
+    // per warp: FWD_NBL load buffers, FWD_NBS store buffers, FWD_NBL mbarriers
+    constexpr int WARP_BYTES = (FWD_NBL + FWD_NBS) * TMA_BUF + 64;
+    const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(tile_smem) + (uint32_t)(warp * WARP_BYTES);
+    const uint32_t sbase = wbase + FWD_NBL * TMA_BUF;
+    const uint32_t bars = sbase + FWD_NBS * TMA_BUF;
+    // where this lane reads / writes its tile rows g and g+8 inside a block buffer
+    const uint32_t myoff = (uint32_t)(g * TMA_RS + 32 * q);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < FWD_NBL; ++i) mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    __syncwarp();
+    uint32_t nblk_done = 0;                       // load blocks consumed so far by this warp (barrier phases)
 
     TransFrag A;
     load_trans<false>(m, g, q, A);
@@ -264,7 +341,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
          gi += (int64_t)gridDim.x * TILE_WARPS) {
         // ---- schedule of the lane's two tile rows
         int ks[2], ke[2];
-        int64_t off[2], cid[2];
+        int64_t cid[2];
         bool first[2], pred[2];
         int kb = TILE_NEVER, kmax = 0;
 #pragma unroll
@@ -273,7 +350,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
             cid[r] = c;
             bool valid = c < b.nchunks;
             if (valid && mode == 1) valid = bad[c] != 0;
-            ks[r] = TILE_NEVER; ke[r] = 0; off[r] = 0; first[r] = false; pred[r] = false;
+            ks[r] = TILE_NEVER; ke[r] = 0; first[r] = false; pred[r] = false;
             if (valid) {
                 const TehmmChunk ch = b.chunks[c];
                 const int64_t dist = ch.t0 - ch.s0;
@@ -283,7 +360,6 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 else if (dist <= W) { ks[r] = W - (int)dist; first[r] = true; }
                 else ks[r] = 0;                                      // speculate from a flat vector
                 ke[r] = W + (int)(ch.t1 - ch.t0);
-                off[r] = (ch.t0 - W) * LD + 8 * q;
                 kb = min(kb, ks[r]);
                 kmax = max(kmax, ke[r]);
             }
@@ -291,6 +367,53 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         kb = __reduce_min_sync(TEHMM_FULL, kb);
         kmax = __reduce_max_sync(TEHMM_FULL, kmax);
         if (kmax <= 0) continue;
+
+        // ---- the tile row this lane moves with bulk copies (lanes 0..15: row = lane)
+        int oks = TILE_NEVER, oke = 0;
+        int64_t ooff = 0;                          // element offset of the row of clock 0
+        {
+            const int64_t c = gi * 16 + lane;
+            bool valid = lane < 16 && c < b.nchunks;
+            if (valid && mode == 1) valid = bad[c] != 0;
+            if (valid) {
+                const TehmmChunk ch = b.chunks[c];
+                const int64_t dist = ch.t0 - ch.s0;
+                if (dist == 0 || mode == 1) oks = W;
+                else if (dist <= W) oks = W - (int)dist;
+                else oks = 0;
+                oke = W + (int)(ch.t1 - ch.t0);
+                ooff = (ch.t0 - W) * LD;
+            }
+        }
+        const int nblk = (kmax - kb + TB - 1) / TB;
+        // bulk-load the b rows of block j (clocks kb + j*TB ...) into buffer (nblk_done + j) % FWD_NBL
+        auto issue_load = [&](int j) {
+            const uint32_t slot = (nblk_done + (uint32_t)j) % FWD_NBL;
+            const int k0 = kb + j * TB;
+            const int a = max(k0, oks), e = min(k0 + TB, oke);
+            const uint32_t bytes = e > a ? (uint32_t)(e - a) * 128u : 0u;
+            const uint32_t total = __reduce_add_sync(TEHMM_FULL, bytes);
+            fence_async_smem();                   // earlier reads of this buffer are done (WAR across proxies)
+            if (lane == 0) mbar_expect_tx(bars + 8 * slot, total);
+            __syncwarp();
+            if (bytes)
+                bulk_load(wbase + slot * TMA_BUF + (uint32_t)(lane * TMA_RS + (a - k0) * 128),
+                          blin + ooff + (int64_t)a * LD, bytes, bars + 8 * slot);
+        };
+        // bulk-store the alpha rows of block j from store buffer j % FWD_NBS
+        auto issue_store = [&](int j) {
+            const int k0 = kb + j * TB;
+            const int a = max(k0, W), e = min(min(k0 + TB, oke), kmax);
+            fence_async_smem();                   // st.shared above -> visible to the async proxy
+            __syncwarp();
+            if (lane < 16) {
+                if (e > a)
+                    bulk_store(alpha + ooff + (int64_t)a * LD,
+                               sbase + (uint32_t)((j % FWD_NBS) * TMA_BUF + lane * TMA_RS + (a - k0) * 128),
+                               (uint32_t)(e - a) * 128u);
+                bulk_commit();
+            }
+        };
 
         // next clock >= k at which some row of the tile starts or ends
         auto next_event = [&](int k) -> int {
@@ -309,115 +432,109 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
 #pragma unroll
         for (int c = 0; c < 8; ++c) xp[c] = 0ull;
 
-        const float *lp[2];             // row of the next clock to stage
-        float *sp[2];                   // alpha row of the current clock
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            lp[r] = blin + off[r] + (int64_t)kb * LD;
-            sp[r] = alpha + off[r] + (int64_t)kb * LD;
-        }
-        auto issue = [&](int k, int stage) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                stage_row(slot0 + (uint32_t)(stage * TILE_STAGE_BYTES + r * 1024), lp[r],
-                          k >= ks[r] && k < ke[r]);
-                lp[r] += LD;
-            }
-            stage_commit();
-        };
-
-#pragma unroll
-        for (int u = 0; u < FWD_STAGES - 1; ++u) issue(kb + u, u);
-        int rs = 0, ws = FWD_STAGES - 1;          // stage read / written at clock k
+        for (int j = 0; j < FWD_NBL - 1 && j < nblk; ++j) issue_load(j);
         int kev = next_event(kb);
-        for (int k = kb; k < kmax; ++k) {
-            issue(k + FWD_STAGES - 1, ws);
-            stage_wait<FWD_STAGES - 1>();         // the group of clock k has landed
-            float bt[2][8];
-            stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES), bt[0]);
-            stage_read(slot0 + (uint32_t)(rs * TILE_STAGE_BYTES + 1024), bt[1]);
-            const bool ev = k == kev;             // warp uniform, rare
-            if (ev) {
+        for (int j = 0; j < nblk; ++j) {
+            if (j + FWD_NBL - 1 < nblk) issue_load(j + FWD_NBL - 1);
+            const uint32_t slot = (nblk_done + (uint32_t)j) % FWD_NBL;
+            mbar_wait(bars + 8 * slot, ((nblk_done + (uint32_t)j) / FWD_NBL) & 1u);
+            const uint32_t lbuf = wbase + slot * TMA_BUF + myoff;
+            const uint32_t sbuf = sbase + (uint32_t)((j % FWD_NBS) * TMA_BUF) + myoff;
+            const bool storing = alpha != nullptr && kb + j * TB + TB > W;
+            if (storing && j >= FWD_NBS) {         // the bulk store that last used this buffer has read it
+                if (lane < 16) bulk_wait_read<FWD_NBS - 1>();
+                __syncwarp();
+            }
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (k == ks[r]) {             // the row starts here
-                        float v[8];
-                        if (mode == 1 && !first[r]) load_vec32(start_vec + cid[r] * 32 + 8 * q, v);
-                        else {
+            for (int s = 0; s < TB; ++s) {
+                const int k = kb + j * TB + s;
+                if (k >= kmax) break;
+                float bt[2][8];
+                lds128(lbuf + s * 128, bt[0], 0);
+                lds128(lbuf + s * 128 + 16, bt[0], 4);
+                lds128(lbuf + s * 128 + 8 * TMA_RS, bt[1], 0);
+                lds128(lbuf + s * 128 + 8 * TMA_RS + 16, bt[1], 4);
+                const bool ev = k == kev;             // warp uniform, rare
+                if (ev) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = ones[i];
+                    for (int r = 0; r < 2; ++r) {
+                        if (k == ks[r]) {             // the row starts here
+                            float v[8];
+                            if (mode == 1 && !first[r]) load_vec32(start_vec + cid[r] * 32 + 8 * q, v);
+                            else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = ones[i];
+                            }
+                            set_row(xp, r, v);
+                            scp[r] = 1.f; shp[r] = 0;
                         }
-                        set_row(xp, r, v);
-                        scp[r] = 1.f; shp[r] = 0;
                     }
                 }
-            }
-            // ---- the step: x <- (x A) .* (b * 2^-shp)
-            u64 bs[2][4];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const u64 s2 = pk2(scp[r], scp[r]);
-#pragma unroll
-                for (int p = 0; p < 4; ++p) bs[r][p] = fmul2(pk2(bt[r][2 * p], bt[r][2 * p + 1]), s2);
-            }
-            float acc[4][4];
-            tile_matmul(xp, A, acc);
-            float m0 = 0.f, m1 = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const float a0 = acc[nt][0] * lo2(bs[0][nt]), a1 = acc[nt][1] * hi2(bs[0][nt]);
-                const float c0 = acc[nt][2] * lo2(bs[1][nt]), c1 = acc[nt][3] * hi2(bs[1][nt]);
-                xp[2 * nt] = pk2(a0, c0);
-                xp[2 * nt + 1] = pk2(a1, c1);
-                m0 = fmax3(m0, a0, a1);
-                m1 = fmax3(m1, c0, c1);
-            }
-            int sh_now[2] = {shp[0], shp[1]};     // exponents applied in this step
-            if (ev) {
+                // ---- the step: x <- (x A) .* (b * 2^-shp)
+                u64 bs[2][4];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    if (k == ks[r] && first[r]) {  // alpha_0 = pi .* b_0
-                        float v[8];
-                        float mm = 0.f;
+                    const u64 s2 = pk2(scp[r], scp[r]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { v[i] = pi[i] * bt[r][i]; mm = fmaxf(mm, v[i]); }
-                        set_row(xp, r, v);
-                        if (r == 0) m0 = mm; else m1 = mm;
-                        sh_now[r] = 0;
+                    for (int p = 0; p < 4; ++p) bs[r][p] = fmul2(pk2(bt[r][2 * p], bt[r][2 * p + 1]), s2);
+                }
+                float acc[4][4];
+                tile_matmul(xp, A, acc);
+                float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float a0 = acc[nt][0] * lo2(bs[0][nt]), a1 = acc[nt][1] * hi2(bs[0][nt]);
+                    const float c0 = acc[nt][2] * lo2(bs[1][nt]), c1 = acc[nt][3] * hi2(bs[1][nt]);
+                    xp[2 * nt] = pk2(a0, c0);
+                    xp[2 * nt + 1] = pk2(a1, c1);
+                    m0 = fmax3(m0, a0, a1);
+                    m1 = fmax3(m1, c0, c1);
+                }
+                int sh_now[2] = {shp[0], shp[1]};     // exponents applied in this step
+                if (ev) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        if (k == ks[r] && first[r]) {  // alpha_0 = pi .* b_0
+                            float v[8];
+                            float mm = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { v[i] = pi[i] * bt[r][i]; mm = fmaxf(mm, v[i]); }
+                            set_row(xp, r, v);
+                            if (r == 0) m0 = mm; else m1 = mm;
+                            sh_now[r] = 0;
+                        }
                     }
                 }
-            }
-            scale_of(quad_max(m0), scp[0], shp[0]);
-            scale_of(quad_max(m1), scp[1], shp[1]);
-            if (k >= W) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool act = k < ke[r];
-                    esum[r] += act ? sh_now[r] : 0;
-                    if (alpha) {
-                        float v[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] = r ? hi2(xp[c]) : lo2(xp[c]);
-                        store_row8(sp[r], act, v);
+                scale_of(quad_max(m0), scp[0], shp[0]);
+                scale_of(quad_max(m1), scp[1], shp[1]);
+                if (k >= W) {
+                    esum[0] += k < ke[0] ? sh_now[0] : 0;
+                    esum[1] += k < ke[1] ? sh_now[1] : 0;
+                    if (alpha) {                       // masked rows stage garbage that is never copied out
+                        sts128(sbuf + s * 128, lo2(xp[0]), lo2(xp[1]), lo2(xp[2]), lo2(xp[3]));
+                        sts128(sbuf + s * 128 + 16, lo2(xp[4]), lo2(xp[5]), lo2(xp[6]), lo2(xp[7]));
+                        sts128(sbuf + s * 128 + 8 * TMA_RS, hi2(xp[0]), hi2(xp[1]), hi2(xp[2]), hi2(xp[3]));
+                        sts128(sbuf + s * 128 + 8 * TMA_RS + 16, hi2(xp[4]), hi2(xp[5]), hi2(xp[6]), hi2(xp[7]));
                     }
+                } else if (k == W - 1 && mode == 0) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+                        if (pred[r] && k >= ks[r] && k < ke[r]) store_row_vec32(start_vec + cid[r] * 32 + 8 * q, xp, r);
                 }
-            } else if (k == W - 1 && mode == 0) {
+                if (ev) {
 #pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (pred[r] && k >= ks[r] && k < ke[r]) store_row_vec32(start_vec + cid[r] * 32 + 8 * q, xp, r);
+                    for (int r = 0; r < 2; ++r)
+                        if (k + 1 == ke[r]) store_row_vec32(end_vec + cid[r] * 32 + 8 * q, xp, r);
+                    kev = next_event(k + 1);
+                }
             }
-            if (ev) {
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-                    if (k + 1 == ke[r]) store_row_vec32(end_vec + cid[r] * 32 + 8 * q, xp, r);
-                kev = next_event(k + 1);
-            }
-#pragma unroll
-            for (int r = 0; r < 2; ++r) sp[r] += LD;
-            rs = rs + 1 == FWD_STAGES ? 0 : rs + 1;
-            ws = ws + 1 == FWD_STAGES ? 0 : ws + 1;
+            if (storing) issue_store(j);
         }
-        stage_wait<0>();
+        nblk_done += (uint32_t)nblk;
+        if (alpha) {
+            if (lane < 16) bulk_wait<0>();         // the stores have left shared memory and are complete
+            __syncwarp();
+        }
 
         // log of everything taken out of each chunk: exponents and row maxima
         for (int rr = 0; rr < 16; ++rr) {
@@ -446,7 +563,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
 {
     constexpr bool want_post = (OUT & TEHMM_BWD_POSTERIORS) != 0;
     constexpr bool want_map = (OUT & TEHMM_BWD_MAP) != 0;
-    extern __shared__ __align__(16) unsigned char tile_smem[];
+    extern __shared__ __align__(128) unsigned char tile_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
@@ -691,7 +808,7 @@ cudaError_t tehmm_launch_forward_tile(cudaStream_t st, const TehmmModelDev &m, c
                                       float *start_vec, float *end_vec, double *cscale,
                                       const int *bad, int mode, int sms)
 {
-    const int smem = TILE_WARPS * FWD_STAGES * TILE_STAGE_BYTES;
+    const int smem = TILE_WARPS * ((FWD_NBL + FWD_NBS) * TMA_BUF + 64);
     cudaError_t e = cudaFuncSetAttribute(fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     fwd_tile_kernel<<<tile_grid(b, sms), TILE_WARPS * 32, smem, st>>>(m, b, blin, rowmax, alpha, start_vec,
