@@ -379,8 +379,72 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     size_t o_tt = align_up(o_tab + (size_t)K * N * S * 8), o_off = align_up(o_tt + (size_t)rows * N * 8);
     size_t o_ns = align_up(o_off + (size_t)K * 4), o_lins = align_up(o_ns + (size_t)K * 4);
     size_t o_lint = align_up(o_lins + (size_t)NP * 8), o_cuts = align_up(o_lint + (size_t)NP * NP * 8);
-    size_t o_cutt = align_up(o_cuts + (size_t)NP * 8), total = align_up(o_cutt + (size_t)NP * NP * 8);
+    size_t o_cutt = align_up(o_cuts + (size_t)NP * 8), o_end = align_up(o_cutt + (size_t)NP * NP * 8);
+    // merged emission tables (fp32 path, N <= 32): group tracks so that a row of the batch
+    // needs as few table look-ups as possible within the shared-memory budget.  Greedy:
+    // repeatedly merge the two groups whose merge adds the fewest rows.
+    struct Grp { std::vector<int> trk; int64_t rows; };
+    std::vector<Grp> grp;
+    int64_t grows = 0;
+    if (NS == 1) {
+        for (int k = 0; k < K; ++k) { grp.push_back(Grp{{k}, nsym[k]}); grows += nsym[k]; }
+        for (;;) {
+            int bi = -1, bj = -1;
+            int64_t best = 0;
+            for (size_t i = 0; i < grp.size(); ++i)
+                for (size_t j = i + 1; j < grp.size(); ++j) {
+                    if (grp[i].trk.size() + grp[j].trk.size() > 4) continue;
+                    const int64_t add = grp[i].rows * grp[j].rows - grp[i].rows - grp[j].rows;
+                    if (grows + add > TEHMM_GROWS_MAX) continue;
+                    if (bi < 0 || add < best) { bi = (int)i; bj = (int)j; best = add; }
+                }
+            if (bi < 0) break;
+            grp[bi].trk.insert(grp[bi].trk.end(), grp[bj].trk.begin(), grp[bj].trk.end());
+            grp[bi].rows *= grp[bj].rows;
+            grp.erase(grp.begin() + bj);
+            grows += best;
+        }
+        if ((int)grp.size() > TEHMM_GMAX || grows > TEHMM_GROWS_MAX) { grp.clear(); grows = 0; }
+    }
+    const int G = (int)grp.size();
+    size_t o_gtab = o_end, o_gc = align_up(o_gtab + (size_t)grows * 32 * 4);
+    size_t o_gd = align_up(o_gc + (size_t)grows * 8), total = align_up(o_gd + (size_t)std::max(G, 1) * TEHMM_GDESC * 4);
     std::vector<unsigned char> h(total, 0);
+    if (G > 0) {
+        float *gtab = (float *)&h[o_gtab];
+        double *gc = (double *)&h[o_gc];
+        int32_t *gd = (int32_t *)&h[o_gd];
+        int64_t base = 0;
+        std::vector<double> acc(N);
+        for (int gi = 0; gi < G; ++gi) {
+            const Grp &gr = grp[gi];
+            int32_t *d = gd + (size_t)gi * TEHMM_GDESC;
+            d[0] = (int32_t)gr.trk.size();
+            d[1] = (int32_t)base;
+            int64_t stride = 1;
+            for (size_t i = 0; i < gr.trk.size(); ++i) {
+                d[2 + i] = gr.trk[i];
+                d[6 + i] = (int32_t)stride;
+                stride *= nsym[gr.trk[i]];
+            }
+            for (int64_t row = 0; row < gr.rows; ++row) {
+                for (int j = 0; j < N; ++j) acc[j] = 0.0;
+                int64_t rem = row;
+                for (size_t i = 0; i < gr.trk.size(); ++i) {       // same track order as the reference's sum
+                    const int k = gr.trk[i];
+                    const int sym = (int)(rem % nsym[k]);
+                    rem /= nsym[k];
+                    for (int j = 0; j < N; ++j) acc[j] += table[((size_t)k * N + j) * S + sym];
+                }
+                double mx = -INFINITY;
+                for (int j = 0; j < N; ++j) { acc[j] *= normalize; mx = std::max(mx, acc[j]); }
+                if (!(mx > -INFINITY)) mx = 0.0;
+                gc[base + row] = mx;
+                for (int j = 0; j < 32; ++j) gtab[(size_t)(base + row) * 32 + j] = j < N ? (float)(acc[j] - mx) : 0.f;
+            }
+            base += gr.rows;
+        }
+    }
     memcpy(&h[o_ls], log_start, (size_t)N * 8);
     memcpy(&h[o_lt], log_trans, (size_t)N * N * 8);
     memcpy(&h[o_tab], table, (size_t)K * N * S * 8);
@@ -418,6 +482,9 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     m.tab_off = (const int32_t *)(d + o_off); m.track_nsym = (const int32_t *)(d + o_ns);
     m.lin_start = (const double *)(d + o_lins); m.lin_trans = (const double *)(d + o_lint);
     m.cut_start = (const double *)(d + o_cuts); m.cut_trans = (const double *)(d + o_cutt);
+    m.G = normalize > 0.0 ? G : 0;      // a negative factor would flip the row maxima
+    m.grows = (int)grows;
+    m.gtab = (const float *)(d + o_gtab); m.gc = (const double *)(d + o_gc); m.gdesc = (const int32_t *)(d + o_gd);
     c->has_model = true;
     return TEHMM_OK;
 }

@@ -45,7 +45,19 @@ struct TehmmModelDev {
     const double *lin_trans;    // [NP*NP]  exp(log_trans)
     const double *cut_start;    // [NP]     log_start with <= cut mapped to -inf
     const double *cut_trans;    // [NP*NP]  log_trans with <= cut mapped to -inf
+    // Merged emission tables of the fp32 path (emission.cu, emission_merged_kernel):
+    // tracks are grouped, a group's table has one row per COMBINATION of its
+    // tracks' symbols, holding normalize * sum of the tracks' log-probs, split
+    // into the row's maximum over states (gc, float64) and the remainder
+    // (gtab, float32, <= 0, 32 floats per row).  G = 0: not available.
+    int G, grows;
+    const float *gtab;          // [grows][32]
+    const double *gc;           // [grows]
+    const int32_t *gdesc;       // [G][TEHMM_GDESC]: ntracks, first row, track[4], stride[4]
 };
+#define TEHMM_GDESC 10
+#define TEHMM_GMAX 16           // groups
+#define TEHMM_GROWS_MAX 1200    // merged rows (x 128 bytes of shared memory)
 
 struct TehmmBatchDev {
     const void *obs;

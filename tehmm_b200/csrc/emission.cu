@@ -173,6 +173,218 @@ emission_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
     }
 }
 
+// ---------------------------------------------------------------------------
+// fp32 production path: merged, centred tables (TehmmModelDev::gtab / gc).
+// The generic kernel above is bound by shared-memory bandwidth: K float64 table
+// rows of 8N bytes per time step (ncu: 1.07 ms of LDS wavefronts at 10 M x 30 x 10).
+// Here tracks are merged into G <= K groups (one look-up per group) and a table
+// row is 128 bytes of float32 -- the part of the log-probability that differs
+// between states -- while the part common to all states (the row's maximum, kept
+// in float64) is summed per time step by one lane and goes into rowmax.  The
+// float32 rounding is that of the elog lattice itself (relative 6e-8 of the
+// distance to the row maximum); the float64 verification mode never takes this
+// path.  One warp per time step, lane = state, 16 steps staged per iteration.
+#define EMG_WARPS 32
+#define EMG_ROWS 16
+
+__device__ __forceinline__ void emg_flag_row(int64_t t, const int64_t *seq_off, int64_t nseq, int *seq_flag)
+{
+    int64_t lo = 0, hi = nseq;   // sequence of row t
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (seq_off[mid] <= t) lo = mid; else hi = mid; }
+    seq_flag[lo] = 1;
+}
+
+// GT = number of groups when 1..8 (look-ups fully unrolled), 0 = any (loop)
+template <typename OBS, int GT, bool RATIO>
+__global__ void __launch_bounds__(EMG_WARPS * 32, 1)
+emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
+                       const double *__restrict__ ratios, float *__restrict__ elog,
+                       float *__restrict__ blin, double *__restrict__ rowmax,
+                       int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq)
+{
+    extern __shared__ __align__(16) unsigned char em_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = m.K, N = m.N, LD = m.LD;
+    const int G = GT ? GT : m.G;
+    // layout: gtab | gc | gdesc | nsym | per warp { csum[16], offs[16][16] }
+    float *tab_s = reinterpret_cast<float *>(em_smem);
+    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * 32);
+    int32_t *gd_s = reinterpret_cast<int32_t *>(gc_s + m.grows);
+    int32_t *nsym_s = gd_s + TEHMM_GMAX * TEHMM_GDESC;
+    const size_t per_warp = (size_t)EMG_ROWS * 8 + (size_t)EMG_ROWS * 16 * 4;
+    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
+    unsigned char *wbase = em_smem + head + (size_t)warp * per_warp;
+    double *csum_s = reinterpret_cast<double *>(wbase);
+    int32_t *offs = reinterpret_cast<int32_t *>(wbase + EMG_ROWS * 8);
+
+    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * 32; e += blockDim.x) tab_s[e] = m.gtab[e];
+    for (int e = threadIdx.x; e < m.grows; e += blockDim.x) gc_s[e] = m.gc[e];
+    for (int e = threadIdx.x; e < G * TEHMM_GDESC; e += blockDim.x) gd_s[e] = m.gdesc[e];
+    for (int e = threadIdx.x; e < K; e += blockDim.x) nsym_s[e] = m.track_nsym[e];
+    __syncthreads();
+
+    // shared-space address of this lane's column of table row 0; offs holds byte offsets of rows
+    const uint32_t lane_tab = (uint32_t)__cvta_generic_to_shared(tab_s) + (uint32_t)lane * 4u;
+    const uint32_t offs_a = (uint32_t)__cvta_generic_to_shared(offs);
+    const bool is_state = lane < N;
+
+    // state-dependent part of row r of the staged batch: sum of the groups' table rows (all <= 0)
+    auto gather = [&](int r) -> float {
+        float v = 0.f;
+        if (GT) {
+            int o[8];
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(offs_a + r * 64));
+            if (GT > 4)
+                asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(offs_a + r * 64 + 16));
+#pragma unroll
+            for (int gq = 0; gq < GT; ++gq) {
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)o[gq]));
+                v += x;
+            }
+        } else {
+            for (int gq = 0; gq < G; ++gq) {
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)offs[r * 16 + gq]));
+                v += x;
+            }
+        }
+        return v;
+    };
+    // normalised row out; returns the maximum over states taken out of v
+    auto emit_row = [&](float *pe, float *pb, float v, float rf) -> float {
+        // v <= 0 everywhere: the bit patterns of non-positive floats grow with the magnitude,
+        // so the maximum is the unsigned minimum (+0.0 = 0 included; -inf is the largest)
+        const unsigned bits = is_state ? __float_as_uint(v) : 0xff800000u;
+        const float Mf = __uint_as_float(__reduce_min_sync(TEHMM_FULL, bits));
+        float d = Mf > -INFINITY ? v - Mf : 0.f;
+        if (RATIO) d *= rf;
+        float bl = __expf(d);
+        if (!is_state) { d = 0.f; bl = 0.f; }          // padding columns
+        if (lane < LD) {
+            if (pe) *pe = d;
+            if (pb) *pb = bl;
+        }
+        return Mf;
+    };
+
+    const int64_t nblocks = (total + EMG_ROWS - 1) / EMG_ROWS;
+    for (int64_t blk = (int64_t)blockIdx.x * EMG_WARPS + warp; blk < nblocks;
+         blk += (int64_t)gridDim.x * EMG_WARPS) {
+        const int64_t tb = blk * EMG_ROWS;
+        const int rows = (int)min((int64_t)EMG_ROWS, total - tb);
+        __syncwarp();
+        // ---- stage: byte offset of the table row of every (row, group); symbols straight from HBM
+        bool bad = false;
+        for (int e = lane; e < rows * G; e += 32) {
+            const int r = e / G, gq = e - r * G;
+            const int32_t *d = gd_s + gq * TEHMM_GDESC;
+            int idx = d[1];
+            for (int i = 0; i < d[0]; ++i) {
+                const int k = d[2 + i];
+                const int sym = (int)obs[(tb + r) * K + k];
+                bad |= (unsigned)sym >= (unsigned)nsym_s[k];
+                idx += sym * d[6 + i];
+            }
+            offs[r * 16 + gq] = idx * 128;
+        }
+        const bool any_slow = __any_sync(TEHMM_FULL, bad);
+        __syncwarp();
+        float mf_keep = 0.f;                     // lane r keeps the state maximum of row r
+        double c_keep = 0.0;
+        if (!any_slow) {
+            if (lane < rows) {
+                double c = 0.0;
+                for (int gq = 0; gq < G; ++gq) c += gc_s[offs[lane * 16 + gq] >> 7];
+                c_keep = c;
+            }
+            float *pe = elog ? elog + tb * LD + lane : nullptr;
+            float *pb = blin ? blin + tb * LD + lane : nullptr;
+            if (rows == EMG_ROWS) {
+#pragma unroll
+                for (int r = 0; r < EMG_ROWS; r += 2) {          // two rows in flight
+                    const float v0 = gather(r), v1 = gather(r + 1);
+                    const float r0 = RATIO ? (float)ratios[tb + r] : 1.f, r1 = RATIO ? (float)ratios[tb + r + 1] : 1.f;
+                    const float M0 = emit_row(pe ? pe + r * LD : nullptr, pb ? pb + r * LD : nullptr, v0, r0);
+                    const float M1 = emit_row(pe ? pe + (r + 1) * LD : nullptr, pb ? pb + (r + 1) * LD : nullptr, v1, r1);
+                    if (lane == r) mf_keep = M0;
+                    if (lane == r + 1) mf_keep = M1;
+                }
+            } else {
+                for (int r = 0; r < rows; ++r) {
+                    const float Mr = emit_row(pe ? pe + r * LD : nullptr, pb ? pb + r * LD : nullptr, gather(r),
+                                              RATIO ? (float)ratios[tb + r] : 1.f);
+                    if (lane == r) mf_keep = Mr;
+                }
+            }
+        } else {
+            // a symbol outside its track's table: index the dense float64 table exactly as the
+            // reference does (rare)
+            for (int r = 0; r < rows; ++r) {
+                double v = 0.0;
+                if (is_state)
+                    for (int k = 0; k < K; ++k) v += m.table[((int64_t)k * N + lane) * m.S + (int64_t)obs[(tb + r) * K + k]];
+                v *= m.normalize;
+                const double M = warp_max(is_state ? v : -INFINITY);
+                emit_row(elog ? elog + (tb + r) * LD + lane : nullptr, blin ? blin + (tb + r) * LD + lane : nullptr,
+                         M > -INFINITY ? (float)(v - M) : 0.f, RATIO ? (float)ratios[tb + r] : 1.f);
+                if (lane == r) { mf_keep = 0.f; c_keep = M; }
+            }
+        }
+        // ---- row maxima of the batch, one lane per row
+        if (lane < rows) {
+            double M = (double)mf_keep + c_keep;
+            if (RATIO) M *= ratios[tb + lane];
+            rowmax[tb + lane] = M;
+            if (!(M > TEHMM_MINDBL) && seq_flag) emg_flag_row(tb + lane, seq_off, nseq, seq_flag);   // _emission.pyx:73-80
+        }
+    }
+}
+
+static size_t emg_smem_bytes(const TehmmModelDev &m)
+{
+    const size_t per_warp = (size_t)EMG_ROWS * 8 + (size_t)EMG_ROWS * 16 * 4;
+    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
+    return head + EMG_WARPS * per_warp;
+}
+
+template <typename OBS, int GT, bool RATIO>
+static cudaError_t launch_emg3(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                               const double *ratios, float *elog, float *blin, double *rowmax,
+                               int *seq_flag, int sms)
+{
+    const size_t smem = emg_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(emission_merged_kernel<OBS, GT, RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t need = ((b.total + EMG_ROWS - 1) / EMG_ROWS + EMG_WARPS - 1) / EMG_WARPS;
+    if (need < 1) need = 1;
+    const int grid = (int)(need < sms ? need : sms);
+    emission_merged_kernel<OBS, GT, RATIO><<<grid, EMG_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
+                                                                               rowmax, seq_flag, b.seq_off, b.nseq);
+    return cudaGetLastError();
+}
+
+template <typename OBS>
+static cudaError_t launch_emg(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                              const double *ratios, float *elog, float *blin, double *rowmax,
+                              int *seq_flag, int sms)
+{
+#define EMG_GO(GT) (ratios ? launch_emg3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms) \
+                           : launch_emg3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms))
+    switch (m.G) {
+    case 1: return EMG_GO(1);
+    case 2: return EMG_GO(2);
+    case 3: return EMG_GO(3);
+    case 4: return EMG_GO(4);
+    case 5: return EMG_GO(5);
+    case 6: return EMG_GO(6);
+    case 7: return EMG_GO(7);
+    case 8: return EMG_GO(8);
+    default: return EMG_GO(0);
+    }
+#undef EMG_GO
+}
+
 // _emission.pyx:59,73-80: the running maximum is never reset, so rows are
 // zeroed only while no earlier row of the sequence had a value > -1e20.
 // One warp per flagged sequence; almost never runs.
@@ -263,6 +475,13 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
     cudaError_t e = cudaMemsetAsync(seq_flag, 0, sizeof(int) * (size_t)b.nseq, st);
     if (e == cudaSuccess) {
         if (frame) e = launch_em_obs<float, 1>(st, m, b, ratios, nullptr, nullptr, nullptr, frame, seq_flag, sms);
+        else if (prec == TEHMM_F32 && m.G > 0 && emg_smem_bytes(m) <= 227 * 1024) {
+            // out-of-range symbols in the slow branch index the dense table: obs must be < S there too,
+            // exactly the generic kernel's contract
+            if (b.obs_bytes == 1) e = launch_emg<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+            else if (b.obs_bytes == 2) e = launch_emg<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+            else e = launch_emg<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+        }
         else if (prec == TEHMM_F32) e = launch_em_obs<float, 0>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, nullptr, seq_flag, sms);
         else e = launch_em_obs<double, 0>(st, m, b, ratios, (double *)elog, (double *)blin, rowmax, nullptr, seq_flag, sms);
     }
