@@ -605,7 +605,7 @@ static Scratch carve(const tehmm_ctx *c, int prec)
     s.xdiag = o; o = align_up(o + nc * NP * ts);
     s.gamma0 = o; o = align_up(o + (size_t)c->b.nseq * NP * ts);
     s.tilemap = o; o = align_up(o + (size_t)c->b.ntiles * NP);
-    s.cmap = o; o = align_up(o + nc * NP);
+    s.cmap = o; o = align_up(o + std::max(nc * NP, 3 * nb));
     s.chunk_end = o; o = align_up(o + nc);
     const size_t smem = tehmm_stats_smem_bytes(c->m.tab_rows, c->m.N, c->m.K, prec);
     s.nparts = 0;
@@ -810,8 +810,12 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     void *sv = w + s.start_vec, *ev = w + s.end_vec;
     double *sp = (double *)(w + s.part_a);
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
-    uint8_t *spec_end = (uint8_t *)(w + s.cmap), *pred = spec_end + c->b.nchunks, *forced = pred + c->b.nchunks;
+    // the traceback is latency bound (one dependent arg-max per step): it walks the FINE partition,
+    // five times as many chunks in flight, while the issue-bound DP keeps the coarse one
+    const TehmmBatchDev &TBP = c->bf;
+    uint8_t *spec_end = (uint8_t *)(w + s.cmap), *pred = spec_end + TBP.nchunks, *forced = pred + TBP.nchunks;
     const int grid = scan_grid(c);
+    const int tb_grid = (int)std::max<int64_t>(1, std::min<int64_t>((TBP.nchunks + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA, (int64_t)c->sms * 5));
     const TehmmBatchDev &PB = c->b;
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     // ---- DP: delta lattice, chunk starts speculated / verified / repaired
@@ -831,19 +835,19 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         c->launches += 1;
     }
     // ---- traceback: chunk end states speculated / verified / repaired
-    CU(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)c->b.nchunks, st));
-    CU(tehmm_launch_traceback(st, c->m, c->b, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 0, grid));
+    CU(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)TBP.nchunks, st));
+    CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 0, tb_grid));
     c->launches += 1;
     for (int64_t pass = 0;; ++pass) {
-        CU(tehmm_launch_tb_verify(st, c->b, spec_end, pred, forced, bad, nbad));
+        CU(tehmm_launch_tb_verify(st, TBP, spec_end, pred, forced, bad, nbad));
         c->launches += 1;
         int nb = 0;
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
-        if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
+        if (pass == 0) adapt_warmup(c, nb, TBP.nchunks);
         if (nb == 0) break;
-        if (pass >= max_pass) return fail(TEHMM_ESTATE, "traceback repair did not converge (%d chunks left)", nb);
+        if (pass >= TBP.nchunks + 1 && pass >= max_pass) return fail(TEHMM_ESTATE, "traceback repair did not converge (%d chunks left)", nb);
         c->stat_repair_tb += 1; c->stat_bad_tb += nb;
-        CU(tehmm_launch_traceback(st, c->m, c->b, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, grid));
+        CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, tb_grid));
         c->launches += 1;
     }
     CU(tehmm_launch_rescore(st, c->m, c->b, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));

@@ -29,7 +29,7 @@
 #include "scan.cuh"
 
 #define VIT_U 4
-#define TB_PF 12   // delta rows in flight ahead of the traceback walk
+#define TB_PF 6    // delta rows in flight ahead of the traceback walk
 
 template <typename T, int NS, bool RATIO>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
@@ -240,7 +240,7 @@ __device__ __forceinline__ int warp_argmax_first(const T (&v)[NS], int lane)
 // record the state it implies for the left neighbour (pred).  mode 1: redo the
 // chunks whose end state was wrong, from the forced end state.
 template <typename T, int NS, bool RATIO>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 5 : 1)
 vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lattice,
                      const double *__restrict__ ratios, uint8_t *__restrict__ states,
                      int64_t *__restrict__ states64, uint8_t *__restrict__ spec_end,
