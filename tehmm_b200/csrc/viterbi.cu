@@ -88,8 +88,8 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
         };
         auto store_d = [&](unsigned row) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s)
-                if (own[s]) ll[row * Nu + (unsigned)(lane + 32 * s)] = d[s];
+            for (int s = 0; s < NS; ++s)     // padding columns (N..LD-1) carry -inf
+                if (lane + 32 * s < m.LD) ll[row * Nu + (unsigned)(lane + 32 * s)] = own[s] ? d[s] : NEG;
         };
         auto init = [&](unsigned row, const T (&et)[NS]) {
 #pragma unroll
@@ -182,7 +182,7 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
                 const float v = y[0] + (own[0] ? et : -INFINITY);
                 const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
                 dd = v - (M > -INFINITY ? M : 0.f);
-                if (own[0]) *lp = dd;
+                *lp = dd;                       // padding columns carry -inf (LD = 32: every lane has one)
                 lp += Nu;
             };
             float en[VIT_U];
@@ -432,6 +432,108 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
     }
 }
 
+// Traceback, FOUR chunks per warp (fp32, N <= 32, no segment ratios).
+// The one-chunk-per-warp walk above spends ~30 issue slots per step on a
+// 32-lane arg-max (REDUX + ballot) of which 30 lanes matter.  Here a chunk gets
+// eight lanes, each owning four consecutive states: one LDG.128 + one LDS.128
+// per step fetch delta[t-1][4u..4u+3] and logA[4u..4u+3][state], the arg-max is
+// a 4-way local minimum of bit patterns (every candidate is <= 0, so the largest
+// value has the smallest unsigned pattern), three xor-shuffles and one ballot
+// (ties: lowest state, as _hmm.pyx:232-247).  ~11 issue slots per chunk step.
+#define TB4_PF 4     // delta rows in flight per chunk
+
+__device__ __forceinline__ int tb4_argmax(float c0, float c1, float c2, float c3, int u, unsigned segshift, int lane0)
+{
+    const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
+    const unsigned m01 = min(b0, b1), m23 = min(b2, b3);
+    const int i01 = b1 < b0 ? 1 : 0, i23 = b3 < b2 ? 3 : 2;
+    const unsigned ml = min(m01, m23);
+    const int il = m23 < m01 ? i23 : i01;
+    unsigned mg = ml;
+    mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 1));
+    mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 2));
+    mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 4));
+    const unsigned vote = __ballot_sync(TEHMM_FULL, ml == mg);
+    const int ulo = __ffs((vote >> segshift) & 0xffu) - 1;
+    return __shfl_sync(TEHMM_FULL, 4 * u + il, lane0 + ulo);
+}
+
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 4)
+vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ lattice,
+                      uint8_t *__restrict__ states, int64_t *__restrict__ states64,
+                      uint8_t *__restrict__ spec_end, uint8_t *__restrict__ pred,
+                      const uint8_t *__restrict__ forced_end, const int *__restrict__ bad, int mode)
+{
+    __shared__ __align__(16) float AT[32 * 32];            // AT[s*32 + i] = min(logA[i][s], 0)
+    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+        const int s = e >> 5, i = e & 31;
+        AT[e] = fminf((float)m.cut_trans[(int64_t)i * 32 + s], 0.f);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = lane >> 3, u = lane & 7;
+    const unsigned segshift = 8u * (unsigned)c;
+    const int lane0 = 8 * c;
+    const uint32_t at_lane = (uint32_t)__cvta_generic_to_shared(AT) + (uint32_t)u * 16u;
+
+    for (int64_t wg = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; wg * 4 < b.nchunks;
+         wg += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
+        const int64_t ci = wg * 4 + c;
+        bool valid = ci < b.nchunks;
+        if (valid && mode == 1) valid = bad[ci] != 0;
+        int row = 0, rlast = 0, st = 0;
+        bool has_pred = false;
+        int64_t tbase = 0;
+        if (valid) {
+            const TehmmChunk ch = b.chunks[ci];
+            has_pred = ch.t0 > ch.s0;
+            tbase = has_pred ? ch.t0 - 1 : ch.t0;        // row 0 = the left neighbour's last step, if any
+            rlast = (int)(ch.t1 - 1 - tbase);
+            row = rlast;
+            if (mode == 1) st = forced_end[ci];
+            else if (ch.t1 < ch.s1)                      // speculate: enter from `warmup` steps to the right
+                row = (int)min((int64_t)rlast + b.warmup, ch.s1 - 1 - tbase);
+        }
+        const float *__restrict__ ll = lattice + tbase * 32 + 4 * u;
+        {   // np.argmax of the row the walk starts from (not used by forced / invalid slots)
+            const float4 dv = *reinterpret_cast<const float4 *>(ll + (int64_t)row * 32);
+            const int s0 = tb4_argmax(dv.x, dv.y, dv.z, dv.w, u, segshift, lane0);
+            if (valid && mode == 0) st = s0;
+        }
+        int spec = st;
+        float4 ring[TB4_PF];
+#pragma unroll
+        for (int p = 0; p < TB4_PF; ++p) ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - p, 0) * 32);
+        while (__any_sync(TEHMM_FULL, row >= 1)) {
+#pragma unroll
+            for (int p = 0; p < TB4_PF; ++p) {
+                const bool act = row >= 1;
+                if (act && row == rlast) spec = st;
+                if (act && row <= rlast && u == 0) {
+                    states[tbase + row] = (uint8_t)st;
+                    if (states64) states64[tbase + row] = st;
+                }
+                const float4 dv = ring[p];
+                ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - TB4_PF, 0) * 32);
+                float4 a;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(at_lane + (uint32_t)st * 128u));
+                const int sn = tb4_argmax(dv.x + a.x, dv.y + a.y, dv.z + a.z, dv.w + a.w, u, segshift, lane0);
+                if (act) { st = sn; row -= 1; }
+            }
+        }
+        if (valid && u == 0) {
+            if (rlast == 0) spec = st;
+            spec_end[ci] = (uint8_t)spec;
+            if (has_pred) pred[ci] = (uint8_t)st;        // the state the left neighbour must end in
+            else {
+                states[tbase] = (uint8_t)st;
+                if (states64) states64[tbase] = st;
+            }
+        }
+    }
+}
+
 // bad[c-1] = the end state chunk c-1 assumed differs from the state its right
 // neighbour c really reaches at t0-1; the true state is handed to the repair pass.
 __global__ void vit_tb_verify_kernel(TehmmBatchDev b, uint8_t *spec_end, const uint8_t *pred,
@@ -559,6 +661,12 @@ cudaError_t tehmm_launch_traceback(cudaStream_t st, const TehmmModelDev &m, cons
                                    int mode, int grid)
 {
     if (prec == TEHMM_F32) {
+        if (m.NS == 1 && m.LD == 32 && !ratios) {
+            const int64_t need = ((b.nchunks + 3) / 4 + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
+            const int g4 = (int)(need < grid ? (need < 1 ? 1 : need) : grid);
+            vit_traceback4_kernel<<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode);
+            return cudaGetLastError();
+        }
         if (m.NS == 1) return launch_tb<float, 1>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
         return launch_tb<float, 2>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
     }
