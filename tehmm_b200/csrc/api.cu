@@ -850,7 +850,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, tb_grid));
         c->launches += 1;
     }
-    CU(tehmm_launch_rescore(st, c->m, c->b, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));
+    CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));   // latency bound too: fine partition
     c->launches += 2;
     return TEHMM_OK;
 }
