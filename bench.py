@@ -62,56 +62,81 @@ def workload_config(T, gpus):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock / throttle reasons DURING the timed region.  The timed region is a
+    few tens of milliseconds, far below nvidia-smi's sampling period, so NVML is
+    polled directly from a thread (nvidia-smi --query-gpu is the fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nvml = None
+        self.thread = threading.Thread(target=self._poll if self.nvml else self._poll_smi, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                try:
+                    power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    power = 0.0
+                self.samples.append((sm, reasons, power))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                bits = 0
+                for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[3:7]):
+                    if v.lower().startswith("active"):
+                        bits |= bit
+                self.max_sm = float(f[1])
+                self.samples.append((float(f[0]), bits, float(f[2])))
+            except Exception:
+                time.sleep(0.05)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=6)
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = set()
+        for _, bits, _ in self.samples:
+            for bit, nm in names.items():
+                if bits & bit:
+                    reasons.add(nm)
+        sm = [x[0] for x in self.samples]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(getattr(self, "max_sm", max(sm))),
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(x[2] for x in self.samples),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ CPU arms
