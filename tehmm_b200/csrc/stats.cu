@@ -81,6 +81,89 @@ emission_stats_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tota
     for (int64_t e = threadIdx.x; e < cells; e += blockDim.x) dst[e] = hist[e];
 }
 
+// fp32 production path (N <= 32, lattice stride 32, K <= 32, no segment ratios):
+// every warp takes batches of 16 time steps, lane = state, and adds its posterior
+// row into a CTA-wide histogram with NATIVE shared-memory atomics.  Floating-point
+// atomics on shared memory are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN),
+// 64-bit integer ones too; 32-bit integer adds are native (ATOMS.ADD).  So a
+// posterior p in [0,1] is added as the 40-bit fixed-point number round(p * 2^40),
+// split into a 22-bit low limb and an 18-bit high limb, each into its own uint32
+// bin; the bins are flushed into the CTA's float64 partial every SA_TILE = 512
+// steps (512 * 2^22 < 2^32).  Quantisation 2^-41 per addition, and -- integer
+// addition being associative -- the result is bit-reproducible whatever the order
+// in which warps get to the bins.  All 32 warps are busy (the one-warp-per-track
+// kernel above keeps K of them busy and chains read-modify-writes).
+#define SA_WARPS 32
+#define SA_ROWS 16
+#define SA_TILE (SA_WARPS * SA_ROWS)
+
+template <typename OBS>
+__global__ void __launch_bounds__(SA_WARPS * 32, 1)
+emission_stats_atomic_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
+                             const float *__restrict__ post, double *__restrict__ part,
+                             double *__restrict__ dense_stats, int64_t steps_per_cta, int statS)
+{
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    const int N = m.N, K = m.K, KP = (K + 3) & ~3;
+    unsigned *hist = reinterpret_cast<unsigned *>(st_smem);                    // [tab_rows][2 limbs][32]
+    int32_t *koff = reinterpret_cast<int32_t *>(hist + (size_t)m.tab_rows * 64);  // [K] first row, [K] widths
+    int32_t *offs_all = koff + 2 * K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t *offs = offs_all + (size_t)warp * SA_ROWS * KP;
+    const int64_t cells = (int64_t)m.tab_rows * N;
+    for (int e = threadIdx.x; e < m.tab_rows * 64; e += blockDim.x) hist[e] = 0u;
+    for (int e = threadIdx.x; e < K; e += blockDim.x) { koff[e] = m.tab_off[e]; koff[K + e] = m.track_nsym[e]; }
+    double *dst = part + (int64_t)blockIdx.x * cells;
+    for (int64_t e = threadIdx.x; e < cells; e += blockDim.x) dst[e] = 0.0;
+    __syncthreads();
+    const uint32_t hist_lane = (uint32_t)__cvta_generic_to_shared(hist) + (uint32_t)lane * 4u;
+
+    const int64_t ta = (int64_t)blockIdx.x * steps_per_cta;
+    const int64_t tz = min(total, ta + steps_per_cta);
+    for (int64_t tile = ta; tile < tz; tile += SA_TILE) {
+        const int64_t tb = tile + (int64_t)warp * SA_ROWS;
+        const int rows = (int)max((int64_t)0, min((int64_t)SA_ROWS, tz - tb));
+        // the batch's posterior rows (coalesced, all in flight) and shared-memory offsets of its symbols
+        float p[SA_ROWS];
+#pragma unroll
+        for (int r = 0; r < SA_ROWS; ++r) p[r] = r < rows ? post[(tb + r) * 32 + lane] : 0.f;
+        for (int e = lane; e < rows * K; e += 32) {
+            const int r = e / K, k = e - r * K;
+            const int sym = (int)obs[tb * K + e];
+            offs[r * KP + k] = sym < koff[K + k] ? (koff[k] + sym) * 256 : -(sym + 1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < SA_ROWS; ++r) {
+            if (r < rows) {
+                // a posterior is in [0,1] up to rounding; clamp so the high limb stays below 2^19
+                const unsigned long long q = __float2ull_rn(fminf(p[r], 2.f) * 1099511627776.f);   // * 2^40
+                const unsigned lo = (unsigned)q & 0x3fffffu, hi = (unsigned)(q >> 22);
+                for (int k = 0; k < K; ++k) {
+                    const int o = offs[r * KP + k];
+                    if (o >= 0) {
+                        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hist_lane + (uint32_t)o), "r"(lo) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hist_lane + (uint32_t)o + 128u), "r"(hi) : "memory");
+                    } else if (lane < N) {  // symbol outside the compact table: dense layout, rare
+                        atomicAdd(&dense_stats[((int64_t)k * N + lane) * statS + (-o - 1)], (double)p[r]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // flush the tile's fixed-point histogram into the CTA's float64 partial (warp per row)
+        for (int row = warp; row < m.tab_rows; row += SA_WARPS) {
+            const unsigned lo = hist[row * 64 + lane], hi = hist[row * 64 + 32 + lane];
+            if ((lo | hi) && lane < N) {
+                dst[(int64_t)row * N + lane] += ((double)hi * 4194304.0 + (double)lo) * 9.094947017729282e-13;    // 2^22, 2^-40
+                hist[row * 64 + lane] = 0u;
+                hist[row * 64 + 32 + lane] = 0u;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Slow path when the compact histogram does not fit shared memory: global atomics.
 template <typename T, typename OBS>
 __global__ void emission_stats_global_kernel(TehmmModelDev m, const OBS *__restrict__ obs,
@@ -128,6 +211,20 @@ static cudaError_t launch_stats(cudaStream_t st, const TehmmModelDev &m, const T
     if (nparts <= 0) {
         emission_stats_global_kernel<T, OBS><<<148 * 8, 256, 0, st>>>(m, (const OBS *)b.obs, b.total, post, ratios, obs_stats, statS);
         return cudaGetLastError();
+    }
+    if (sizeof(T) == 4 && m.LD == 32 && m.K <= 32 && !ratios) {
+        const int KP = (m.K + 3) & ~3;
+        const size_t sm2 = (size_t)m.tab_rows * 256 + (size_t)2 * m.K * 4 + (size_t)SA_WARPS * SA_ROWS * KP * 4 + 16;
+        if (sm2 <= 220 * 1024) {
+            const int64_t per = ((b.total + nparts - 1) / nparts + SA_TILE - 1) / SA_TILE * SA_TILE;
+            auto k2 = emission_stats_atomic_kernel<OBS>;
+            cudaError_t e2 = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+            if (e2 != cudaSuccess) return e2;
+            k2<<<nparts, SA_WARPS * 32, sm2, st>>>(m, (const OBS *)b.obs, b.total, (const float *)post, part, obs_stats, per, statS);
+            const int64_t cells = (int64_t)m.tab_rows * m.N;
+            emission_stats_reduce_kernel<<<(int)((cells + 127) / 128), 128, 0, st>>>(m, part, nparts, obs_stats, statS);
+            return cudaGetLastError();
+        }
     }
     auto kern = emission_stats_kernel<T, OBS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

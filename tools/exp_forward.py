@@ -29,3 +29,13 @@ print("backward POST        %.3f ms" % timeit(lambda: eng.run_backward(prec, tdt
 print("emission both        %.3f ms" % timeit(lambda: eng.run_emission(prec, tdt, None, True, True)))
 print("emission lin only    %.3f ms" % timeit(lambda: eng.run_emission(prec, tdt, None, False, True)))
 print("viterbi              %.3f ms" % timeit(lambda: eng.run_viterbi(prec, elog, None, None, want64=False)))
+import torch
+N, K, S = eng.N, eng.K, eng.S
+packed = torch.zeros(2 + N + N * N + K * N * S, dtype=torch.float64, device=eng.device)
+def bw_trans():
+    return eng.run_backward(prec, tdt, _lib.BWD_TRANS | _lib.BWD_POSTERIORS, blin, alpha, None, start_trans=packed[2:2 + N + N * N])
+print("backward TRANS|POST  %.3f ms" % timeit(bw_trans))
+print("backward TRANS       %.3f ms" % timeit(lambda: eng.run_backward(prec, tdt, _lib.BWD_TRANS, blin, alpha, None, start_trans=packed[2:2 + N + N * N])))
+post, _, _ = bw_trans()
+print("emission stats       %.3f ms" % timeit(lambda: eng.run_emission_stats(prec, post, None, packed[2 + N + N * N:], S)))
+print("estep total          %.3f ms" % timeit(lambda: eng.estep(device_result=True)))
