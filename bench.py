@@ -283,6 +283,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launches
+    ctx.set_option("timing", 1)          # per-kernel CUDA events, read after the timed region
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):
@@ -310,22 +311,33 @@ def run_ours(args):
               "repairs": {k: ctx.stat("repaired_chunks_" + k) for k in ("forward", "backward", "viterbi")},
               "chunks": ctx.stat("chunks")}
 
-    # ---- roofline of the dominant kernel (SURVEY.md section 8d per-step bytes)
+    # ---- roofline of the dominant KERNEL: its own duration from CUDA events the library records
+    # around it on the launching stream during the timed region (mean over the K steps), against
+    # its algorithmic bytes (SURVEY.md section 8d per-step figures split per kernel)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     K = m["K"]
-    alg_bytes = {"emission": K, "forward": K + 4 * N_STATES, "backward_map": K + 4 * N_STATES + 1,
-                 "viterbi_dp_traceback": K + N_STATES + 2}
-    dom = int(np.argmax(stage_ms))
-    dom_ms = stage_ms[dom] / args.steps
-    achieved = alg_bytes[stage_names[dom]] * T / (dom_ms * 1e-3) / 1e9
+    kern_us = {k: ctx.stat("us_" + k) for k in ("emission", "forward", "backward", "viterbi_dp", "traceback", "rescore")}
+    ctx.set_option("timing", 0)
+    # algorithmic bytes per time step of each kernel: symbols in, compulsory fp32 lattice spill, states out
+    alg_bytes = {"emission": K, "forward": K + 4 * N_STATES, "backward": K + 4 * N_STATES + 1,
+                 "viterbi_dp": K + N_STATES, "traceback": 2, "rescore": 0}
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this command
+    # (profiles/r01_ncu_full_v2.txt: dram__bytes_read.sum + dram__bytes_write.sum), 10 M x 30 x 10 only
+    ncu_traffic = {"emission": 2.68e9, "forward": 2.79e9, "backward": 2.73e9, "viterbi_dp": 2.55e9, "traceback": 1.45e9}
+    dom = max(kern_us, key=lambda k: kern_us[k])
+    dom_s = kern_us[dom] * 1e-6
+    achieved = alg_bytes[dom] * T / dom_s / 1e9
     sweep_achieved = (3 * K + 9 * N_STATES + 3) * T / (total_ms / args.steps * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": stage_names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_step": alg_bytes[stage_names[dom]],
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": ncu_traffic.get(dom) if (T == T_DEFAULT and args.precision == "f32") else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes[dom],
+                "kernel_us": kern_us,
+                "kernel_frac": {k: (alg_bytes[k] * T / (v * 1e-6) / 1e9 / peak if v > 0 else None) for k, v in kern_us.items()},
                 "sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,
                           "algorithmic_bytes_per_step": 3 * K + 9 * N_STATES + 3},
                 "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(stage_names, stage_ms)}}

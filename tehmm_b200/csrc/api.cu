@@ -64,6 +64,11 @@ struct DevBuf {   // RAII device allocation for the strict host-pointer entry po
     template <typename T> T *as() { return (T *)p; }
 };
 
+#define TEHMM_TRING 32
+enum { TK_EMISSION, TK_FORWARD, TK_BACKWARD, TK_VITERBI_DP, TK_TRACEBACK, TK_RESCORE, TK_STATS, TEHMM_NTIMED };
+static const char *const tk_names[TEHMM_NTIMED] = {"us_emission", "us_forward", "us_backward", "us_viterbi_dp",
+                                                    "us_traceback", "us_rescore", "us_emission_stats"};
+
 struct tehmm_ctx {
     int device = 0;
     int sms = 148;
@@ -72,6 +77,11 @@ struct tehmm_ctx {
     int64_t launches = 0;
     int64_t opt_chunk_tiles = 0, opt_warmup = 0, opt_max_repair = 0;
     int64_t opt_tile = 1, opt_fine_len = 0;   // tensor-core tile kernels on / fine chunk length (0 = auto)
+    // option "timing": CUDA events around the first (speculative) launch of each main kernel, on the
+    // launching stream; read back in microseconds with tehmm_ctx_get_stat("us_<kernel>")
+    int64_t opt_timing = 0;
+    cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
+    int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
     int64_t stat_tile_passes = 0;
     int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0, stat_bad_tb = 0, stat_repair_tb = 0;
@@ -129,6 +139,10 @@ int tehmm_ctx_destroy(tehmm_ctx *c)
     if (c->batch_blob) cudaFree(c->batch_blob);
     if (c->d_seq_flag) cudaFree(c->d_seq_flag);
     if (c->h_nbad) cudaFreeHost(c->h_nbad);
+    for (int i = 0; i < TEHMM_NTIMED; ++i)
+        for (int r = 0; r < TEHMM_TRING; ++r)
+            for (int j = 0; j < 2; ++j)
+                if (c->ev[i][r][j]) cudaEventDestroy(c->ev[i][r][j]);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return TEHMM_OK;
@@ -162,6 +176,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "warmup")) c->opt_warmup = v;
     else if (!strcmp(name, "max_repair")) c->opt_max_repair = v;
     else if (!strcmp(name, "tile")) c->opt_tile = v;
+    else if (!strcmp(name, "timing")) { c->opt_timing = v; for (int i = 0; i < TEHMM_NTIMED; ++i) c->ev_n[i] = 0; }
     else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
@@ -183,6 +198,19 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
     if (!strcmp(name, "fine_chunks")) return c->has_batch ? c->bf.nchunks : 0;
     if (!strcmp(name, "tile_passes")) return c->stat_tile_passes;
+    for (int i = 0; i < TEHMM_NTIMED; ++i)
+        if (!strcmp(name, tk_names[i])) {
+            // average over the launches recorded since "timing" was set (at most the last TEHMM_TRING)
+            const int n = std::min(c->ev_n[i], TEHMM_TRING);
+            if (n <= 0) return -1;
+            double tot = 0.0;
+            for (int r = 0; r < n; ++r) {
+                float ms = 0.f;
+                if (cudaEventSynchronize(c->ev[i][r][1]) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev[i][r][0], c->ev[i][r][1]) != cudaSuccess) return -1;
+                tot += ms;
+            }
+            return (int64_t)(tot / n * 1000.0 + 0.5);
+        }
     if (!strcmp(name, "warmup")) return c->has_batch ? c->b.warmup : 0;
     return -1;
 }
@@ -641,6 +669,21 @@ static int scan_grid(const tehmm_ctx *c)
     return (int)std::max<int64_t>(1, std::min(need, cap));
 }
 
+// timing brackets (no-ops unless the "timing" option is set)
+static void tk_begin(tehmm_ctx *c, int which)
+{
+    if (!c->opt_timing) return;
+    const int r = c->ev_n[which] % TEHMM_TRING;
+    if (!c->ev[which][r][0]) { cudaEventCreate(&c->ev[which][r][0]); cudaEventCreate(&c->ev[which][r][1]); }
+    cudaEventRecord(c->ev[which][r][0], c->stream);
+}
+static void tk_end(tehmm_ctx *c, int which)
+{
+    if (!c->opt_timing) return;
+    cudaEventRecord(c->ev[which][c->ev_n[which] % TEHMM_TRING][1], c->stream);
+    c->ev_n[which] += 1;
+}
+
 static int read_nbad(tehmm_ctx *c, const int *d_nbad, int *out)
 {
     CU(cudaMemcpyAsync(c->h_nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -655,7 +698,9 @@ int tehmm_run_emission(tehmm_ctx *c, int prec, const double *d_ratios, void *d_e
     RUN_PROLOGUE();
     if (!d_rowmax || (!d_elog && !d_blin)) return fail(TEHMM_EINVAL, "need d_rowmax and at least one of d_elog / d_blin");
     cudaError_t e;
+    tk_begin(c, TK_EMISSION);
     int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, d_elog, d_blin, d_rowmax, nullptr, c->d_seq_flag, c->sms, &e);
+    tk_end(c, TK_EMISSION);
     if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
     c->launches += n;
     return TEHMM_OK;
@@ -719,7 +764,9 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
         }
         return tehmm_launch_forward(st, c->m, PB, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, mode, grid);
     };
+    tk_begin(c, TK_FORWARD);
     CU(launch(0));
+    tk_end(c, TK_FORWARD);
     c->launches += 1;
     const double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
@@ -765,7 +812,9 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
         }
         return tehmm_launch_backward(st, c->m, PB, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, mode, grid);
     };
+    tk_begin(c, TK_BACKWARD);
     CU(launch(0));
+    tk_end(c, TK_BACKWARD);
     c->launches += 1;
     const double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
@@ -794,7 +843,9 @@ int tehmm_run_emission_stats(tehmm_ctx *c, int prec, const void *d_post, const d
     if (stats_S <= 0) return fail(TEHMM_EINVAL, "stats_S must be positive");
     const Scratch s = carve(c, prec);
     double *part = (double *)((char *)d_scratch + s.hist);
+    tk_begin(c, TK_STATS);
     CU(tehmm_launch_emission_stats(st, c->m, c->b, prec, d_post, d_ratios, d_obs_stats, part, s.nparts, stats_S));
+    tk_end(c, TK_STATS);
     c->launches += s.nparts > 0 ? 2 * ((c->m.K + 31) / 32) : 1;
     return TEHMM_OK;
 }
@@ -819,7 +870,9 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     const TehmmBatchDev &PB = c->b;
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
     // ---- DP: delta lattice, chunk starts speculated / verified / repaired
+    tk_begin(c, TK_VITERBI_DP);
     CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid));
+    tk_end(c, TK_VITERBI_DP);
     c->launches += 1;
     const double tol = tolerance(prec, true);
     for (int64_t pass = 0;; ++pass) {
@@ -836,7 +889,9 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     }
     // ---- traceback: chunk end states speculated / verified / repaired
     CU(cudaMemsetAsync(bad, 0, sizeof(int) * (size_t)TBP.nchunks, st));
+    tk_begin(c, TK_TRACEBACK);
     CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 0, tb_grid));
+    tk_end(c, TK_TRACEBACK);
     c->launches += 1;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_tb_verify(st, TBP, spec_end, pred, forced, bad, nbad));
@@ -850,7 +905,9 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, tb_grid));
         c->launches += 1;
     }
+    tk_begin(c, TK_RESCORE);
     CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));   // latency bound too: fine partition
+    tk_end(c, TK_RESCORE);
     c->launches += 2;
     return TEHMM_OK;
 }
