@@ -243,6 +243,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     T = args.T
+    # one process per GPU shares the host's cores: the host side of the e2e path (widening the
+    # state paths to int64) must not oversubscribe them
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
 
     m = synth.make_model(N=N_STATES, seed=0)
     obs, _ = synth.sample_obs(m, T, seed=1 + rank)

@@ -440,7 +440,7 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
 // a 4-way local minimum of bit patterns (every candidate is <= 0, so the largest
 // value has the smallest unsigned pattern), three xor-shuffles and one ballot
 // (ties: lowest state, as _hmm.pyx:232-247).  ~11 issue slots per chunk step.
-#define TB4_PF 4     // delta rows in flight per chunk
+#define TB4_PF 8     // delta rows in flight per chunk
 
 __device__ __forceinline__ int tb4_argmax(float c0, float c1, float c2, float c3, int u, unsigned segshift, int lane0)
 {
