@@ -208,6 +208,29 @@ int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
                       void *d_lattice, uint8_t *d_states, int64_t *d_states64,
                       double *d_logprob, void *d_scratch);
 
+/* ------------------------------------------------------------- host buffers
+ * The whole call MultitrackHmm.decode makes (/root/reference/basehmm.py:361-396
+ * -> hmm.py:668-676 -> _hmm.pyx:201-259 for Viterbi; basehmm.py:332-359 for
+ * MAP), with HOST buffers on both sides: h_obs (total,K) symbols (pageable or
+ * pinned), h_offsets nseq+1 row offsets, h_states int64[total] out (the dtype
+ * the reference returns, _hmm.pyx:210), h_logprob float64[nseq] out (Viterbi:
+ * path log-probability; MAP: forward log-likelihood), h_score float64[nseq] out
+ * (MAP: sum of the posterior maxima, basehmm.py:357; may be NULL for Viterbi).
+ * No segment ratios.  The library owns everything in between: a grow-only
+ * device arena, pinned staging rings and a thread pool (TEHMM_HOST_THREADS,
+ * default min(16, cores)) that stages pageable input and widens the uint8
+ * states that crossed PCIe.  Blocks until the outputs are complete.          */
+#define TEHMM_DECODE_VITERBI 0
+#define TEHMM_DECODE_MAP 1
+int tehmm_decode_host(tehmm_ctx *ctx, const void *h_obs, int obs_bytes, int64_t nseq,
+                      const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
+                      double *h_logprob, double *h_score);
+/* bytes the last tehmm_decode_host moved over PCIe: which = 0 host->device, 1 device->host */
+int64_t tehmm_decode_host_bytes(tehmm_ctx *ctx, int which);
+/* device index / model shape of a context */
+int tehmm_ctx_device(tehmm_ctx *ctx);
+int tehmm_model_dims(tehmm_ctx *ctx, int *N, int *K, int *S);
+
 /* widen / convert on the device before a D2H copy */
 int tehmm_widen_states(tehmm_ctx *ctx, const uint8_t *d_in, int64_t *d_out, int64_t n);
 int tehmm_convert_lattice(tehmm_ctx *ctx, int prec, const void *d_in, double *d_out, int64_t n);

@@ -17,6 +17,7 @@ TEHMM_OK, TEHMM_EINVAL, TEHMM_ECUDA, TEHMM_ENOMEM, TEHMM_ESTATE, TEHMM_ELIMIT = 
 F32, F64 = 0, 1
 BWD_POSTERIORS, BWD_MAP, BWD_TRANS, BWD_RENORM_EPS = 1, 2, 4, 8
 MAX_STATES = 64
+DECODE_VITERBI, DECODE_MAP = 0, 1
 
 _c_void = ctypes.c_void_p
 _c_i64 = ctypes.c_int64
@@ -57,6 +58,10 @@ SIGNATURES = {
     "tehmm_run_emission_stats": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_int, _c_void]),
     "tehmm_viterbi_workspace_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_decode_host": (_c_int, [_c_void, _c_void, _c_int, _c_i64, _c_void, _c_int, _c_int, _c_void, _c_void, _c_void]),
+    "tehmm_decode_host_bytes": (_c_i64, [_c_void, _c_int]),
+    "tehmm_ctx_device": (_c_int, [_c_void]),
+    "tehmm_model_dims": (_c_int, [_c_void, _c_void, _c_void, _c_void]),
     "tehmm_widen_states": (_c_int, [_c_void, _c_void, _c_void, _c_i64]),
     "tehmm_convert_lattice": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_i64]),
 }

@@ -49,6 +49,8 @@ static int fail(int code, const char *fmt, ...)
     g_err = buf;
     return code;
 }
+void tehmm_set_error(int code, const char *msg) { (void)code; g_err = msg ? msg : ""; }   // host.cu
+void tehmm_hostpipe_release(tehmm_ctx *c);                                                  // host.cu
 #define CU(x)                                                                                 \
     do {                                                                                      \
         cudaError_t e__ = (x);                                                                \
@@ -90,12 +92,16 @@ struct tehmm_ctx {
     bool has_model = false;
     TehmmModelDev m{};
     void *model_blob = nullptr;
+    size_t model_blob_bytes = 0;
+    std::vector<unsigned char> model_key;     // raw inputs of the last tehmm_set_model
     // batch
     bool has_batch = false;
     TehmmBatchDev b{};            // coarse partition: one chunk per warp (forward.cu, backward.cu, viterbi.cu)
     TehmmBatchDev bf{};           // fine partition: sixteen chunks per warp (tile.cu)
     void *batch_blob = nullptr;
+    size_t batch_blob_bytes = 0;      // capacity (grow-only: decode calls come back with similar batches)
     int *d_seq_flag = nullptr;
+    int64_t seq_flag_n = 0;
     int64_t max_tiles_per_chunk = 1;
 };
 
@@ -135,6 +141,7 @@ int tehmm_ctx_destroy(tehmm_ctx *c)
     if (!c) return TEHMM_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    tehmm_hostpipe_release(c);
     if (c->model_blob) cudaFree(c->model_blob);
     if (c->batch_blob) cudaFree(c->batch_blob);
     if (c->d_seq_flag) cudaFree(c->d_seq_flag);
@@ -393,6 +400,21 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     if (!c || !log_start || !log_trans || !table) return fail(TEHMM_EINVAL, "NULL argument");
     if (N <= 0 || K <= 0 || S <= 0) return fail(TEHMM_EINVAL, "bad shape N=%d K=%d S=%d", N, K, S);
     if (N > TEHMM_MAX_STATES) return fail(TEHMM_ELIMIT, "batched path supports N <= %d (got %d)", TEHMM_MAX_STATES, N);
+    {   // decode()/score() hand the same model over on every call: skip the rebuild when nothing changed
+        const size_t nb = (size_t)N * 8 + (size_t)N * N * 8 + (size_t)K * N * S * 8;
+        std::vector<unsigned char> key(32 + nb + (size_t)K * 4, 0);
+        int32_t hdr[4] = {N, K, S, track_nsym ? 1 : 0};
+        memcpy(&key[0], hdr, 16);
+        memcpy(&key[16], &normalize, 8);
+        unsigned char *q = &key[32];
+        memcpy(q, log_start, (size_t)N * 8); q += (size_t)N * 8;
+        memcpy(q, log_trans, (size_t)N * N * 8); q += (size_t)N * N * 8;
+        memcpy(q, table, (size_t)K * N * S * 8); q += (size_t)K * N * S * 8;
+        if (track_nsym) memcpy(q, track_nsym, (size_t)K * 4);
+        if (c->has_model && key == c->model_key) return TEHMM_OK;
+        c->model_key.swap(key);
+        c->has_model = false;
+    }
     CU(cudaSetDevice(c->device));
     const int NS = N <= 32 ? 1 : 2, NP = 32 * NS;
     std::vector<int32_t> nsym(K), off(K);
@@ -468,7 +490,7 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
                 for (int j = 0; j < N; ++j) { acc[j] *= normalize; mx = std::max(mx, acc[j]); }
                 if (!(mx > -INFINITY)) mx = 0.0;
                 gc[base + row] = mx;
-                for (int j = 0; j < 32; ++j) gtab[(size_t)(base + row) * 32 + j] = j < N ? (float)(acc[j] - mx) : 0.f;
+                for (int j = 0; j < 32; ++j) gtab[(size_t)(base + row) * 32 + j] = j < N ? (float)(acc[j] - mx) : -INFINITY;   // padding never wins a maximum
             }
             base += gr.rows;
         }
@@ -497,8 +519,11 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
         }
     }
     CU(cudaStreamSynchronize(c->stream));
-    if (c->model_blob) { cudaFree(c->model_blob); c->model_blob = nullptr; }
-    CU(cudaMalloc(&c->model_blob, total));
+    if (total > c->model_blob_bytes) {
+        if (c->model_blob) { cudaFree(c->model_blob); c->model_blob = nullptr; c->model_blob_bytes = 0; }
+        CU(cudaMalloc(&c->model_blob, total));
+        c->model_blob_bytes = total;
+    }
     CU(cudaMemcpy(c->model_blob, h.data(), total, cudaMemcpyHostToDevice));
     unsigned char *d = (unsigned char *)c->model_blob;
     TehmmModelDev &m = c->m;
@@ -581,11 +606,17 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
     memcpy(&h[o_fsc], seq_fchunk0.data(), (size_t)(nseq + 1) * 8);
     memcpy(&h[o_fch], fchunks.data(), (size_t)nfchunks * sizeof(TehmmChunk));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->batch_blob) { cudaFree(c->batch_blob); c->batch_blob = nullptr; }
-    if (c->d_seq_flag) { cudaFree(c->d_seq_flag); c->d_seq_flag = nullptr; }
-    CU(cudaMalloc(&c->batch_blob, bytes));
+    if (bytes > c->batch_blob_bytes) {
+        if (c->batch_blob) { cudaFree(c->batch_blob); c->batch_blob = nullptr; c->batch_blob_bytes = 0; }
+        CU(cudaMalloc(&c->batch_blob, bytes + bytes / 4));
+        c->batch_blob_bytes = bytes + bytes / 4;
+    }
     CU(cudaMemcpy(c->batch_blob, h.data(), bytes, cudaMemcpyHostToDevice));
-    CU(cudaMalloc((void **)&c->d_seq_flag, sizeof(int) * (size_t)nseq));
+    if (nseq > c->seq_flag_n) {
+        if (c->d_seq_flag) { cudaFree(c->d_seq_flag); c->d_seq_flag = nullptr; c->seq_flag_n = 0; }
+        CU(cudaMalloc((void **)&c->d_seq_flag, sizeof(int) * (size_t)(nseq + nseq / 4 + 1)));
+        c->seq_flag_n = nseq + nseq / 4 + 1;
+    }
     unsigned char *d = (unsigned char *)c->batch_blob;
     TehmmBatchDev &b = c->b;
     b.obs = d_obs; b.obs_bytes = obs_bytes; b.nseq = nseq; b.total = total;
@@ -603,6 +634,16 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
 }
 
 int64_t tehmm_batch_total(tehmm_ctx *c) { return c && c->has_batch ? c->b.total : 0; }
+int tehmm_ctx_device(tehmm_ctx *c) { return c ? c->device : -1; }
+int tehmm_model_dims(tehmm_ctx *c, int *N, int *K, int *S)
+{
+    if (!c) return fail(TEHMM_EINVAL, "ctx is NULL");
+    if (!c->has_model) return fail(TEHMM_ESTATE, "tehmm_set_model has not been called");
+    if (N) *N = c->m.N;
+    if (K) *K = c->m.K;
+    if (S) *S = c->m.S;
+    return TEHMM_OK;
+}
 int tehmm_lattice_stride(tehmm_ctx *c) { return c && c->has_model ? c->m.LD : 0; }
 int64_t tehmm_batch_chunks(tehmm_ctx *c) { return c && c->has_batch ? c->b.nchunks : 0; }
 int64_t tehmm_viterbi_workspace_bytes(tehmm_ctx *c, int prec)

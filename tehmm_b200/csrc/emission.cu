@@ -385,6 +385,201 @@ static cudaError_t launch_emg(cudaStream_t st, const TehmmModelDev &m, const Teh
 #undef EMG_GO
 }
 
+// ---------------------------------------------------------------------------
+// Four time steps per warp pass (fp32, LD == 32, G <= 8): the production kernel.
+// emission_merged_kernel above spends one warp instruction per (row, group)
+// look-up and per row reduction: 78 instructions per row, issue bound at 0.85 ms
+// for 10 M rows against 0.42 ms of HBM time.  Here a row belongs to EIGHT lanes,
+// each owning four consecutive states: a look-up is one LDS.128 serving four
+// rows (each quarter-warp reads one 128-byte table row: 4 wavefronts, no
+// conflicts), the row maximum is a 4-way local max + three xor-shuffles, and
+// the outputs leave as STG.128 (four rows = 512 contiguous bytes per store).
+// ~20 instructions per row; the sum over groups keeps the group order, so the
+// values are bit-identical to emission_merged_kernel's.
+// Table padding (states N..31) is -inf, so padding never wins the maximum.
+#define EM4_WARPS 32
+#define EM4_ROWS 32
+
+static size_t em4_smem_bytes(const TehmmModelDev &m)
+{
+    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
+    return head + (size_t)EM4_WARPS * EM4_ROWS * 8 * 4;
+}
+
+template <typename OBS, int GT, bool RATIO>
+__global__ void __launch_bounds__(EM4_WARPS * 32, 1)
+emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
+                        const double *__restrict__ ratios, float *__restrict__ elog,
+                        float *__restrict__ blin, double *__restrict__ rowmax,
+                        int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq)
+{
+    extern __shared__ __align__(16) unsigned char em_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = m.K, N = m.N;
+    // layout: gtab | gc | gdesc | nsym | per warp offs[32][8]
+    float *tab_s = reinterpret_cast<float *>(em_smem);
+    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * 32);
+    int32_t *gd_s = reinterpret_cast<int32_t *>(gc_s + m.grows);
+    int32_t *nsym_s = gd_s + TEHMM_GMAX * TEHMM_GDESC;
+    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
+    int32_t *offs = reinterpret_cast<int32_t *>(em_smem + head) + (size_t)warp * EM4_ROWS * 8;
+
+    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * 32; e += blockDim.x) tab_s[e] = m.gtab[e];
+    for (int e = threadIdx.x; e < m.grows; e += blockDim.x) gc_s[e] = m.gc[e];
+    for (int e = threadIdx.x; e < GT * TEHMM_GDESC; e += blockDim.x) gd_s[e] = m.gdesc[e];
+    for (int e = threadIdx.x; e < K; e += blockDim.x) nsym_s[e] = m.track_nsym[e];
+    __syncthreads();
+
+    const int q = lane >> 3, c = lane & 7;
+    const uint32_t lane_tab = (uint32_t)__cvta_generic_to_shared(tab_s) + (uint32_t)c * 16u;
+    const uint32_t offs_a = (uint32_t)__cvta_generic_to_shared(offs);
+    // pm[i]: -inf for a real state (max(d, -inf) = d), 0 for a padding column (max(-inf, 0) = 0)
+    float pm[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pm[i] = (4 * c + i < N) ? -INFINITY : 0.f;
+
+    const int64_t nblocks = (total + EM4_ROWS - 1) / EM4_ROWS;
+    for (int64_t blk = (int64_t)blockIdx.x * EM4_WARPS + warp; blk < nblocks;
+         blk += (int64_t)gridDim.x * EM4_WARPS) {
+        const int64_t tb = blk * EM4_ROWS;
+        const int rows = (int)min((int64_t)EM4_ROWS, total - tb);
+        __syncwarp();
+        // ---- stage (lane = row): byte offset of the table row of every group, and the
+        //      float64 part common to all states
+        bool bad = false;
+        double csum = 0.0;
+        {
+            const OBS *orow = obs + (tb + (lane < rows ? lane : 0)) * K;
+#pragma unroll
+            for (int gq = 0; gq < GT; ++gq) {
+                const int32_t *d = gd_s + gq * TEHMM_GDESC;
+                int idx = d[1];
+                const int nt = d[0];
+                for (int i = 0; i < nt; ++i) {
+                    const int k = d[2 + i];
+                    const int sym = (int)orow[k];
+                    bad |= (unsigned)sym >= (unsigned)nsym_s[k];
+                    idx += sym * d[6 + i];
+                }
+                if (bad) idx = 0;
+                offs[lane * 8 + gq] = idx * 128;
+                csum += gc_s[idx];
+            }
+        }
+        const bool any_slow = __any_sync(TEHMM_FULL, bad && lane < rows);
+        __syncwarp();
+        float mf_keep = 0.f;                     // lane r keeps the state maximum of row r
+        if (!any_slow) {
+#pragma unroll 2
+            for (int p = 0; p < EM4_ROWS / 4; ++p) {
+                const int r = 4 * p + q;
+                int o[8];
+                asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(offs_a + r * 32));
+                if (GT > 4)
+                    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(offs_a + r * 32 + 16));
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int gq = 0; gq < GT; ++gq) {
+                    float x0, x1, x2, x3;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(lane_tab + (uint32_t)o[gq]));
+                    v[0] += x0; v[1] += x1; v[2] += x2; v[3] += x3;
+                }
+                float mx = fmax3(v[0], v[1], fmaxf(v[2], v[3]));
+                mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 2));
+                mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 4));
+                const float rf = RATIO ? (float)ratios[min(tb + r, total - 1)] : 1.f;
+                float d[4], bl[4];
+                if (__builtin_expect(__any_sync(TEHMM_FULL, !(mx > -INFINITY)), 0)) {
+                    // a row no state can emit (in float): zeros / ones, as emission_merged_kernel
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        d[i] = mx > -INFINITY ? v[i] - mx : 0.f;
+                        if (RATIO) d[i] *= rf;
+                        bl[i] = __expf(d[i]);
+                        if (pm[i] == 0.f) { d[i] = 0.f; bl[i] = 0.f; }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        d[i] = v[i] - mx;
+                        if (RATIO) d[i] *= rf;
+                        bl[i] = __expf(d[i]);            // padding: exp(-inf) = 0
+                        d[i] = fmaxf(d[i], pm[i]);       // padding: 0
+                    }
+                }
+                if (r < rows) {
+                    const int64_t o4 = (tb + r) * 32 + 4 * c;
+                    if (elog) *reinterpret_cast<float4 *>(elog + o4) = make_float4(d[0], d[1], d[2], d[3]);
+                    if (blin) *reinterpret_cast<float4 *>(blin + o4) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+                }
+                const float mm = __shfl_sync(TEHMM_FULL, mx, (lane & 3) * 8);
+                if ((lane >> 2) == p) mf_keep = mm;
+            }
+        } else {
+            // a symbol outside its track's table: index the dense float64 table exactly as the
+            // reference does (rare); lane = state
+            for (int r = 0; r < rows; ++r) {
+                double v = 0.0;
+                if (lane < N)
+                    for (int k = 0; k < K; ++k) v += m.table[((int64_t)k * N + lane) * m.S + (int64_t)obs[(tb + r) * K + k]];
+                v *= m.normalize;
+                const double M = warp_max(lane < N ? v : -INFINITY);
+                float d = M > -INFINITY ? (float)(v - M) : 0.f;
+                if (RATIO) d *= (float)ratios[tb + r];
+                float bl = __expf(d);
+                if (lane >= N) { d = 0.f; bl = 0.f; }
+                if (elog) elog[(tb + r) * 32 + lane] = d;
+                if (blin) blin[(tb + r) * 32 + lane] = bl;
+                if (lane == r) { mf_keep = 0.f; csum = M; }
+            }
+        }
+        // ---- row maxima of the batch, one lane per row
+        if (lane < rows) {
+            double M = (double)mf_keep + csum;
+            if (RATIO) M *= ratios[tb + lane];
+            rowmax[tb + lane] = M;
+            if (!(M > TEHMM_MINDBL) && seq_flag) emg_flag_row(tb + lane, seq_off, nseq, seq_flag);   // _emission.pyx:73-80
+        }
+    }
+}
+
+template <typename OBS, int GT, bool RATIO>
+static cudaError_t launch_em4_3(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                const double *ratios, float *elog, float *blin, double *rowmax,
+                                int *seq_flag, int sms)
+{
+    const size_t smem = em4_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(emission_merged4_kernel<OBS, GT, RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t need = ((b.total + EM4_ROWS - 1) / EM4_ROWS + EM4_WARPS - 1) / EM4_WARPS;
+    if (need < 1) need = 1;
+    const int grid = (int)(need < sms ? need : sms);
+    emission_merged4_kernel<OBS, GT, RATIO><<<grid, EM4_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
+                                                                                rowmax, seq_flag, b.seq_off, b.nseq);
+    return cudaGetLastError();
+}
+
+template <typename OBS>
+static cudaError_t launch_em4(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                              const double *ratios, float *elog, float *blin, double *rowmax,
+                              int *seq_flag, int sms)
+{
+#define EM4_GO(GT) (ratios ? launch_em4_3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms) \
+                           : launch_em4_3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms))
+    switch (m.G) {
+    case 1: return EM4_GO(1);
+    case 2: return EM4_GO(2);
+    case 3: return EM4_GO(3);
+    case 4: return EM4_GO(4);
+    case 5: return EM4_GO(5);
+    case 6: return EM4_GO(6);
+    case 7: return EM4_GO(7);
+    default: return EM4_GO(8);
+    }
+#undef EM4_GO
+}
+
 // _emission.pyx:59,73-80: the running maximum is never reset, so rows are
 // zeroed only while no earlier row of the sequence had a value > -1e20.
 // One warp per flagged sequence; almost never runs.
@@ -478,7 +673,12 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
         else if (prec == TEHMM_F32 && m.G > 0 && emg_smem_bytes(m) <= 227 * 1024) {
             // out-of-range symbols in the slow branch index the dense table: obs must be < S there too,
             // exactly the generic kernel's contract
-            if (b.obs_bytes == 1) e = launch_emg<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+            if (m.LD == 32 && m.G <= 8 && em4_smem_bytes(m) <= 227 * 1024) {
+                if (b.obs_bytes == 1) e = launch_em4<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+                else if (b.obs_bytes == 2) e = launch_em4<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+                else e = launch_em4<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+            }
+            else if (b.obs_bytes == 1) e = launch_emg<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
             else if (b.obs_bytes == 2) e = launch_emg<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
             else e = launch_emg<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
         }

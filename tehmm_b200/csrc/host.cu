@@ -1,0 +1,397 @@
+// Host-buffer decode: the whole call MultitrackHmm.decode makes
+// (hmm.py:668-676 Viterbi, basehmm.py:332-359 MAP), natively.
+//
+//   host symbols --(pinned staging, worker threads)--> HBM
+//       -> emission -> Viterbi DP + traceback | forward + backward(MAP)
+//   uint8 states --PCIe--> pinned --(worker threads, widened)--> caller's int64[T]
+//
+// Everything between the two host buffers is owned by the library: a grow-only
+// device arena per context, two pinned staging rings and a small persistent
+// thread pool.  The Python layer used torch for these steps before: a pageable
+// 100 MB observation matrix took 9.2 ms to upload (one thread, one bounce
+// buffer) and the int64 widening of 10 M states 4.4 ms; see profiles/.
+// Built only on the public C ABI (tehmm_set_batch / tehmm_run_*), so it is a
+// caller of the batched path, not a second implementation of it.
+#include "common.cuh"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+void tehmm_set_error(int code, const char *msg);   // api.cu
+
+namespace {
+
+// ---------------------------------------------------------------- thread pool
+class Pool {
+public:
+    explicit Pool(int n) : stop_(false), gen_(0), pending_(0), ntasks_(0)
+    {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size() + 1; }
+    // run fn(i) for i in [0, n); the calling thread takes part
+    void parallel_for(int n, const std::function<void(int)> &fn)
+    {
+        if (n <= 0) return;
+        if (workers_.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            fn_ = &fn; ntasks_ = n; pending_ = n; next_.store(0); ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> l(mu_);
+        done_.wait(l, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void work()
+    {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= ntasks_) return;
+            (*fn_)(i);
+            std::lock_guard<std::mutex> l(mu_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    bool stop_;
+    uint64_t gen_;
+    int pending_, ntasks_;
+    std::atomic<int> next_;
+    const std::function<void(int)> *fn_ = nullptr;
+};
+
+// uint8 -> int64 with streaming stores (the output is 8x the input and is not read back here)
+void widen_u8_i64(const uint8_t *in, int64_t *out, int64_t n)
+{
+    int64_t i = 0;
+#if defined(__SSE2__)
+    while (i < n && ((uintptr_t)(out + i) & 15)) { out[i] = in[i]; ++i; }
+    const __m128i z = _mm_setzero_si128();
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i *)(in + i));
+        const __m128i w0 = _mm_unpacklo_epi8(v, z), w1 = _mm_unpackhi_epi8(v, z);
+        const __m128i d0 = _mm_unpacklo_epi16(w0, z), d1 = _mm_unpackhi_epi16(w0, z);
+        const __m128i d2 = _mm_unpacklo_epi16(w1, z), d3 = _mm_unpackhi_epi16(w1, z);
+        __m128i *o = (__m128i *)(out + i);
+        _mm_stream_si128(o + 0, _mm_unpacklo_epi32(d0, z));
+        _mm_stream_si128(o + 1, _mm_unpackhi_epi32(d0, z));
+        _mm_stream_si128(o + 2, _mm_unpacklo_epi32(d1, z));
+        _mm_stream_si128(o + 3, _mm_unpackhi_epi32(d1, z));
+        _mm_stream_si128(o + 4, _mm_unpacklo_epi32(d2, z));
+        _mm_stream_si128(o + 5, _mm_unpackhi_epi32(d2, z));
+        _mm_stream_si128(o + 6, _mm_unpacklo_epi32(d3, z));
+        _mm_stream_si128(o + 7, _mm_unpackhi_epi32(d3, z));
+    }
+    _mm_sfence();
+#endif
+    for (; i < n; ++i) out[i] = in[i];
+}
+
+constexpr size_t SLICE = (size_t)8 << 20;   // staging slice
+constexpr int NRING = 4;
+
+struct HostPipe {
+    int device = 0;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    unsigned char *ring[NRING] = {};
+    cudaEvent_t ring_ev[NRING] = {};
+    bool ring_used[NRING] = {};
+    unsigned char *pin_out = nullptr;       // states + the per-sequence scalars
+    size_t pin_out_bytes = 0;
+    Pool *pool = nullptr;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+
+    ~HostPipe()
+    {
+        cudaSetDevice(device);
+        if (arena) cudaFree(arena);
+        for (int i = 0; i < NRING; ++i) {
+            if (ring[i]) cudaFreeHost(ring[i]);
+            if (ring_ev[i]) cudaEventDestroy(ring_ev[i]);
+        }
+        if (pin_out) cudaFreeHost(pin_out);
+        delete pool;
+    }
+};
+
+std::mutex g_mu;
+std::map<tehmm_ctx *, HostPipe *> g_pipes;
+
+int host_threads()
+{
+    const char *e = getenv("TEHMM_HOST_THREADS");
+    int n = e ? atoi(e) : 0;
+    if (n <= 0) {
+        n = (int)std::thread::hardware_concurrency();
+        if (n > 16) n = 16;
+    }
+    return n < 1 ? 1 : n;
+}
+
+HostPipe *get_pipe(tehmm_ctx *c, int device)
+{
+    std::lock_guard<std::mutex> l(g_mu);
+    auto it = g_pipes.find(c);
+    if (it != g_pipes.end()) return it->second;
+    HostPipe *p = new HostPipe();
+    p->device = device;
+    p->pool = new Pool(host_threads() - 1);
+    g_pipes[c] = p;
+    return p;
+}
+
+int herr(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    tehmm_set_error(code, buf);
+    return code;
+}
+#define HCU(x)                                                                                  \
+    do {                                                                                        \
+        cudaError_t e__ = (x);                                                                  \
+        if (e__ != cudaSuccess)                                                                 \
+            return herr(TEHMM_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e__),      \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+#define HOK(x) do { int r__ = (x); if (r__ != TEHMM_OK) return r__; } while (0)
+
+size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// TEHMM_HOST_TRACE=1: wall-clock phases of tehmm_decode_host on stderr (adds a stream sync per phase)
+struct Trace {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t0;
+    std::string line;
+    Trace(cudaStream_t s) : on(getenv("TEHMM_HOST_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *name, bool sync)
+    {
+        if (!on) return;
+        if (sync) cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof buf, " %s %.2f", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+    ~Trace() { if (on) fprintf(stderr, "[tehmm_decode_host ms]%s\n", line.c_str()); }
+};
+
+}   // namespace
+
+// called by tehmm_ctx_destroy
+void tehmm_hostpipe_release(tehmm_ctx *c)
+{
+    HostPipe *p = nullptr;
+    {
+        std::lock_guard<std::mutex> l(g_mu);
+        auto it = g_pipes.find(c);
+        if (it == g_pipes.end()) return;
+        p = it->second;
+        g_pipes.erase(it);
+    }
+    delete p;
+}
+
+extern "C" {
+
+int tehmm_decode_host(tehmm_ctx *c, const void *h_obs, int obs_bytes, int64_t nseq,
+                      const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
+                      double *h_logprob, double *h_score)
+{
+    if (!c || !h_obs || !h_offsets || !h_states || !h_logprob) return herr(TEHMM_EINVAL, "NULL argument");
+    if (algorithm != TEHMM_DECODE_VITERBI && algorithm != TEHMM_DECODE_MAP) return herr(TEHMM_EINVAL, "bad algorithm");
+    if (algorithm == TEHMM_DECODE_MAP && !h_score) return herr(TEHMM_EINVAL, "h_score is required for MAP");
+    if (prec != TEHMM_F32 && prec != TEHMM_F64) return herr(TEHMM_EINVAL, "bad prec");
+    if (nseq <= 0) return herr(TEHMM_EINVAL, "nseq must be positive");
+    int N = 0, K = 0, S = 0;
+    HOK(tehmm_model_dims(c, &N, &K, &S));
+    const int device = tehmm_ctx_device(c);
+    HCU(cudaSetDevice(device));
+    const cudaStream_t st = (cudaStream_t)(uintptr_t)tehmm_ctx_stream(c);
+    HostPipe *p = get_pipe(c, device);
+    Trace tr(st);
+    const int64_t total = h_offsets[nseq];
+    if (total <= 0) return herr(TEHMM_EINVAL, "empty batch");
+    const int LD = tehmm_lattice_stride(c);
+    const size_t ts = prec == TEHMM_F32 ? 4 : 8;
+    const size_t obs_bytes_total = (size_t)total * K * obs_bytes;
+    const size_t lat = (size_t)total * LD * ts;
+
+    // ---- arena layout: obs | states | logprob, score | rowmax | lattice A | lattice B | scratch
+    size_t o = 0;
+    const size_t o_obs = o; o = up256(o + obs_bytes_total);
+    const size_t o_states = o; o = up256(o + (size_t)total);
+    const size_t o_lp = o; o = up256(o + (size_t)nseq * 16);
+    const size_t o_rowmax = o; o = up256(o + (size_t)total * 8);
+    const size_t o_la = o; o = up256(o + lat);
+    const size_t o_lb = o; o = up256(o + lat);
+    const size_t o_scratch = o;
+    // the scratch size depends on the partition: describe the batch first, with the obs pointer
+    // the arena will have (the arena may have to grow before anything is enqueued)
+    auto ensure = [&](size_t need) -> int {
+        if (need <= p->arena_bytes) return TEHMM_OK;
+        HCU(cudaStreamSynchronize(st));
+        if (p->arena) { cudaFree(p->arena); p->arena = nullptr; p->arena_bytes = 0; }
+        const size_t want = need + need / 8;
+        HCU(cudaMalloc(&p->arena, want));
+        p->arena_bytes = want;
+        return TEHMM_OK;
+    };
+    HOK(ensure(o_scratch + ((size_t)96 << 20) + (size_t)total * 8));
+    HOK(tehmm_set_batch(c, (char *)p->arena + o_obs, obs_bytes, nseq, h_offsets));
+    size_t scratch = (size_t)tehmm_scratch_bytes(c, prec);
+    if (o_scratch + scratch > p->arena_bytes) {
+        HOK(ensure(o_scratch + scratch));
+        HOK(tehmm_set_batch(c, (char *)p->arena + o_obs, obs_bytes, nseq, h_offsets));
+        scratch = (size_t)tehmm_scratch_bytes(c, prec);
+    }
+    char *A = (char *)p->arena;
+    tr.mark("set_batch", false);
+
+    // ---- host -> device
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_obs) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned) {
+        HCU(cudaMemcpyAsync(A + o_obs, h_obs, obs_bytes_total, cudaMemcpyHostToDevice, st));
+    } else {
+        // pageable: worker threads fill a pinned slice while the previous one is on the wire
+        const int nth = p->pool->size();
+        int64_t slot = 0;
+        for (size_t off = 0; off < obs_bytes_total; off += SLICE, ++slot) {
+            const int r = (int)(slot % NRING);
+            if (!p->ring[r]) {
+                HCU(cudaMallocHost((void **)&p->ring[r], SLICE));
+                HCU(cudaEventCreateWithFlags(&p->ring_ev[r], cudaEventDisableTiming));
+            }
+            if (p->ring_used[r]) HCU(cudaEventSynchronize(p->ring_ev[r]));
+            const size_t n = std::min(SLICE, obs_bytes_total - off);
+            const unsigned char *src = (const unsigned char *)h_obs + off;
+            unsigned char *dst = p->ring[r];
+            const size_t per = ((n + nth - 1) / nth + 63) & ~(size_t)63;
+            p->pool->parallel_for(nth, [&](int i) {
+                const size_t a = (size_t)i * per;
+                if (a < n) memcpy(dst + a, src + a, std::min(per, n - a));
+            });
+            HCU(cudaMemcpyAsync(A + o_obs + off, dst, n, cudaMemcpyHostToDevice, st));
+            HCU(cudaEventRecord(p->ring_ev[r], st));
+            p->ring_used[r] = true;
+        }
+    }
+    p->h2d_bytes = (int64_t)obs_bytes_total;
+    tr.mark("h2d", true);
+
+    // ---- the trellis
+    double *d_lp = (double *)(A + o_lp), *d_sc = d_lp + nseq;
+    uint8_t *d_states = (uint8_t *)(A + o_states);
+    if (algorithm == TEHMM_DECODE_VITERBI) {
+        HOK(tehmm_run_emission(c, prec, nullptr, A + o_la, nullptr, (double *)(A + o_rowmax)));
+        HOK(tehmm_run_viterbi(c, prec, A + o_la, nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
+    } else {
+        HOK(tehmm_run_emission(c, prec, nullptr, nullptr, A + o_la, (double *)(A + o_rowmax)));
+        HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
+        HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_la, A + o_lb, nullptr, nullptr,
+                               d_states, d_sc, nullptr, A + o_scratch));
+    }
+
+    tr.mark("trellis", true);
+    // ---- device -> host: one byte per step over PCIe, widened by the host's cores
+    const size_t out_bytes = up256((size_t)total) + (size_t)nseq * 16;
+    if (p->pin_out_bytes < out_bytes) {
+        HCU(cudaStreamSynchronize(st));
+        if (p->pin_out) cudaFreeHost(p->pin_out);
+        p->pin_out = nullptr; p->pin_out_bytes = 0;
+        HCU(cudaMallocHost((void **)&p->pin_out, out_bytes + out_bytes / 8));
+        p->pin_out_bytes = out_bytes + out_bytes / 8;
+    }
+    double *pin_lp = (double *)(p->pin_out + up256((size_t)total));
+    HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 16, cudaMemcpyDeviceToHost, st));
+    // slices, so that the widening of slice i overlaps the transfer of slice i+1
+    const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
+    const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
+    std::vector<cudaEvent_t> evs(nsl);
+    for (int i = 0; i < nsl; ++i) {
+        const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+        HCU(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
+        if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
+        HCU(cudaEventRecord(evs[i], st));
+    }
+    const int nth = p->pool->size();
+    int rc = TEHMM_OK;
+    for (int i = 0; i < nsl; ++i) {
+        const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+        cudaError_t e = cudaEventSynchronize(evs[i]);
+        cudaEventDestroy(evs[i]);
+        if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
+        if (n <= 0 || rc != TEHMM_OK) continue;
+        const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
+        const uint8_t *src = p->pin_out + a;
+        int64_t *dst = h_states + a;
+        p->pool->parallel_for(nth, [&](int t) {
+            const int64_t b0 = (int64_t)t * per;
+            if (b0 < n) widen_u8_i64(src + b0, dst + b0, std::min(per, n - b0));
+        });
+    }
+    if (rc != TEHMM_OK) return rc;
+    HCU(cudaStreamSynchronize(st));
+    tr.mark("d2h+widen", false);
+    memcpy(h_logprob, pin_lp, (size_t)nseq * 8);
+    if (h_score) memcpy(h_score, pin_lp + nseq, (size_t)nseq * 8);
+    p->d2h_bytes = (int64_t)total + nseq * 16;
+    return TEHMM_OK;
+}
+
+int64_t tehmm_decode_host_bytes(tehmm_ctx *c, int which)
+{
+    std::lock_guard<std::mutex> l(g_mu);
+    auto it = g_pipes.find(c);
+    if (it == g_pipes.end()) return 0;
+    return which == 0 ? it->second->h2d_bytes : it->second->d2h_bytes;
+}
+
+}   // extern "C"

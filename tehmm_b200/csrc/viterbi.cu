@@ -251,6 +251,149 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
     }
 }
 
+// ---------------------------------------------------------------------------
+// fp32 production DP (N <= 32, LD == 32, no segment ratios): 16 x 2 layout.
+//
+// viterbi_kernel above gives lane j the whole column j of log A and reads the
+// 32 deltas back with 8 broadcast LDS.128 per step.  A broadcast LDS.128 returns
+// 512 bytes to the register file and issues once per 8 cycles per SM
+// sub-partition (profiles/r01_ubench_instruction_rates.txt), i.e. 64 cycles per
+// step against 32 cycles of FADD2/FMNMX3 work: the kernel was bound by the
+// shared-memory return path, not by arithmetic.  Here lane l = 2a + h owns the
+// candidates of from-states i in [16h, 16h+16) for the TWO to-states 2a, 2a+1
+// (still 32 packed entries of log A in registers), so a step needs only
+// delta[16h .. 16h+15] = 4 LDS.128, and one xor-1 shuffle combines the two
+// halves: lane l keeps the maximum of to-state 2a+h = l, so e rows, delta rows
+// and the normalisation stay one-lane-per-state.  max is exact and the adds see
+// the same operands as before, so the lattice is bit-identical to viterbi_kernel's.
+__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 3)
+viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ elog,
+                    float *__restrict__ lattice, float *__restrict__ start_vec,
+                    float *__restrict__ end_vec, const int *__restrict__ bad, int mode)
+{
+    __shared__ __align__(16) float ds_all[TEHMM_WARPS_PER_CTA][2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane & 1, a2 = lane & ~1;
+    const bool own = lane < m.N;
+    // A2[jj][q] = (logA[16h+2q][2a+jj], logA[16h+2q+1][2a+jj])
+    u64 A2[2][8];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            A2[jj][q] = pk2((float)m.cut_trans[(int64_t)(16 * h + 2 * q) * 32 + a2 + jj],
+                            (float)m.cut_trans[(int64_t)(16 * h + 2 * q + 1) * 32 + a2 + jj]);
+    const float ls = (float)m.cut_start[lane];
+    const uint32_t ds_base = (uint32_t)__cvta_generic_to_shared(&ds_all[warp][0][0]);
+    const uint32_t ds_rd = ds_base + 64u * (uint32_t)h, ds_wr = ds_base + 4u * (uint32_t)lane;
+
+    for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
+         ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
+        if (mode == 1 && !bad[ci]) continue;
+        const TehmmChunk ch = b.chunks[ci];
+        int64_t tw = ch.t0;
+        bool from_start = ch.t0 == ch.s0;
+        if (mode == 0 && ch.t0 > ch.s0) {
+            tw = ch.t0 - b.warmup;
+            if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
+        }
+        const float *ep = elog + tw * 32 + lane;
+        float *lp = lattice + tw * 32 + lane;
+        unsigned row = 0;
+        const unsigned row0 = (unsigned)(ch.t0 - tw), row1 = (unsigned)(ch.t1 - tw);
+        float dd;
+
+        // one DP step from dd (all lanes) with emission value et.  wr / rd: shared-space
+        // addresses of this lane's slot and of its half of the vector in the buffer used by
+        // this step (the two buffers alternate, so a lane may run one step ahead of the others).
+        // Lanes >= N need no masking: their columns of log A are -inf and elog padding is 0.
+        auto lean_step = [&](float et, uint32_t wr, uint32_t rd) {
+            asm volatile("st.shared.f32 [%0], %1;" :: "r"(wr), "f"(dd) : "memory");
+            __syncwarp();
+            u64 x[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[2 * q]), "=l"(x[2 * q + 1]) : "r"(rd + 16u * q) : "memory");
+            float p0, p1;
+            {
+                const u64 c0 = fadd2(x[0], A2[0][0]), c1 = fadd2(x[0], A2[1][0]);
+                p0 = fmaxf(lo2(c0), hi2(c0));
+                p1 = fmaxf(lo2(c1), hi2(c1));
+            }
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const u64 c0 = fadd2(x[q], A2[0][q]), c1 = fadd2(x[q], A2[1][q]);
+                p0 = fmax3(p0, lo2(c0), hi2(c0));
+                p1 = fmax3(p1, lo2(c1), hi2(c1));
+            }
+            // lane 2a keeps to-state 2a and needs the partner's p0; lane 2a+1 keeps 2a+1
+            const float give = h ? p0 : p1, keep = h ? p1 : p0;
+            const float v = fmaxf(keep, __shfl_xor_sync(TEHMM_FULL, give, 1)) + et;
+            // every delta and log-probability is <= 0: the row maximum is the unsigned MINIMUM
+            // of the bit patterns (+0.0 = 0 is the smallest pattern, -inf the largest).  An
+            // all -inf row gives -inf - -inf = NaN, which the max turns back into -inf.
+            const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
+            dd = fmaxf(v - M, -INFINITY);
+        };
+        uint32_t wrA = ds_wr, wrB = ds_wr + 128u, rdA = ds_rd, rdB = ds_rd + 128u;
+        auto step1 = [&](float et) {       // single step, then swap the buffers
+            lean_step(et, wrA, rdA);
+            uint32_t t = wrA; wrA = wrB; wrB = t;
+            t = rdA; rdA = rdB; rdB = t;
+        };
+
+        if (mode == 1) {
+            dd = start_vec[ci * 32 + lane];
+        } else if (from_start) {
+            const float v = ls + (own ? *ep : -INFINITY);
+            const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
+            dd = v - (M > -INFINITY ? M : 0.f);
+            if (row0 == 0) *lp = dd;
+            ep += 32; lp += 32;
+            row = 1;
+        } else {
+            dd = own ? 0.f : -INFINITY;
+        }
+        if (mode == 0 && row0 > 0) {
+            for (; row < row0; ++row) { step1(*ep); ep += 32; lp += 32; }
+            start_vec[ci * 32 + lane] = dd;
+        }
+        // steady state: the next VIT_U rows of e in flight; VIT_U is even, so the buffer
+        // parity is the same at the top of every iteration
+        float en[VIT_U];
+        if (row + VIT_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 32];
+        }
+        while (row + 2 * VIT_U <= row1) {
+            float ec[VIT_U];
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) ec[u] = en[u];
+            ep += VIT_U * 32;
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 32];
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) {
+                if (u & 1) lean_step(ec[u], wrB, rdB); else lean_step(ec[u], wrA, rdA);
+                lp[u * 32] = dd;
+            }
+            lp += VIT_U * 32;
+            row += VIT_U;
+        }
+        if (row + VIT_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) {
+                if (u & 1) lean_step(en[u], wrB, rdB); else lean_step(en[u], wrA, rdA);
+                lp[u * 32] = dd;
+            }
+            ep += VIT_U * 32; lp += VIT_U * 32;
+            row += VIT_U;
+        }
+        for (; row < row1; ++row) { step1(*ep); *lp = dd; ep += 32; lp += 32; }
+        end_vec[ci * 32 + lane] = dd;
+    }
+}
+
 // order-preserving key of a float for REDUX (larger value -> larger key)
 __device__ __forceinline__ unsigned order_key(float v)
 {
@@ -628,6 +771,10 @@ cudaError_t tehmm_launch_viterbi(cudaStream_t st, const TehmmModelDev &m, const 
                                  void *start_vec, void *end_vec, const int *bad, int mode, int grid)
 {
     if (prec == TEHMM_F32) {
+        if (m.NS == 1 && m.LD == 32 && !ratios) {
+            viterbi_lean_kernel<<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode);
+            return cudaGetLastError();
+        }
         if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
         return launch_vit<float, 2>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
     }

@@ -7,7 +7,10 @@ described by row offsets; the library partitions time into chunks and runs one
 warp per chunk (see csrc/forward.cu for the speculate / verify / repair scheme).
 """
 import ctypes
+import mmap
 import os
+import threading
+import weakref
 
 import numpy as np
 
@@ -47,6 +50,48 @@ def as_obs_array(obs):
     if a.dtype in (np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.int32)):
         return np.ascontiguousarray(a)
     return np.ascontiguousarray(a.astype(np.int32))
+
+
+class _ResultPool(object):
+    """Host memory for the int64 state paths handed back by decode().
+
+    A fresh 80 MB NumPy array costs ~4 ms of first-touch page faults per 10 M steps,
+    as much as the rest of the decode call.  Blocks are anonymous mmaps; an array
+    handed out is np.frombuffer(block), so it and every slice taken from it keep
+    the block's export alive, and a weakref finalizer returns the block to the pool
+    only when the last of them is unreachable -- the caller sees ordinary, writable,
+    independent int64 arrays."""
+    MAX_FREE = 4
+
+    def __init__(self):
+        self._free = []
+        self._lock = threading.Lock()
+
+    def _put(self, block):
+        with self._lock:
+            if len(self._free) < self.MAX_FREE:
+                self._free.append(block)
+
+    def empty_int64(self, n):
+        nbytes = max(8, int(n) * 8)
+        block = None
+        with self._lock:
+            for i, b in enumerate(self._free):
+                if nbytes <= len(b) <= 2 * nbytes + (4 << 20):
+                    block = self._free.pop(i)
+                    break
+        if block is None:
+            block = mmap.mmap(-1, (nbytes + (2 << 20) - 1) & ~((2 << 20) - 1))
+            try:                                  # first touch in 2 MB pages where the kernel allows it
+                block.madvise(mmap.MADV_HUGEPAGE)
+            except (AttributeError, OSError, ValueError):
+                pass
+        arr = np.frombuffer(block, dtype=np.int64, count=int(n))
+        weakref.finalize(arr, self._put, block)
+        return arr
+
+
+_result_pool = _ResultPool()
 
 
 class Engine(object):
@@ -123,6 +168,39 @@ class Engine(object):
         self.nseq = len(arrays)
         self.h2d_bytes = host.nbytes
         return offsets
+
+    def decode_host(self, obs_list, algorithm, precision=None):
+        """The whole decode call with host buffers on both sides, in the library
+        (tehmm_decode_host: pinned staging + worker threads in, uint8 states over PCIe and
+        widened to the reference's int64 out).  No segment ratios.
+        Returns (logprob float64[nseq], score float64[nseq] (MAP only), [int64 states])."""
+        self._bind_stream()
+        prec, _ = self._prec(precision)
+        arrays = [as_obs_array(o) for o in obs_list]
+        assert len(arrays) > 0
+        K = arrays[0].shape[1]
+        for a in arrays:
+            assert a.shape[1] == K, "all sequences must have the same number of tracks"
+        dt = arrays[0].dtype
+        if any(a.dtype != dt for a in arrays):
+            dt = np.dtype(np.int32)
+            arrays = [a.astype(np.int32) for a in arrays]
+        offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
+        np.cumsum([a.shape[0] for a in arrays], out=offsets[1:])
+        host = arrays[0] if len(arrays) == 1 else np.concatenate(arrays, axis=0)
+        total = int(offsets[-1])
+        states = _result_pool.empty_int64(total)
+        logprob = np.empty(len(arrays), dtype=np.float64)
+        score = np.empty(len(arrays), dtype=np.float64)
+        _lib.check(self.lib.tehmm_decode_host(self.ctx.handle, _lib.ptr(host), dt.itemsize, len(arrays),
+                                              _lib.ptr(offsets), int(algorithm), prec, _lib.ptr(states),
+                                              _lib.ptr(logprob), _lib.ptr(score)))
+        self._keep.pop("obs", None)            # the batch now points into the library's arena
+        self._keep["offsets"] = offsets
+        self.total, self.nseq = total, len(arrays)
+        self.h2d_bytes = int(self.lib.tehmm_decode_host_bytes(self.ctx.handle, 0))
+        self.d2h_bytes = int(self.lib.tehmm_decode_host_bytes(self.ctx.handle, 1))
+        return logprob, score, [states[offsets[i]:offsets[i + 1]] for i in range(len(arrays))]
 
     def use_device_batch(self, d_obs, obs_bytes, offsets):
         """Batch already resident on the device (bench / multi-call reuse)."""

@@ -17,7 +17,7 @@ import string
 import numpy as np
 from numpy.testing import assert_array_almost_equal
 
-from . import parallel
+from . import _lib, parallel
 from .common import EPSILON, logger, logsumexp, myLog, normalize
 from .engine import as_obs_array, get_engine
 
@@ -231,11 +231,20 @@ class MultitrackHmm(BaseHMM):
         if self._algorithm in decoder_algorithms:
             algorithm = self._algorithm
         eng = self._engine()
+        ratios_dp = [self._seg_ratios(o) for o in obs_list] if algorithm == "viterbi" else None
+        if algorithm in ("viterbi", "map") and (ratios_dp is None or all(r is None for r in ratios_dp)):
+            # host buffers in and out, everything in between inside the library
+            lps, scores, states = eng.decode_host(
+                obs_list, _lib.DECODE_VITERBI if algorithm == "viterbi" else _lib.DECODE_MAP)
+            if algorithm == "viterbi":
+                return [(float(lp), st) for lp, st in zip(lps, states)]
+            for lp in lps:
+                self._note_forward_logprob(float(lp))
+            return [(float(sc), st) for sc, st in zip(scores, states)]
         eng.upload_batch(obs_list)
         if algorithm == "viterbi":
             # basehmm.py:327: emission from np.asarray(obs) (no ratios);
             # hmm.py:674: the DP does see the table's segment ratios
-            ratios_dp = [self._seg_ratios(o) for o in obs_list]
             lps, states = eng.viterbi(ratios_em=None, ratios_dp=ratios_dp)
             return [(float(lp), st) for lp, st in zip(lps, states)]
         out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)

@@ -1,0 +1,85 @@
+"""-m gpu: tehmm_decode_host -- the whole decode call with HOST buffers on both
+sides (pinned staging + worker threads in, uint8 states over PCIe widened to the
+reference's int64 out) -- against the oracle and against the device-pointer path
+it is built on.  Reference call being replaced: basehmm.py:361-396 decode ->
+hmm.py:668-676 / basehmm.py:332-359.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_array_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    from tehmm_b200.engine import get_engine
+    eng = get_engine(0)
+    for k in ("chunk_tiles", "warmup", "fine_len"):
+        eng.ctx.set_option(k, 0)
+    eng.ctx.set_option("tile", 1)
+    return eng
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int32])
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_decode_host_matches_oracle(oracle, dtype, prec):
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=5)
+    lens = [1, 7, 4099, 20000, 333]                       # ragged, incl. a one-step sequence
+    seqs = [synth.sample_obs(m, n, seed=10 + i)[0].astype(dtype) for i, n in enumerate(lens)]
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    lp, _, states = eng.decode_host(seqs, _lib.DECODE_VITERBI, precision=prec)
+    flp, score, mstates = eng.decode_host(seqs, _lib.DECODE_MAP, precision=prec)
+    for i, obs in enumerate(seqs):
+        ref = oracle.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+        assert states[i].dtype == np.int64 and states[i].shape == (lens[i],)
+        if prec == "f64":
+            assert_array_equal(states[i], ref["vit_states"])
+            assert_array_equal(mstates[i], ref["map_states"])
+        else:
+            assert np.mean(states[i] == ref["vit_states"]) >= 0.98
+            assert np.mean(mstates[i] == ref["map_states"]) >= 0.98
+        tol = 1e-10 if prec == "f64" else 1e-5
+        assert lp[i] == pytest.approx(ref["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
+        assert flp[i] == pytest.approx(ref["logprob"], rel=tol)
+
+
+def test_decode_host_equals_device_path_large():
+    """1.5 M steps (several staging slices and D2H slices), pageable and pinned input:
+    bit-identical to the torch-plumbed device-pointer path."""
+    import torch
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=0)
+    T = 1_500_000
+    obs, _ = synth.sample_obs(m, T, seed=2)
+    obs2, _ = synth.sample_obs(m, 200_003, seed=3)
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs, obs2])
+    lp_d, st_d = eng.viterbi()
+    out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
+    pinned = torch.from_numpy(obs).pin_memory().numpy()
+    for first in (obs, pinned):
+        lp, _, st = eng.decode_host([first, obs2], _lib.DECODE_VITERBI)
+        assert_array_equal(lp, lp_d)
+        assert_array_equal(st[0], st_d[0])
+        assert_array_equal(st[1], st_d[1])
+        flp, sc, ms = eng.decode_host([first, obs2], _lib.DECODE_MAP)
+        assert_array_equal(flp, out["logprob"])
+        assert_array_equal(sc, out["map_score"])
+        assert_array_equal(ms[0], out["map_states"][0])
+        assert_array_equal(ms[1], out["map_states"][1])
+    assert eng.h2d_bytes == (T + 200_003) * 10 and eng.d2h_bytes == T + 200_003 + 32
+
+
+def test_decode_api_uses_host_path_and_keeps_reference_answers():
+    """hmmTest.py:48-135 known answer through MultitrackHmm.decode (now tehmm_decode_host)."""
+    from tehmm_b200.emission import IndependentMultinomialEmissionModel
+    from tehmm_b200.hmm import MultitrackHmm
+    em = IndependentMultinomialEmissionModel(2, [3], [[[0.1, 0.4, 0.5], [0.6, 0.3, 0.1]]], zeroAsMissingData=False)
+    hmm = MultitrackHmm(em, startprob=[0.6, 0.4], transmat=[[0.7, 0.3], [0.4, 0.6]])
+    lp, st = hmm.decode(np.array([[0], [1], [2]], dtype=np.int64))   # non-fast dtype: cast on host
+    assert np.exp(lp) == pytest.approx(0.01344, rel=1e-6)
+    assert_array_equal(st, [1, 0, 0])
+    assert st.dtype == np.int64

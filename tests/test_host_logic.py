@@ -125,3 +125,31 @@ def test_track_table_ratios_and_overlap():
     assert t.getOverlapInTableCoords(("d", 110, 195, 3)) is None
     u = IntegerTrackTable(2, "c", 100, 200)
     assert u.getOverlapInTableCoords(("c", 50, 120, 1)) == ["c", 0, 20, 1]
+
+
+def test_result_pool_recycles_only_unreachable_blocks():
+    """engine._ResultPool: a block goes back to the pool only when the array handed out
+    and every slice of it are gone; live results are never aliased."""
+    import gc
+    from tehmm_b200.engine import _ResultPool
+    pool = _ResultPool()
+    a = pool.empty_int64(1000)
+    a[:] = 7
+    part = a[10:20]
+    b = pool.empty_int64(1000)
+    b[:] = 9
+    assert a[0] == 7 and not np.shares_memory(a, b)
+    del a
+    gc.collect()
+    assert len(pool._free) == 0          # `part` still references the block
+    c = pool.empty_int64(1000)
+    c[:] = 1
+    assert part[0] == 7
+    del part
+    gc.collect()
+    assert len(pool._free) == 1
+    d = pool.empty_int64(900)            # recycled
+    assert len(pool._free) == 0
+    d[:] = 5
+    assert b[0] == 9 and c[0] == 1
+    assert d.dtype == np.int64 and d.flags.writeable and d.shape == (900,)
