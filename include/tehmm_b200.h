@@ -211,8 +211,11 @@ int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
 /* ------------------------------------------------------------- host buffers
  * The whole call MultitrackHmm.decode makes (/root/reference/basehmm.py:361-396
  * -> hmm.py:668-676 -> _hmm.pyx:201-259 for Viterbi; basehmm.py:332-359 for
- * MAP), with HOST buffers on both sides: h_obs (total,K) symbols (pageable or
- * pinned), h_offsets nseq+1 row offsets, h_states int64[total] out (the dtype
+ * MAP), with HOST buffers on both sides: h_obs_ptrs = nptr pointers to (T_i,K)
+ * symbol matrices, pageable or pinned -- nptr = 1: one matrix holding all the
+ * sequences back to back; nptr = nseq: one matrix per sequence, as the
+ * reference's list of TrackTables (no host-side concatenation) --, h_offsets
+ * nseq+1 row offsets, h_states int64[total] out (the dtype
  * the reference returns, _hmm.pyx:210), h_logprob float64[nseq] out (Viterbi:
  * path log-probability; MAP: forward log-likelihood), h_score float64[nseq] out
  * (MAP: sum of the posterior maxima, basehmm.py:357; may be NULL for Viterbi).
@@ -222,14 +225,23 @@ int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
  * states that crossed PCIe.  Blocks until the outputs are complete.          */
 #define TEHMM_DECODE_VITERBI 0
 #define TEHMM_DECODE_MAP 1
-int tehmm_decode_host(tehmm_ctx *ctx, const void *h_obs, int obs_bytes, int64_t nseq,
-                      const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
-                      double *h_logprob, double *h_score);
+int tehmm_decode_host(tehmm_ctx *ctx, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes,
+                      int64_t nseq, const int64_t *h_offsets, int algorithm, int prec,
+                      int64_t *h_states, double *h_logprob, double *h_score);
 /* bytes the last tehmm_decode_host moved over PCIe: which = 0 host->device, 1 device->host */
 int64_t tehmm_decode_host_bytes(tehmm_ctx *ctx, int which);
 /* device index / model shape of a context */
 int tehmm_ctx_device(tehmm_ctx *ctx);
 int tehmm_model_dims(tehmm_ctx *ctx, int *N, int *K, int *S);
+
+/* float64 score of a state path over the rows [lo, hi) of the current batch, in the
+ * reference's terms (_hmm.pyx:222-225,232-248: start or transition term + emission
+ * per row): d_logprob[s] = sum over the rows of sequence s inside the range.  With
+ * [0, total) this is what tehmm_run_viterbi returns; a sub-range is one rank's
+ * share when a single long sequence is sharded in time.  */
+int tehmm_path_score(tehmm_ctx *ctx, const uint8_t *d_states, const double *d_ratios_emission,
+                     const double *d_ratios_dp, int64_t lo, int64_t hi, double *d_logprob,
+                     void *d_scratch);
 
 /* widen / convert on the device before a D2H copy */
 int tehmm_widen_states(tehmm_ctx *ctx, const uint8_t *d_in, int64_t *d_out, int64_t n);

@@ -28,7 +28,7 @@ cudaError_t tehmm_launch_map_reduce(cudaStream_t, const TehmmBatchDev &, const d
 cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, void *, void *, void *, const int *, int, int);
 cudaError_t tehmm_launch_traceback(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, uint8_t *, int64_t *, uint8_t *, uint8_t *, const uint8_t *, const int *, int, int);
 cudaError_t tehmm_launch_tb_verify(cudaStream_t, const TehmmBatchDev &, uint8_t *, const uint8_t *, uint8_t *, int *, int *);
-cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const uint8_t *, const double *, const double *, double *, double *);
+cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const uint8_t *, const double *, const double *, double *, double *, int64_t, int64_t);
 cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, double *, double *, int, int);
 size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
 cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
@@ -947,8 +947,22 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         c->launches += 1;
     }
     tk_begin(c, TK_RESCORE);
-    CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob));   // latency bound too: fine partition
+    CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob, 0, TBP.total));   // latency bound too: fine partition
     tk_end(c, TK_RESCORE);
+    c->launches += 2;
+    return TEHMM_OK;
+}
+
+int tehmm_path_score(tehmm_ctx *c, const uint8_t *d_states, const double *d_ratios_emission,
+                     const double *d_ratios_dp, int64_t lo, int64_t hi, double *d_logprob, void *d_scratch)
+{
+    int prec = TEHMM_F32;
+    RUN_PROLOGUE();
+    if (!d_states || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument");
+    if (lo < 0 || hi > c->b.total || lo > hi) return fail(TEHMM_EINVAL, "row range [%lld,%lld) outside the batch", (long long)lo, (long long)hi);
+    const Scratch s = carve(c, prec);
+    double *sp = (double *)((char *)d_scratch + s.part_a);
+    CU(tehmm_launch_rescore(st, c->m, c->bf, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob, lo, hi));
     c->launches += 2;
     return TEHMM_OK;
 }

@@ -238,11 +238,14 @@ void tehmm_hostpipe_release(tehmm_ctx *c)
 
 extern "C" {
 
-int tehmm_decode_host(tehmm_ctx *c, const void *h_obs, int obs_bytes, int64_t nseq,
+int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes, int64_t nseq,
                       const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
                       double *h_logprob, double *h_score)
 {
-    if (!c || !h_obs || !h_offsets || !h_states || !h_logprob) return herr(TEHMM_EINVAL, "NULL argument");
+    if (!c || !h_obs_ptrs || !h_offsets || !h_states || !h_logprob) return herr(TEHMM_EINVAL, "NULL argument");
+    if (nptr != 1 && nptr != nseq) return herr(TEHMM_EINVAL, "nptr must be 1 (one contiguous matrix) or nseq (one matrix per sequence)");
+    for (int64_t i = 0; i < nptr; ++i)
+        if (!h_obs_ptrs[i] && (nptr == 1 || h_offsets[i + 1] > h_offsets[i])) return herr(TEHMM_EINVAL, "h_obs_ptrs[%lld] is NULL", (long long)i);
     if (algorithm != TEHMM_DECODE_VITERBI && algorithm != TEHMM_DECODE_MAP) return herr(TEHMM_EINVAL, "bad algorithm");
     if (algorithm == TEHMM_DECODE_MAP && !h_score) return herr(TEHMM_EINVAL, "h_score is required for MAP");
     if (prec != TEHMM_F32 && prec != TEHMM_F64) return herr(TEHMM_EINVAL, "bad prec");
@@ -293,16 +296,28 @@ int tehmm_decode_host(tehmm_ctx *c, const void *h_obs, int obs_bytes, int64_t ns
     tr.mark("set_batch", false);
 
     // ---- host -> device
-    cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, h_obs) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    else cudaGetLastError();
+    // the batch as a list of host segments (one, or one per sequence -- no host-side concatenation)
+    struct Seg { const unsigned char *src; size_t off, n; };
+    std::vector<Seg> segs;
+    if (nptr == 1) segs.push_back(Seg{(const unsigned char *)h_obs_ptrs[0], 0, obs_bytes_total});
+    else
+        for (int64_t i = 0; i < nseq; ++i) {
+            const size_t off = (size_t)h_offsets[i] * K * obs_bytes, n = (size_t)(h_offsets[i + 1] - h_offsets[i]) * K * obs_bytes;
+            if (n) segs.push_back(Seg{(const unsigned char *)h_obs_ptrs[i], off, n});
+        }
+    bool pinned = nptr == 1;
     if (pinned) {
-        HCU(cudaMemcpyAsync(A + o_obs, h_obs, obs_bytes_total, cudaMemcpyHostToDevice, st));
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, h_obs_ptrs[0]) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        else { cudaGetLastError(); pinned = false; }
+    }
+    if (pinned) {
+        HCU(cudaMemcpyAsync(A + o_obs, h_obs_ptrs[0], obs_bytes_total, cudaMemcpyHostToDevice, st));
     } else {
         // pageable: worker threads fill a pinned slice while the previous one is on the wire
         const int nth = p->pool->size();
         int64_t slot = 0;
+        size_t si = 0;                                   // first segment that reaches into the slice
         for (size_t off = 0; off < obs_bytes_total; off += SLICE, ++slot) {
             const int r = (int)(slot % NRING);
             if (!p->ring[r]) {
@@ -311,12 +326,21 @@ int tehmm_decode_host(tehmm_ctx *c, const void *h_obs, int obs_bytes, int64_t ns
             }
             if (p->ring_used[r]) HCU(cudaEventSynchronize(p->ring_ev[r]));
             const size_t n = std::min(SLICE, obs_bytes_total - off);
-            const unsigned char *src = (const unsigned char *)h_obs + off;
+            while (si + 1 < segs.size() && segs[si].off + segs[si].n <= off) ++si;
             unsigned char *dst = p->ring[r];
             const size_t per = ((n + nth - 1) / nth + 63) & ~(size_t)63;
+            const Seg *sg = segs.data();
+            const size_t nsg = segs.size(), si0 = si;
             p->pool->parallel_for(nth, [&](int i) {
-                const size_t a = (size_t)i * per;
-                if (a < n) memcpy(dst + a, src + a, std::min(per, n - a));
+                size_t a = off + (size_t)i * per;                       // byte range [a, e) of the batch
+                const size_t e = std::min(off + n, a + per);
+                size_t k = si0;
+                while (a < e) {
+                    while (k + 1 < nsg && sg[k].off + sg[k].n <= a) ++k;
+                    const size_t m = std::min(e, sg[k].off + sg[k].n) - a;
+                    memcpy(dst + (a - off), sg[k].src + (a - sg[k].off), m);
+                    a += m;
+                }
             });
             HCU(cudaMemcpyAsync(A + o_obs + off, dst, n, cudaMemcpyHostToDevice, st));
             HCU(cudaEventRecord(p->ring_ev[r], st));

@@ -704,7 +704,7 @@ __global__ void vit_rescore_kernel(TehmmModelDev m, TehmmBatchDev b, const OBS *
                                    const uint8_t *__restrict__ states,
                                    const double *__restrict__ ratios_em,
                                    const double *__restrict__ ratios_dp,
-                                   double *__restrict__ score_part)
+                                   double *__restrict__ score_part, int64_t lo, int64_t hi)
 {
     int64_t ci = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -712,7 +712,9 @@ __global__ void vit_rescore_kernel(TehmmModelDev m, TehmmBatchDev b, const OBS *
     const TehmmChunk ch = b.chunks[ci];
     const int N = m.N;
     double acc = 0.0;
-    for (int64_t t = ch.t0 + lane; t < ch.t1; t += 32) {
+    // [lo, hi): the rows whose terms are wanted (the whole batch for decode; a core range
+    // when one long sequence is sharded in time across ranks, parallel.py)
+    for (int64_t t = max(ch.t0, lo) + lane; t < min(ch.t1, hi); t += 32) {
         const int j = states[t];
         double e = 0.0;
         for (int k = 0; k < m.K; ++k)
@@ -833,13 +835,14 @@ cudaError_t tehmm_launch_tb_verify(cudaStream_t st, const TehmmBatchDev &b, uint
 // float64 re-score of the path: 2 launches
 cudaError_t tehmm_launch_rescore(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                  const uint8_t *states, const double *ratios_em,
-                                 const double *ratios_dp, double *score_part, double *logprob)
+                                 const double *ratios_dp, double *score_part, double *logprob,
+                                 int64_t lo, int64_t hi)
 {
     int warps = 4;
     int rgrid = (int)((b.nchunks + warps - 1) / warps);
-    if (b.obs_bytes == 1) vit_rescore_kernel<uint8_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint8_t *)b.obs, states, ratios_em, ratios_dp, score_part);
-    else if (b.obs_bytes == 2) vit_rescore_kernel<uint16_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint16_t *)b.obs, states, ratios_em, ratios_dp, score_part);
-    else vit_rescore_kernel<int32_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const int32_t *)b.obs, states, ratios_em, ratios_dp, score_part);
+    if (b.obs_bytes == 1) vit_rescore_kernel<uint8_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint8_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
+    else if (b.obs_bytes == 2) vit_rescore_kernel<uint16_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint16_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
+    else vit_rescore_kernel<int32_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const int32_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
     vit_score_reduce_kernel<<<(int)b.nseq, b.nchunks / b.nseq >= 256 ? 256 : 64, 0, st>>>(b, score_part, logprob);
     return cudaGetLastError();
 }

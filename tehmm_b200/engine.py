@@ -187,12 +187,12 @@ class Engine(object):
             arrays = [a.astype(np.int32) for a in arrays]
         offsets = np.zeros(len(arrays) + 1, dtype=np.int64)
         np.cumsum([a.shape[0] for a in arrays], out=offsets[1:])
-        host = arrays[0] if len(arrays) == 1 else np.concatenate(arrays, axis=0)
+        ptrs = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])   # no concatenation
         total = int(offsets[-1])
         states = _result_pool.empty_int64(total)
         logprob = np.empty(len(arrays), dtype=np.float64)
         score = np.empty(len(arrays), dtype=np.float64)
-        _lib.check(self.lib.tehmm_decode_host(self.ctx.handle, _lib.ptr(host), dt.itemsize, len(arrays),
+        _lib.check(self.lib.tehmm_decode_host(self.ctx.handle, ptrs, len(arrays), dt.itemsize, len(arrays),
                                               _lib.ptr(offsets), int(algorithm), prec, _lib.ptr(states),
                                               _lib.ptr(logprob), _lib.ptr(score)))
         self._keep.pop("obs", None)            # the batch now points into the library's arena
@@ -404,6 +404,80 @@ class Engine(object):
         elog, _, _ = self.run_emission(prec, tdt, d_re, True, False)
         states, _, logprob = self.run_viterbi(prec, elog, d_re, d_rd, want64=False)
         return logprob.cpu().numpy(), self.split(self.states_to_host(states))
+
+    # ------------------------------------------------------------ one window of a time-sharded sequence
+    # (parallel.run_time_sharded: core = this rank's rows, window = core + halo on both sides)
+    def viterbi_window(self, obs, core, window, precision=None):
+        """Viterbi on obs[window]; returns what parallel.run_time_sharded needs: the core's
+        states (int64), the float64 path score of the core rows, the states at a-1 / b-1 and
+        the max-normalised delta rows at those two times."""
+        torch = self.torch
+        prec, tdt = self._prec(precision)
+        (a, b), (w0, w1) = core, window
+        self.upload_batch([obs[w0:w1]])
+        elog, _, _ = self.run_emission(prec, tdt, None, True, False)
+        lattice = self.empty(int(self.lib.tehmm_viterbi_workspace_bytes(self.ctx.handle, prec)), torch.uint8)
+        states = self.empty(self.total, torch.uint8)
+        logprob = self.empty(1, torch.float64)
+        sc = self.scratch(prec)
+        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), None, None, self._p(lattice),
+                                              self._p(states), None, self._p(logprob), self._p(sc)))
+        part = self.empty(1, torch.float64)
+        _lib.check(self.lib.tehmm_path_score(self.ctx.handle, self._p(states), None, None, a - w0, b - w0,
+                                             self._p(part), self._p(sc)))
+        lat = lattice.view(tdt).view(self.total, self.LD)
+
+        def row(t):
+            return lat[t - w0, :self.N].double().cpu().numpy()
+        out = {"mode": "diff", "tol": 1e-5 if prec == _lib.F32 else 1e-11,
+               "right_state": int(states[b - 1 - w0].item()), "right_probe": row(b - 1),
+               "left_state": int(states[a - 1 - w0].item()) if a > w0 else None,
+               "left_probe": row(a - 1) if a > w0 else None}
+        core_states = self.states_to_host(states[a - w0:b - w0])
+        out["result"] = (float(part.item()), core_states)
+        return out
+
+    def map_window(self, obs, core, window, band=64, precision=None):
+        """posterior (MAP) decoding of obs[window]: the core's states; the probes are the
+        decoded states in a band around each core boundary, which both neighbours compute
+        (one with an exact forward and a speculative backward pass, the other the reverse)."""
+        (a, b), (w0, w1) = core, window
+        self.upload_batch([obs[w0:w1]])
+        out = self.posteriors(renorm_eps=True, want_post=False, want_map=True, precision=precision)
+        st = out["map_states"][0]
+
+        def bandv(t):          # states over [t - band, t + band), clipped identically on both ranks
+            lo, hi = max(0, t - band), min(obs.shape[0], t + band)
+            v = np.full(2 * band, -1.0)
+            seg = st[max(lo, w0) - w0:min(hi, w1) - w0]
+            v[max(lo, w0) - (t - band):max(lo, w0) - (t - band) + len(seg)] = seg
+            return v
+        res = {"mode": "equal", "tol": 0.0, "left_state": None, "right_state": None,
+               "right_probe": bandv(b), "left_probe": bandv(a) if a > 0 else None}
+        res["result"] = st[a - w0:b - w0]
+        return res
+
+    def score_window(self, obs, core, window, precision=None):
+        """this rank's increment of the forward log-likelihood: logP(x[w0:b)) - logP(x[w0:a)),
+        both from a flat start at w0 (rank 0: w0 = a = 0 and the increment is logP(x[0:b)));
+        probes are the forward vectors at a-1 and b-1."""
+        prec, tdt = self._prec(precision)
+        (a, b), (w0, w1) = core, window
+        seqs = [obs[w0:b]] + ([obs[w0:a]] if a > w0 else [])
+        self.upload_batch(seqs)
+        _, blin, rowmax = self.run_emission(prec, tdt, None, False, True)
+        alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, None)
+        lp = logprob.cpu().numpy()
+        al = alpha.view(self.total, self.LD)
+
+        def row(i):
+            v = al[i, :self.N].double().cpu().numpy()
+            return v / v.max() if v.max() > 0 else v
+        res = {"mode": "ratio", "tol": 4e-6 if prec == _lib.F32 else 1e-12, "left_state": None,
+               "right_state": None, "right_probe": row(b - w0 - 1),
+               "left_probe": row((b - w0) + (a - w0) - 1) if a > w0 else None}
+        res["result"] = float(lp[0] - (lp[1] if a > w0 else 0.0))
+        return res
 
     def estep(self, ratios=None, want_start=True, want_trans=True, want_obs=True,
               precision=None, device_result=False, seq_slots=None, stats_S=None):

@@ -254,6 +254,36 @@ class MultitrackHmm(BaseHMM):
             res.append((float(sc), st))
         return res
 
+    # ------------------------------------------------------------ one long sequence over all ranks
+    def decode_sharded(self, obs, algorithm="viterbi", halo=4096, gather=True):
+        """decode() of ONE long sequence with its time axis split over the ranks of the
+        process group (parallel.run_time_sharded).  Every
+        rank passes the same `obs`; no segment ratios.  Returns (logprob, states): the whole
+        int64 path on every rank (gather=True) or this rank's core range only.  For
+        algorithm="map" the first value is the forward log-likelihood (score_sharded), not
+        the reference's sum of posterior maxima."""
+        if self._algorithm in decoder_algorithms:
+            algorithm = self._algorithm
+        obs = as_obs_array(obs)
+        T = obs.shape[0]
+        eng = self._engine()
+        if algorithm == "viterbi":
+            (part, core), _, _ = parallel.run_time_sharded(T, lambda c, w: eng.viterbi_window(obs, c, w), halo)
+            lp = parallel.sum_over_ranks(part)
+        elif algorithm == "map":
+            core, _, _ = parallel.run_time_sharded(T, lambda c, w: eng.map_window(obs, c, w), halo)
+            lp = self.score_sharded(obs, halo)
+        else:
+            raise ValueError("Decoder algorithm %r is not one of %s" % (algorithm, decoder_algorithms))
+        return lp, (parallel.gather_states(core, T) if gather else core)
+
+    def score_sharded(self, obs, halo=4096):
+        """score() of one long sequence, forward pass split in time over the ranks."""
+        obs = as_obs_array(obs)
+        eng = self._engine()
+        inc, _, _ = parallel.run_time_sharded(obs.shape[0], lambda c, w: eng.score_window(obs, c, w), halo)
+        return parallel.sum_over_ranks(inc)
+
     def decode(self, obs, algorithm="viterbi"):
         """(logprob, state_sequence int64) (basehmm.py:361-396)."""
         return self.decode_batch([obs], algorithm)[0]

@@ -83,3 +83,52 @@ def test_decode_api_uses_host_path_and_keeps_reference_answers():
     assert np.exp(lp) == pytest.approx(0.01344, rel=1e-6)
     assert_array_equal(st, [1, 0, 0])
     assert st.dtype == np.int64
+
+
+@pytest.mark.parametrize("nranks", [2, 5])
+def test_time_sharded_single_sequence_virtual_ranks(nranks):
+    """one long sequence split in time over `nranks` (virtual) ranks --
+    every rank's window decoded on this GPU in turn, the boundary vectors exchanged through
+    the same verdict the all-gather feeds -- equals the single-GPU decode of the whole
+    sequence: Viterbi path and float64 score, MAP path, forward log-likelihood."""
+    from tehmm_b200 import parallel, synth
+    m = synth.make_model(N=30, seed=4)
+    T = 400_000
+    obs, _ = synth.sample_obs(m, T, seed=9)
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    lp_full, st_full = eng.viterbi()
+    out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
+    shards = parallel.time_shards(T, nranks)
+    H = 2048
+    for fn, kind in ((eng.viterbi_window, "viterbi"), (eng.map_window, "map"), (eng.score_window, "score")):
+        res = [fn(obs, c, (max(0, c[0] - H), min(T, c[1] + H))) for c in shards]
+        allv = [parallel.boundary_vector(r) for r in res]
+        assert parallel.boundaries_agree(allv, shards, res[0]["mode"], res[0]["tol"]), kind
+        if kind == "viterbi":
+            path = np.concatenate([r["result"][1] for r in res])
+            assert_array_equal(path, st_full[0])
+            assert sum(r["result"][0] for r in res) == pytest.approx(lp_full[0], rel=1e-12)
+        elif kind == "map":
+            assert_array_equal(np.concatenate([r["result"] for r in res]), out["map_states"][0])
+        else:
+            assert sum(r["result"] for r in res) == pytest.approx(out["logprob"][0], rel=1e-9)
+    # a halo of 2 steps must be caught at the boundaries
+    res = [eng.viterbi_window(obs, c, (max(0, c[0] - 2), min(T, c[1] + 2))) for c in shards]
+    assert not parallel.boundaries_agree([parallel.boundary_vector(r) for r in res], shards, "diff", 1e-5)
+
+
+def test_decode_host_list_of_sequences_without_concatenation():
+    """nptr = nseq: one host matrix per sequence (the reference's list of TrackTables)"""
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=6)
+    lens = [3_000_001, 17, 1_200_000, 5]                 # slices of the staging ring span sequences
+    seqs = [synth.sample_obs(m, n, seed=40 + i)[0] for i, n in enumerate(lens)]
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    lp, _, st = eng.decode_host(seqs, _lib.DECODE_VITERBI)
+    for i, s in enumerate(seqs):
+        lp1, _, st1 = eng.decode_host([s], _lib.DECODE_VITERBI)
+        assert_array_equal(st[i], st1[0])
+        assert lp[i] == pytest.approx(lp1[0], rel=1e-12)

@@ -24,6 +24,6 @@ lp = np.empty(1); sc = np.empty(1)
 off = np.array([0, T], dtype=np.int64)
 for it in range(3):
     t0 = time.perf_counter()
-    _lib.check(eng.lib.tehmm_decode_host(eng.ctx.handle, _lib.ptr(pinned), 1, 1, _lib.ptr(off), 0, 0, _lib.ptr(states), _lib.ptr(lp), _lib.ptr(sc)))
+    _lib.check(eng.lib.tehmm_decode_host(eng.ctx.handle, (ctypes.c_void_p * 1)(pinned.ctypes.data), 1, 1, 1, _lib.ptr(off), 0, 0, _lib.ptr(states), _lib.ptr(lp), _lib.ptr(sc)))
     print("warm output: %.2f ms" % ((time.perf_counter() - t0) * 1e3), file=sys.stderr)
 print(open("/sys/kernel/mm/transparent_hugepage/enabled").read(), open("/sys/kernel/mm/transparent_hugepage/defrag").read(), file=sys.stderr)
