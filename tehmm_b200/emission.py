@@ -158,22 +158,18 @@ class IndependentMultinomialEmissionModel(object):
         off = self._offset()
         for track in range(self.numTracks):
             lo, hi = off, self.numSymbolsPerTrack[track] + off
-            for state in range(self.numStates):
-                counts = obsStats[track, state, lo:hi]
-                total = 0.0
-                for c in counts:                      # sequential sum, as the reference
-                    total += c
-                denom = max(self.fudge, total)
-                if denom != 0.:
-                    probs = counts / denom
-                else:
-                    probs = np.zeros_like(counts)
-                trackSum = 0
-                for p in probs:
-                    trackSum += p
-                if trackSum < EPSILON:
-                    continue                          # orphaned state/track: leave as was
-                self.logProbs[track, state, lo:hi] = myLog(probs, logZeroVal=-1e6)
+            if hi <= lo:
+                continue
+            counts = np.asarray(obsStats[track, :, lo:hi], dtype=np.float64)      # (states, symbols)
+            # np.cumsum adds left to right, like the reference's `total += c` loop (np.sum is pairwise)
+            total = np.cumsum(counts, axis=1)[:, -1]
+            denom = np.maximum(self.fudge, total)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                probs = np.where(denom[:, None] != 0., counts / denom[:, None], 0.)
+            trackSum = np.cumsum(probs, axis=1)[:, -1]
+            keep = ~(trackSum < EPSILON)              # orphaned state/track: leave as was
+            if keep.any():
+                self.logProbs[track, keep, lo:hi] = myLog(probs[keep], logZeroVal=-1e6)
         self.validate()
 
     def validate(self):
@@ -185,15 +181,13 @@ class IndependentMultinomialEmissionModel(object):
             return
         # product of per-track sums == sum over the product space
         off = self._offset()
-        for state in range(self.numStates):
-            total = 1.0
-            for track in range(self.numTracks):
-                if self.numSymbolsPerTrack[track] > 0:
-                    total *= np.exp(self.logProbs[track, state,
-                                                  off:self.numSymbolsPerTrack[track] + off]).sum()
-                else:
-                    total *= np.exp(self.logProbs[track, state, 0])
-            assert_array_almost_equal(total, 1.)
+        total = np.ones(self.numStates)
+        for track in range(self.numTracks):
+            if self.numSymbolsPerTrack[track] > 0:
+                total *= np.exp(self.logProbs[track, :, off:self.numSymbolsPerTrack[track] + off]).sum(axis=1)
+            else:
+                total *= np.exp(self.logProbs[track, :, 0])
+        assert_array_almost_equal(total, np.ones(self.numStates))
 
     def sample(self, state):
         return None

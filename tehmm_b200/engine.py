@@ -106,6 +106,8 @@ class Engine(object):
         self.device = torch.device("cuda", self.ctx.device)
         self._keep = {}
         self.N = self.K = self.S = None
+        self.batch_token = None        # set by fit(): the resident batch is reused across EM iterations
+        self.batch_ratios = None
 
     # ------------------------------------------------------------ plumbing
     def _bind_stream(self):
@@ -143,6 +145,7 @@ class Engine(object):
         Returns (offsets ndarray int64[nseq+1])."""
         torch = self.torch
         self._bind_stream()
+        self.batch_token = None
         arrays = [as_obs_array(o) for o in obs_list]
         assert len(arrays) > 0
         K = arrays[0].shape[1]
@@ -175,6 +178,7 @@ class Engine(object):
         widened to the reference's int64 out).  No segment ratios.
         Returns (logprob float64[nseq], score float64[nseq] (MAP only), [int64 states])."""
         self._bind_stream()
+        self.batch_token = None
         prec, _ = self._prec(precision)
         arrays = [as_obs_array(o) for o in obs_list]
         assert len(arrays) > 0
@@ -205,6 +209,7 @@ class Engine(object):
     def use_device_batch(self, d_obs, obs_bytes, offsets):
         """Batch already resident on the device (bench / multi-call reuse)."""
         self._bind_stream()
+        self.batch_token = None
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self._keep["obs"] = d_obs
         self._keep["offsets"] = offsets
@@ -492,7 +497,7 @@ class Engine(object):
         N, K = self.N, self.K
         S = self.stats_S = int(stats_S) if stats_S else self.S    # width of the caller's obsStats
         n_total, slots = seq_slots if seq_slots is not None else (self.nseq, list(range(self.nseq)))
-        d_r = self.upload_ratios(ratios)
+        d_r = ratios if (ratios is None or torch.is_tensor(ratios)) else self.upload_ratios(ratios)
         _, blin, rowmax = self.run_emission(prec, tdt, d_r, False, True)
         alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_r)
         base = 2 + N + N * N + K * N * S
