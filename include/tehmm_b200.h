@@ -93,12 +93,14 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
 /* options: "chunk_tiles" (tiles of 64 steps per chunk, 0 = auto),
  * "warmup" (speculative warm-up steps, 0 = auto), "max_repair" (passes),
  * "tile" (0 = never use the tensor-core tile kernels), "fine_len" (steps per
- * chunk of the fine partition, 0 = auto), "timing" (1 = bracket the first
+ * chunk of the fine partition, 0 = auto), "xi_tile" (0 = expected transition
+ * counts by the one-chunk-per-warp backward kernel instead of the tensor-core
+ * xi kernel), "timing" (1 = bracket the first
  * launch of each main kernel with CUDA events on the context's stream).
  * stats: "launches", "chunks", "fine_chunks", "repaired_chunks_<pass>",
  * "repair_passes_<pass>", "tile_passes", and with "timing" the mean duration in
  * microseconds (over the launches since "timing" was set, at most 32) of "us_emission", "us_forward", "us_backward",
- * "us_viterbi_dp", "us_traceback", "us_rescore", "us_emission_stats" launch
+ * "us_viterbi_dp", "us_traceback", "us_rescore", "us_emission_stats", "us_xi" launch
  * (blocks until that launch has finished; -1 if it never ran). */
 int tehmm_ctx_set_option(tehmm_ctx *ctx, const char *name, int64_t value);
 int64_t tehmm_ctx_get_stat(tehmm_ctx *ctx, const char *name);

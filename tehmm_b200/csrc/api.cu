@@ -35,6 +35,8 @@ cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t
 cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int);
 cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int);
 int tehmm_tile_warps(void);
+cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
+size_t tehmm_xi_tile_scratch_bytes(int sms);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
 
 // ---------------------------------------------------------------- errors
@@ -67,9 +69,9 @@ struct DevBuf {   // RAII device allocation for the strict host-pointer entry po
 };
 
 #define TEHMM_TRING 32
-enum { TK_EMISSION, TK_FORWARD, TK_BACKWARD, TK_VITERBI_DP, TK_TRACEBACK, TK_RESCORE, TK_STATS, TEHMM_NTIMED };
+enum { TK_EMISSION, TK_FORWARD, TK_BACKWARD, TK_VITERBI_DP, TK_TRACEBACK, TK_RESCORE, TK_STATS, TK_XI, TEHMM_NTIMED };
 static const char *const tk_names[TEHMM_NTIMED] = {"us_emission", "us_forward", "us_backward", "us_viterbi_dp",
-                                                    "us_traceback", "us_rescore", "us_emission_stats"};
+                                                    "us_traceback", "us_rescore", "us_emission_stats", "us_xi"};
 
 struct tehmm_ctx {
     int device = 0;
@@ -82,6 +84,7 @@ struct tehmm_ctx {
     // option "timing": CUDA events around the first (speculative) launch of each main kernel, on the
     // launching stream; read back in microseconds with tehmm_ctx_get_stat("us_<kernel>")
     int64_t opt_timing = 0;
+    int64_t opt_xi_tile = 1;          // expected transition counts by xi_tile_kernel (0: one-chunk-per-warp backward)
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
     int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
@@ -185,6 +188,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "tile")) c->opt_tile = v;
     else if (!strcmp(name, "timing")) { c->opt_timing = v; for (int i = 0; i < TEHMM_NTIMED; ++i) c->ev_n[i] = 0; }
     else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
+    else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -434,10 +438,11 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     // needs as few table look-ups as possible within the shared-memory budget.  Greedy:
     // repeatedly merge the two groups whose merge adds the fewest rows.
     struct Grp { std::vector<int> trk; int64_t rows; };
-    std::vector<Grp> grp;
-    int64_t grows = 0;
-    if (NS == 1) {
-        for (int k = 0; k < K; ++k) { grp.push_back(Grp{{k}, nsym[k]}); grows += nsym[k]; }
+    auto make_groups = [&](int64_t row_budget, int max_groups, std::vector<Grp> &grp) -> int64_t {
+        int64_t total_rows = 0;
+        grp.clear();
+        if (NS != 1) return 0;
+        for (int k = 0; k < K; ++k) { grp.push_back(Grp{{k}, nsym[k]}); total_rows += nsym[k]; }
         for (;;) {
             int bi = -1, bj = -1;
             int64_t best = 0;
@@ -445,21 +450,44 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
                 for (size_t j = i + 1; j < grp.size(); ++j) {
                     if (grp[i].trk.size() + grp[j].trk.size() > 4) continue;
                     const int64_t add = grp[i].rows * grp[j].rows - grp[i].rows - grp[j].rows;
-                    if (grows + add > TEHMM_GROWS_MAX) continue;
+                    if (total_rows + add > row_budget) continue;
                     if (bi < 0 || add < best) { bi = (int)i; bj = (int)j; best = add; }
                 }
             if (bi < 0) break;
             grp[bi].trk.insert(grp[bi].trk.end(), grp[bj].trk.begin(), grp[bj].trk.end());
             grp[bi].rows *= grp[bj].rows;
             grp.erase(grp.begin() + bj);
-            grows += best;
+            total_rows += best;
         }
-        if ((int)grp.size() > TEHMM_GMAX || grows > TEHMM_GROWS_MAX) { grp.clear(); grows = 0; }
-    }
+        if ((int)grp.size() > max_groups || total_rows > row_budget) { grp.clear(); total_rows = 0; }
+        return total_rows;
+    };
+    auto write_desc = [&](const std::vector<Grp> &grp, int32_t *gd) {
+        int64_t base = 0;
+        for (size_t gi = 0; gi < grp.size(); ++gi) {
+            int32_t *d = gd + gi * TEHMM_GDESC;
+            d[0] = (int32_t)grp[gi].trk.size();
+            d[1] = (int32_t)base;
+            int64_t stride = 1;
+            for (size_t i = 0; i < grp[gi].trk.size(); ++i) {
+                d[2 + i] = grp[gi].trk[i];
+                d[6 + i] = (int32_t)stride;
+                stride *= nsym[grp[gi].trk[i]];
+            }
+            base += grp[gi].rows;
+        }
+    };
+    std::vector<Grp> grp, sgrp;
+    const int64_t grows = make_groups(TEHMM_GROWS_MAX, TEHMM_GMAX, grp);
+    // second grouping for the emission histograms (stats.cu): a merged row costs 256 bytes there
+    const int64_t srows = make_groups(TEHMM_SROWS_MAX, 8, sgrp);
+    const int SG = (int)sgrp.size();
     const int G = (int)grp.size();
     size_t o_gtab = o_end, o_gc = align_up(o_gtab + (size_t)grows * 32 * 4);
-    size_t o_gd = align_up(o_gc + (size_t)grows * 8), total = align_up(o_gd + (size_t)std::max(G, 1) * TEHMM_GDESC * 4);
+    size_t o_gd = align_up(o_gc + (size_t)grows * 8), o_sgd = align_up(o_gd + (size_t)std::max(G, 1) * TEHMM_GDESC * 4);
+    size_t total = align_up(o_sgd + (size_t)std::max(SG, 1) * TEHMM_GDESC * 4);
     std::vector<unsigned char> h(total, 0);
+    if (SG > 0) write_desc(sgrp, (int32_t *)&h[o_sgd]);
     if (G > 0) {
         float *gtab = (float *)&h[o_gtab];
         double *gc = (double *)&h[o_gc];
@@ -538,6 +566,7 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     m.G = normalize > 0.0 ? G : 0;      // a negative factor would flip the row maxima
     m.grows = (int)grows;
     m.gtab = (const float *)(d + o_gtab); m.gc = (const double *)(d + o_gc); m.gdesc = (const int32_t *)(d + o_gd);
+    m.SG = SG; m.srows = (int)srows; m.sgdesc = (const int32_t *)(d + o_sgd);
     c->has_model = true;
     return TEHMM_OK;
 }
@@ -670,7 +699,7 @@ static Scratch carve(const tehmm_ctx *c, int prec)
     s.part_a = o; o = align_up(o + nb * 8);
     s.bad = o; o = align_up(o + nb * 4);
     s.nbad = o; o = align_up(o + 4);
-    s.xi = o; o = align_up(o + nc * NP * NP * ts);
+    s.xi = o; o = align_up(o + std::max(nc * NP * NP * ts, tehmm_xi_tile_scratch_bytes(c->sms)));
     s.xdiag = o; o = align_up(o + nc * NP * ts);
     s.gamma0 = o; o = align_up(o + (size_t)c->b.nseq * NP * ts);
     s.tilemap = o; o = align_up(o + (size_t)c->b.ntiles * NP);
@@ -684,7 +713,7 @@ static Scratch carve(const tehmm_ctx *c, int prec)
         int64_t cap = (c->b.total + 255) / 256;     // at least 256 steps per CTA
         s.nparts = (int)std::max<int64_t>(1, std::min(want, cap));
     }
-    s.hist = o; o = align_up(o + (size_t)s.nparts * c->m.tab_rows * c->m.N * 8);
+    s.hist = o; o = align_up(o + (size_t)s.nparts * std::max(c->m.tab_rows, c->m.srows) * c->m.N * 8);
     s.total = o;
     return s;
 }
@@ -844,6 +873,11 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     void *xi = w + s.xi, *xd = w + s.xdiag, *g0 = w + s.gamma0;
     const int grid = scan_grid(c);
+    // Expected transition counts on the tensor-core path: posteriors from bwd_tile_kernel, then
+    // xi_tile_kernel (two dense products per 16 steps).  Needs the posterior lattice, un-renormalised.
+    const bool xi_tile = use_tile(c, prec, d_ratios) && (flags & TEHMM_BWD_TRANS) && (flags & TEHMM_BWD_POSTERIORS) &&
+                         !(flags & TEHMM_BWD_RENORM_EPS) && c->opt_xi_tile != 0;
+    if (xi_tile) flags &= ~TEHMM_BWD_TRANS;
     const bool tile = use_tile(c, prec, d_ratios) && !(flags & TEHMM_BWD_TRANS);
     const TehmmBatchDev &PB = tile ? c->bf : c->b;
     auto launch = [&](int mode) -> cudaError_t {
@@ -873,6 +907,12 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     }
     if (flags & TEHMM_BWD_MAP) { CU(tehmm_launch_map_reduce(st, PB, mp, d_map_score)); c->launches += 1; }
     if (flags & TEHMM_BWD_TRANS) { CU(tehmm_launch_trans_reduce(st, c->m, c->b, prec, xi, xd, g0, d_start_trans)); c->launches += 1; }
+    if (xi_tile) {
+        tk_begin(c, TK_XI);
+        CU(tehmm_launch_xi_tile(st, c->m, c->bf, (const float *)d_alpha, (const float *)d_post, (double *)xi, (float *)g0, d_start_trans, c->sms));
+        tk_end(c, TK_XI);
+        c->launches += 2;
+    }
     return TEHMM_OK;
 }
 

@@ -54,10 +54,15 @@ struct TehmmModelDev {
     const float *gtab;          // [grows][32]
     const double *gc;           // [grows]
     const int32_t *gdesc;       // [G][TEHMM_GDESC]: ntracks, first row, track[4], stride[4]
+    // Merged rows of the emission HISTOGRAMS (stats.cu, emission_stats_merged_kernel): the same
+    // kind of grouping under a smaller row budget (a histogram row is 256 bytes of shared memory).
+    int SG, srows;
+    const int32_t *sgdesc;      // [SG][TEHMM_GDESC]
 };
 #define TEHMM_GDESC 10
 #define TEHMM_GMAX 16           // groups
 #define TEHMM_GROWS_MAX 1200    // merged rows (x 128 bytes of shared memory)
+#define TEHMM_SROWS_MAX 704     // merged histogram rows (x 256 bytes of shared memory)
 
 struct TehmmBatchDev {
     const void *obs;

@@ -795,6 +795,160 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     }
 }
 
+// ------------------------------------------------------------------ transition counts (xi)
+// Expected transition counts of Baum-Welch (hmm.py:545-568 -> _hmm.pyx:62-117) as two
+// dense products per tile of 16 CONSECUTIVE time steps, from the lattices the E-step keeps
+// anyway (alpha from fwd_tile_kernel, the posteriors gamma from bwd_tile_kernel):
+//     pred_{t+1} = alpha_t A                       (16 x 32) (32 x 32)     -- tile_matmul
+//     W'_{t+1}   = gamma_{t+1} ./ pred_{t+1}
+//     xi[i][j]  += sum_t alpha_t[i] W'_{t+1}[j]    (32 x 16) (16 x 32)     -- contraction over time
+// and xi[i][j] * A[i][j] is the summed two-slice marginal: sum_i xi_t[i][j] A[i][j] =
+// gamma_{t+1}[j] exactly, whatever power-of-two scale alpha_t carries (it cancels), so no
+// recursion, no normaliser and no T x N x N tensor are needed -- every tile is independent.
+// The second product contracts over the tile's ROWS, so both operands are needed transposed
+// with respect to how lanes hold them: they take one trip through shared memory ([time][40]
+// floats: fragment reads hit 32 distinct banks).  Both products are 3xTF32.  Accumulators are
+// flushed into a per-warp float64 partial every XI_FLUSH tiles (tensor-core accumulation may
+// truncate; 48 accumulations bound the bias near 3e-6 relative, far below it in practice).
+#define XI_LDS 40
+#define XI_FLUSH 8
+
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+
+__global__ void __launch_bounds__(TILE_WARPS * 32, 1)
+xi_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ alpha,
+               const float *__restrict__ post, double *__restrict__ xi_part, float *__restrict__ gamma0)
+{
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    float *Xs = reinterpret_cast<float *>(tile_smem) + (size_t)warp * (2 * 16 * XI_LDS);
+    float *Ws = Xs + 16 * XI_LDS;
+    TransFrag A;
+    load_trans<false>(m, g, q, A);
+    float cacc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) cacc[mt][nt][0] = cacc[mt][nt][1] = cacc[mt][nt][2] = cacc[mt][nt][3] = 0.f;
+    const int64_t wid = (int64_t)blockIdx.x * TILE_WARPS + warp, nw = (int64_t)gridDim.x * TILE_WARPS;
+    double *mine = xi_part + wid * 1024;
+    for (int e = lane; e < 1024; e += 32) mine[e] = 0.0;
+    __syncwarp();
+    int pending = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int i0 = 16 * mt + g, j0 = 8 * nt + 2 * q;
+                mine[i0 * 32 + j0] += (double)cacc[mt][nt][0];
+                mine[i0 * 32 + j0 + 1] += (double)cacc[mt][nt][1];
+                mine[(i0 + 8) * 32 + j0] += (double)cacc[mt][nt][2];
+                mine[(i0 + 8) * 32 + j0 + 1] += (double)cacc[mt][nt][3];
+                cacc[mt][nt][0] = cacc[mt][nt][1] = cacc[mt][nt][2] = cacc[mt][nt][3] = 0.f;
+            }
+        pending = 0;
+    };
+
+    for (int64_t ci = wid; ci < b.nchunks; ci += nw) {
+        const TehmmChunk ch = b.chunks[ci];
+        if (ch.t0 == ch.s0 && ch.t1 > ch.t0) gamma0[(int64_t)ch.seq * 32 + lane] = post[ch.t0 * 32 + lane];
+        for (int64_t t = ch.t0; t < ch.t1; t += 16) {
+            // rows g and g+8 of the tile: alpha_t and gamma_{t+1}; a row without a successor in its
+            // sequence (or beyond the chunk) is zero and contributes nothing
+            float xv[2][8], gv[2][8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int64_t tr = t + g + 8 * r;
+                if (tr < ch.t1 && tr + 1 < ch.s1) {
+                    load_vec32(alpha + tr * 32 + 8 * q, xv[r]);
+                    load_vec32(post + (tr + 1) * 32 + 8 * q, gv[r]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { xv[r][i] = 0.f; gv[r][i] = 0.f; }
+                }
+            }
+            u64 xp[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) xp[c] = pk2(xv[0][c], xv[1][c]);
+            float acc[4][4];
+            tile_matmul(xp, A, acc);
+            __syncwarp();                              // the previous tile's fragment reads are done
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float wv[8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float p0 = acc[nt][2 * r], p1 = acc[nt][2 * r + 1];
+                    wv[2 * nt] = p0 > 0.f ? __fdividef(gv[r][2 * nt], p0) : 0.f;
+                    wv[2 * nt + 1] = p1 > 0.f ? __fdividef(gv[r][2 * nt + 1], p1) : 0.f;
+                }
+                float *xr = Xs + (g + 8 * r) * XI_LDS + 8 * q, *wr = Ws + (g + 8 * r) * XI_LDS + 8 * q;
+                *reinterpret_cast<float4 *>(xr) = make_float4(xv[r][0], xv[r][1], xv[r][2], xv[r][3]);
+                *reinterpret_cast<float4 *>(xr + 4) = make_float4(xv[r][4], xv[r][5], xv[r][6], xv[r][7]);
+                *reinterpret_cast<float4 *>(wr) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+                *reinterpret_cast<float4 *>(wr + 4) = make_float4(wv[4], wv[5], wv[6], wv[7]);
+            }
+            __syncwarp();
+            // xi += X^T W': M = from-state i, N = to-state j, K = time row of the tile
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const float *base = Xs + (8 * kt + q) * XI_LDS + 16 * mt + g;
+                    tf32_split(base[0], ah[mt][0], al[mt][0]);
+                    tf32_split(base[8], ah[mt][1], al[mt][1]);
+                    tf32_split(base[4 * XI_LDS], ah[mt][2], al[mt][2]);
+                    tf32_split(base[4 * XI_LDS + 8], ah[mt][3], al[mt][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float *base = Ws + (8 * kt + q) * XI_LDS + 8 * nt + g;
+                    tf32_split(base[0], bh[nt][0], bl[nt][0]);
+                    tf32_split(base[4 * XI_LDS], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        mma_tf32(cacc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh[nt][0], bh[nt][1]);
+                        mma_tf32(cacc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl[nt][0], bl[nt][1]);
+                        mma_tf32(cacc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh[nt][0], bh[nt][1]);
+                    }
+            }
+            if (++pending == XI_FLUSH) flush();
+        }
+    }
+    flush();
+}
+
+// start[i] += sum_seq gamma0[seq][i];  trans[i][j] += (1/N) A[i][j] sum_warps xi_part[w][i][j]
+// (the 1/N is the reference's beta[T-1] = log(1/N), _hmm.pyx:179).  Fixed order, float64.
+__global__ void xi_reduce_kernel(TehmmModelDev m, TehmmBatchDev b, const double *__restrict__ xi_part,
+                                 int nparts, const float *__restrict__ gamma0, double *__restrict__ start_trans)
+{
+    const int N = m.N;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < N) {
+        double acc = 0.0;
+        for (int64_t s = 0; s < b.nseq; ++s)
+            if (b.seq_off[s + 1] > b.seq_off[s]) acc += (double)gamma0[s * 32 + e];
+        start_trans[e] += acc;
+    }
+    if (e < N * N) {
+        const int i = e / N, j = e - i * N;
+        double acc = 0.0;
+        for (int p = 0; p < nparts; ++p) acc += xi_part[(int64_t)p * 1024 + i * 32 + j];
+        start_trans[N + e] += acc * m.lin_trans[(int64_t)i * 32 + j] / (double)N;
+    }
+}
+
 // ------------------------------------------------------------------ launchers
 static int tile_grid(const TehmmBatchDev &b, int sms)
 {
@@ -837,3 +991,18 @@ cudaError_t tehmm_launch_backward_tile(cudaStream_t st, const TehmmModelDev &m, 
 }
 
 int tehmm_tile_warps(void) { return TILE_WARPS; }
+
+// expected start / transition counts from the alpha and posterior lattices (fine partition b);
+// xi_part: sms * TILE_WARPS * 1024 doubles, gamma0: nseq * 32 floats.  2 launches.
+cudaError_t tehmm_launch_xi_tile(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                 const float *alpha, const float *post, double *xi_part, float *gamma0,
+                                 double *start_trans, int sms)
+{
+    const int smem = TILE_WARPS * 2 * 16 * XI_LDS * 4;
+    const int64_t need = (b.nchunks + TILE_WARPS - 1) / TILE_WARPS;       // a chunk at a time per warp
+    const int grid = (int)(need < 1 ? 1 : (need < sms ? need : sms));
+    xi_tile_kernel<<<grid, TILE_WARPS * 32, smem, st>>>(m, b, alpha, post, xi_part, gamma0);
+    xi_reduce_kernel<<<(m.N * m.N + 127) / 128, 128, 0, st>>>(m, b, xi_part, grid * TILE_WARPS, gamma0, start_trans);
+    return cudaGetLastError();
+}
+size_t tehmm_xi_tile_scratch_bytes(int sms) { return (size_t)sms * TILE_WARPS * 1024 * sizeof(double); }

@@ -285,3 +285,32 @@ def test_tile_and_warp_kernels_interoperate(oracle):
     for key, (lp, post) in res.items():
         assert_allclose(lp, base[0], rtol=1e-7)
         assert_allclose(post, base[1], rtol=TOL["f32"], atol=ATOL["f32"])
+
+
+def test_xi_tensor_core_kernel_vs_scan_and_f64():
+    """Expected transition counts: the tensor-core xi kernel (two dense products per 16 steps,
+    csrc/tile.cu) against the one-chunk-per-warp accumulation it replaces and against the
+    float64 verification mode, at a size where per-entry counts span six decades; and the
+    size-independent conservation law sum(xi) * N == (steps - sequences)  (1/N: _hmm.pyx:179)."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=8)
+    lens = [250_000, 17, 64_001, 5]
+    obs = [synth.sample_obs(m, T, seed=70 + i)[0] for i, T in enumerate(lens)]
+    eng = engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    ref = eng.estep(precision="f64")
+    eng.ctx.set_option("xi_tile", 0)
+    scan = eng.estep(precision="f32")
+    eng.ctx.set_option("xi_tile", 1)
+    before = eng.ctx.stat("launches")
+    tile = eng.estep(precision="f32")
+    assert eng.ctx.stat("launches") > before
+    N = 30
+    for st in (scan, tile):
+        assert_allclose(st["trans"], ref["trans"], rtol=1e-5, atol=2e-6)
+        assert_allclose(st["start"], ref["start"], rtol=1e-5, atol=2e-6)
+        assert st["trans"].sum() * N == pytest.approx(sum(lens) - len(lens), rel=1e-6)
+    assert_allclose(tile["obs"], scan["obs"], rtol=1e-5, atol=2e-6)
+    # zero transitions of the model stay exactly zero
+    assert np.all(tile["trans"][m["A"] == 0] == 0)

@@ -20,5 +20,5 @@ for _ in range(3):
     eng.estep(device_result=True)
 b.record(); torch.cuda.synchronize()
 print("E-step %.3f ms" % (a.elapsed_time(b) / 3))
-for k in ("emission", "forward", "backward", "emission_stats"):
+for k in ("emission", "forward", "backward", "xi", "emission_stats"):
     print("  %-16s %d us" % (k, ctx.stat("us_" + k)))
