@@ -858,10 +858,10 @@ xi_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ alpha
     for (int64_t ci = wid; ci < b.nchunks; ci += nw) {
         const TehmmChunk ch = b.chunks[ci];
         if (ch.t0 == ch.s0 && ch.t1 > ch.t0) gamma0[(int64_t)ch.seq * 32 + lane] = post[ch.t0 * 32 + lane];
-        for (int64_t t = ch.t0; t < ch.t1; t += 16) {
-            // rows g and g+8 of the tile: alpha_t and gamma_{t+1}; a row without a successor in its
-            // sequence (or beyond the chunk) is zero and contributes nothing
-            float xv[2][8], gv[2][8];
+        // rows g and g+8 of a tile: alpha_t and gamma_{t+1}; a row without a successor in its
+        // sequence (or beyond the chunk) is zero and contributes nothing.  The next tile's rows
+        // are in flight while this one is multiplied.
+        auto load_tile = [&](int64_t t, float (&xv)[2][8], float (&gv)[2][8]) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const int64_t tr = t + g + 8 * r;
@@ -873,6 +873,16 @@ xi_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ alpha
                     for (int i = 0; i < 8; ++i) { xv[r][i] = 0.f; gv[r][i] = 0.f; }
                 }
             }
+        };
+        float nx[2][8], ng[2][8];
+        load_tile(ch.t0, nx, ng);
+        for (int64_t t = ch.t0; t < ch.t1; t += 16) {
+            float xv[2][8], gv[2][8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { xv[r][i] = nx[r][i]; gv[r][i] = ng[r][i]; }
+            load_tile(t + 16, nx, ng);                 // beyond the chunk: zeros, no access
             u64 xp[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) xp[c] = pk2(xv[0][c], xv[1][c]);
