@@ -168,6 +168,16 @@ int64_t tehmm_scratch_bytes(tehmm_ctx *ctx, int prec);
  * in the element type `prec`.  d_ratios (DEVICE, float64, total) or NULL.     */
 int tehmm_run_emission(tehmm_ctx *ctx, int prec, const double *d_ratios,
                        void *d_elog, void *d_blin, double *d_rowmax);
+/* The same for the rows [row0, row1) of the batch only, so that a caller streaming the
+ * observations onto the device can run the rows that have arrived.  Pieces must come in
+ * increasing order, the first starting at row 0 and the last ending at the batch's
+ * total (the fix-up of _emission.pyx:59,73-80 runs then); row0 must be a multiple of
+ * 32.  stream: the cudaStream_t to enqueue on, or UINT64_MAX for the context's.
+ * Only when tehmm_emission_rows_supported() returns 1 (fp32, N <= 32, merged tables). */
+int tehmm_emission_rows_supported(tehmm_ctx *ctx, int prec);
+int tehmm_run_emission_rows(tehmm_ctx *ctx, int prec, const double *d_ratios, void *d_elog,
+                            void *d_blin, double *d_rowmax, int64_t row0, int64_t row1,
+                            uint64_t stream);
 /* Reference-layout frame: d_frame[t][j] float64 = what fastAllLogProbs writes */
 int tehmm_run_emission_f64(tehmm_ctx *ctx, const double *d_ratios, double *d_frame);
 

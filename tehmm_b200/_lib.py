@@ -52,6 +52,8 @@ SIGNATURES = {
     "tehmm_lattice_stride": (_c_int, [_c_void]),
     "tehmm_scratch_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_emission": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_emission_rows_supported": (_c_int, [_c_void, _c_int]),
+    "tehmm_run_emission_rows": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_i64, _c_i64, _c_u64]),
     "tehmm_run_emission_f64": (_c_int, [_c_void, _c_void, _c_void]),
     "tehmm_run_forward": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_run_backward": (_c_int, [_c_void, _c_int, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),

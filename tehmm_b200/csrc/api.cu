@@ -18,7 +18,8 @@ void tehmm_launch_strict_lneta(cudaStream_t, int64_t, int, const double *, const
 void tehmm_launch_strict_accumulate(cudaStream_t, const void *, int, int64_t, int, double *, int, int, const double *, const double *);
 void tehmm_launch_strict_counts(cudaStream_t, const void *, int, int, int64_t, int64_t, int, double *, int, int, const double *);
 size_t tehmm_emission_table_budget(int K);
-int tehmm_launch_emission(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const double *, void *, void *, double *, double *, int *, int, cudaError_t *);
+int tehmm_launch_emission(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const double *, void *, void *, double *, double *, int *, int, cudaError_t *, int64_t, int64_t);
+bool tehmm_emission_rows_ok(const TehmmModelDev &, int, const double *);
 cudaError_t tehmm_launch_forward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, const double *, void *, void *, void *, double *, const int *, int, int);
 cudaError_t tehmm_launch_verify(cudaStream_t, const TehmmBatchDev &, int, int, void *, const void *, double, int, int, int *, int *, double *);
 cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, int, int, const void *, const double *, const double *, double *);
@@ -101,6 +102,7 @@ struct tehmm_ctx {
     bool has_batch = false;
     TehmmBatchDev b{};            // coarse partition: one chunk per warp (forward.cu, backward.cu, viterbi.cu)
     TehmmBatchDev bf{};           // fine partition: sixteen chunks per warp (tile.cu)
+    std::vector<int64_t> batch_key;   // offsets, address and options of the last tehmm_set_batch
     void *batch_blob = nullptr;
     size_t batch_blob_bytes = 0;      // capacity (grow-only: decode calls come back with similar batches)
     int *d_seq_flag = nullptr;
@@ -583,6 +585,17 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
     CU(cudaSetDevice(c->device));
     const int64_t total = h_offsets[nseq];
     if (total <= 0) return fail(TEHMM_EINVAL, "empty batch");
+    {   // the same batch shape at the same address again (a stream of decode calls): keep the partition
+        std::vector<int64_t> key(h_offsets, h_offsets + nseq + 1);
+        key.push_back((int64_t)(uintptr_t)d_obs); key.push_back(obs_bytes);
+        key.push_back(c->opt_chunk_tiles); key.push_back(c->opt_fine_len); key.push_back(c->opt_warmup);
+        if (c->has_batch && key == c->batch_key) {
+            if (c->opt_warmup <= 0 && c->b.warmup != 64) c->b.warmup = c->bf.warmup = 64;   // forget an adapted warm-up
+            return TEHMM_OK;
+        }
+        c->batch_key.swap(key);
+        c->has_batch = false;
+    }
     // time partition: tiles of TEHMM_TILE steps, chunks of `tpc` tiles
     int64_t tpc = c->opt_chunk_tiles;
     if (tpc <= 0) {
@@ -769,8 +782,28 @@ int tehmm_run_emission(tehmm_ctx *c, int prec, const double *d_ratios, void *d_e
     if (!d_rowmax || (!d_elog && !d_blin)) return fail(TEHMM_EINVAL, "need d_rowmax and at least one of d_elog / d_blin");
     cudaError_t e;
     tk_begin(c, TK_EMISSION);
-    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, d_elog, d_blin, d_rowmax, nullptr, c->d_seq_flag, c->sms, &e);
+    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, d_elog, d_blin, d_rowmax, nullptr, c->d_seq_flag, c->sms, &e, 0, c->b.total);
     tk_end(c, TK_EMISSION);
+    if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
+    c->launches += n;
+    return TEHMM_OK;
+}
+
+int tehmm_emission_rows_supported(tehmm_ctx *c, int prec)
+{
+    return c && c->has_model && tehmm_emission_rows_ok(c->m, prec, nullptr) ? 1 : 0;
+}
+
+int tehmm_run_emission_rows(tehmm_ctx *c, int prec, const double *d_ratios, void *d_elog, void *d_blin,
+                            double *d_rowmax, int64_t row0, int64_t row1, uint64_t stream)
+{
+    RUN_PROLOGUE();
+    if (!d_rowmax || (!d_elog && !d_blin)) return fail(TEHMM_EINVAL, "need d_rowmax and at least one of d_elog / d_blin");
+    if (row0 < 0 || row1 > c->b.total || row0 >= row1 || (row0 & 31)) return fail(TEHMM_EINVAL, "bad row range [%lld,%lld) (row0 must be a multiple of 32)", (long long)row0, (long long)row1);
+    if (!tehmm_emission_rows_ok(c->m, prec, d_ratios)) return fail(TEHMM_ESTATE, "this model / precision cannot run the emission in pieces (tehmm_emission_rows_supported)");
+    if (stream != UINT64_MAX) st = (cudaStream_t)(uintptr_t)stream;
+    cudaError_t e;
+    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, d_elog, d_blin, d_rowmax, nullptr, c->d_seq_flag, c->sms, &e, row0, row1);
     if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
     c->launches += n;
     return TEHMM_OK;
@@ -782,7 +815,7 @@ int tehmm_run_emission_f64(tehmm_ctx *c, const double *d_ratios, double *d_frame
     RUN_PROLOGUE();
     if (!d_frame) return fail(TEHMM_EINVAL, "d_frame is NULL");
     cudaError_t e;
-    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, nullptr, nullptr, nullptr, d_frame, c->d_seq_flag, c->sms, &e);
+    int n = tehmm_launch_emission(st, c->m, c->b, prec, d_ratios, nullptr, nullptr, nullptr, d_frame, c->d_seq_flag, c->sms, &e, 0, c->b.total);
     if (n < 0) return fail(TEHMM_ECUDA, "emission launch failed: %s", cudaGetErrorString(e));
     c->launches += n;
     return TEHMM_OK;

@@ -411,8 +411,11 @@ __global__ void __launch_bounds__(EM4_WARPS * 32, 1)
 emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                         const double *__restrict__ ratios, float *__restrict__ elog,
                         float *__restrict__ blin, double *__restrict__ rowmax,
-                        int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq)
+                        int *__restrict__ seq_flag, const int64_t *__restrict__ seq_off, int64_t nseq,
+                        int64_t row0)
 {
+    // rows [row0, total) of the batch (row0 a multiple of EM4_ROWS): a caller that streams the
+    // observations in can run the rows that have arrived (tehmm_run_emission_rows)
     extern __shared__ __align__(16) unsigned char em_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = m.K, N = m.N;
@@ -439,7 +442,7 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
     for (int i = 0; i < 4; ++i) pm[i] = (4 * c + i < N) ? -INFINITY : 0.f;
 
     const int64_t nblocks = (total + EM4_ROWS - 1) / EM4_ROWS;
-    for (int64_t blk = (int64_t)blockIdx.x * EM4_WARPS + warp; blk < nblocks;
+    for (int64_t blk = row0 / EM4_ROWS + (int64_t)blockIdx.x * EM4_WARPS + warp; blk < nblocks;
          blk += (int64_t)gridDim.x * EM4_WARPS) {
         const int64_t tb = blk * EM4_ROWS;
         const int rows = (int)min((int64_t)EM4_ROWS, total - tb);
@@ -547,26 +550,26 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
 template <typename OBS, int GT, bool RATIO>
 static cudaError_t launch_em4_3(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                 const double *ratios, float *elog, float *blin, double *rowmax,
-                                int *seq_flag, int sms)
+                                int *seq_flag, int sms, int64_t row0, int64_t row1)
 {
     const size_t smem = em4_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(emission_merged4_kernel<OBS, GT, RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t need = ((b.total + EM4_ROWS - 1) / EM4_ROWS + EM4_WARPS - 1) / EM4_WARPS;
+    int64_t need = ((row1 - row0 + EM4_ROWS - 1) / EM4_ROWS + EM4_WARPS - 1) / EM4_WARPS;
     if (need < 1) need = 1;
     const int grid = (int)(need < sms ? need : sms);
-    emission_merged4_kernel<OBS, GT, RATIO><<<grid, EM4_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
-                                                                                rowmax, seq_flag, b.seq_off, b.nseq);
+    emission_merged4_kernel<OBS, GT, RATIO><<<grid, EM4_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, row1, ratios, elog, blin,
+                                                                                rowmax, seq_flag, b.seq_off, b.nseq, row0);
     return cudaGetLastError();
 }
 
 template <typename OBS>
 static cudaError_t launch_em4(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                               const double *ratios, float *elog, float *blin, double *rowmax,
-                              int *seq_flag, int sms)
+                              int *seq_flag, int sms, int64_t row0, int64_t row1)
 {
-#define EM4_GO(GT) (ratios ? launch_em4_3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms) \
-                           : launch_em4_3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms))
+#define EM4_GO(GT) (ratios ? launch_em4_3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1) \
+                           : launch_em4_3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1))
     switch (m.G) {
     case 1: return EM4_GO(1);
     case 2: return EM4_GO(2);
@@ -663,20 +666,32 @@ static cudaError_t launch_em_obs(cudaStream_t st, const TehmmModelDev &m, const 
 }
 
 // returns number of kernels launched, or -1 with *err set
+// whether rows of the batch can be run in pieces (tehmm_run_emission_rows): the four-rows-per-pass kernel only
+bool tehmm_emission_rows_ok(const TehmmModelDev &m, int prec, const double *ratios)
+{
+    (void)ratios;
+    return prec == TEHMM_F32 && m.G > 0 && m.G <= 8 && m.LD == 32 && em4_smem_bytes(m) <= 227 * 1024;
+}
+
+// rows [row0, row1) of the batch; pieces must come in increasing order, the first one starting at
+// row 0 (clears the per-sequence flags) and the last one ending at b.total (applies the
+// _emission.pyx:59,73-80 fix-up).  Anything but [0, total) needs tehmm_emission_rows_ok().
 int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b, int prec,
                           const double *ratios, void *elog, void *blin, double *rowmax,
-                          double *frame, int *seq_flag, int sms, cudaError_t *err)
+                          double *frame, int *seq_flag, int sms, cudaError_t *err, int64_t row0, int64_t row1)
 {
-    cudaError_t e = cudaMemsetAsync(seq_flag, 0, sizeof(int) * (size_t)b.nseq, st);
+    cudaError_t e = cudaSuccess;
+    int launched = 0;
+    if (row0 == 0) e = cudaMemsetAsync(seq_flag, 0, sizeof(int) * (size_t)b.nseq, st);
     if (e == cudaSuccess) {
         if (frame) e = launch_em_obs<float, 1>(st, m, b, ratios, nullptr, nullptr, nullptr, frame, seq_flag, sms);
         else if (prec == TEHMM_F32 && m.G > 0 && emg_smem_bytes(m) <= 227 * 1024) {
             // out-of-range symbols in the slow branch index the dense table: obs must be < S there too,
             // exactly the generic kernel's contract
             if (m.LD == 32 && m.G <= 8 && em4_smem_bytes(m) <= 227 * 1024) {
-                if (b.obs_bytes == 1) e = launch_em4<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
-                else if (b.obs_bytes == 2) e = launch_em4<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
-                else e = launch_em4<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
+                if (b.obs_bytes == 1) e = launch_em4<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);
+                else if (b.obs_bytes == 2) e = launch_em4<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);
+                else e = launch_em4<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);
             }
             else if (b.obs_bytes == 1) e = launch_emg<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
             else if (b.obs_bytes == 2) e = launch_emg<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms);
@@ -685,7 +700,9 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
         else if (prec == TEHMM_F32) e = launch_em_obs<float, 0>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, nullptr, seq_flag, sms);
         else e = launch_em_obs<double, 0>(st, m, b, ratios, (double *)elog, (double *)blin, rowmax, nullptr, seq_flag, sms);
     }
-    if (e == cudaSuccess) {
+    launched = 1;
+    if (e == cudaSuccess && row1 == b.total) {
+        launched = 2;
         int warps = 4;
         int grid = (int)((b.nseq + warps - 1) / warps);
         if (frame || prec == TEHMM_F32)
@@ -695,5 +712,5 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
         e = cudaGetLastError();
     }
     *err = e;
-    return e == cudaSuccess ? 2 : -1;
+    return e == cudaSuccess ? launched : -1;
 }

@@ -135,6 +135,8 @@ struct HostPipe {
     unsigned char *ring[NRING] = {};
     cudaEvent_t ring_ev[NRING] = {};
     bool ring_used[NRING] = {};
+    cudaStream_t copy_stream = nullptr;     // host -> device copies, ahead of the compute stream
+    std::vector<cudaEvent_t> slice_ev;      // one per slice of a call, reused
     unsigned char *pin_out = nullptr;       // states + the per-sequence scalars
     size_t pin_out_bytes = 0;
     Pool *pool = nullptr;
@@ -149,6 +151,8 @@ struct HostPipe {
             if (ring_ev[i]) cudaEventDestroy(ring_ev[i]);
         }
         if (pin_out) cudaFreeHost(pin_out);
+        for (cudaEvent_t e : slice_ev) cudaEventDestroy(e);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         delete pool;
     }
 };
@@ -311,21 +315,34 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         if (cudaPointerGetAttributes(&attr, h_obs_ptrs[0]) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
         else { cudaGetLastError(); pinned = false; }
     }
-    if (pinned) {
-        HCU(cudaMemcpyAsync(A + o_obs, h_obs_ptrs[0], obs_bytes_total, cudaMemcpyHostToDevice, st));
-    } else {
-        // pageable: worker threads fill a pinned slice while the previous one is on the wire
-        const int nth = p->pool->size();
-        int64_t slot = 0;
-        size_t si = 0;                                   // first segment that reaches into the slice
-        for (size_t off = 0; off < obs_bytes_total; off += SLICE, ++slot) {
+    // The copy runs on its own stream in slices of whole rows; the emission kernel of a slice is
+    // enqueued on the compute stream behind that slice's event, so it overlaps the transfer of the
+    // next one (the emission is the only stage that can start before the whole batch has arrived).
+    if (!p->copy_stream) HCU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    double *d_lp = (double *)(A + o_lp), *d_sc = d_lp + nseq;
+    uint8_t *d_states = (uint8_t *)(A + o_states);
+    const bool viterbi = algorithm == TEHMM_DECODE_VITERBI;
+    void *em_log = viterbi ? (void *)(A + o_la) : nullptr, *em_lin = viterbi ? nullptr : (void *)(A + o_la);
+    const bool piecewise = tehmm_emission_rows_supported(c, prec) == 1;
+    const size_t row_bytes = (size_t)K * obs_bytes;
+    int64_t slice_rows = (int64_t)(SLICE / row_bytes) & ~(int64_t)31;
+    if (slice_rows < 32) slice_rows = 32;
+    const int nth = p->pool->size();
+    size_t si = 0;                                       // first segment that reaches into the slice
+    int64_t slot = 0;
+    for (int64_t r0 = 0; r0 < total; r0 += slice_rows, ++slot) {
+        const int64_t r1 = std::min(total, r0 + slice_rows);
+        const size_t off = (size_t)r0 * row_bytes, n = (size_t)(r1 - r0) * row_bytes;
+        if (pinned) {
+            HCU(cudaMemcpyAsync(A + o_obs + off, (const unsigned char *)h_obs_ptrs[0] + off, n, cudaMemcpyHostToDevice, p->copy_stream));
+        } else {
+            // pageable: worker threads fill a pinned slice while the previous one is on the wire
             const int r = (int)(slot % NRING);
             if (!p->ring[r]) {
                 HCU(cudaMallocHost((void **)&p->ring[r], SLICE));
                 HCU(cudaEventCreateWithFlags(&p->ring_ev[r], cudaEventDisableTiming));
             }
             if (p->ring_used[r]) HCU(cudaEventSynchronize(p->ring_ev[r]));
-            const size_t n = std::min(SLICE, obs_bytes_total - off);
             while (si + 1 < segs.size() && segs[si].off + segs[si].n <= off) ++si;
             unsigned char *dst = p->ring[r];
             const size_t per = ((n + nth - 1) / nth + 63) & ~(size_t)63;
@@ -342,22 +359,27 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
                     a += m;
                 }
             });
-            HCU(cudaMemcpyAsync(A + o_obs + off, dst, n, cudaMemcpyHostToDevice, st));
-            HCU(cudaEventRecord(p->ring_ev[r], st));
+            HCU(cudaMemcpyAsync(A + o_obs + off, dst, n, cudaMemcpyHostToDevice, p->copy_stream));
+            HCU(cudaEventRecord(p->ring_ev[r], p->copy_stream));
             p->ring_used[r] = true;
         }
+        if ((size_t)slot >= p->slice_ev.size()) {
+            cudaEvent_t ev;
+            HCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            p->slice_ev.push_back(ev);
+        }
+        HCU(cudaEventRecord(p->slice_ev[slot], p->copy_stream));
+        HCU(cudaStreamWaitEvent(st, p->slice_ev[slot], 0));
+        if (piecewise) HOK(tehmm_run_emission_rows(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax), r0, r1, UINT64_MAX));
     }
     p->h2d_bytes = (int64_t)obs_bytes_total;
-    tr.mark("h2d", true);
+    tr.mark("h2d+emission", true);
 
     // ---- the trellis
-    double *d_lp = (double *)(A + o_lp), *d_sc = d_lp + nseq;
-    uint8_t *d_states = (uint8_t *)(A + o_states);
-    if (algorithm == TEHMM_DECODE_VITERBI) {
-        HOK(tehmm_run_emission(c, prec, nullptr, A + o_la, nullptr, (double *)(A + o_rowmax)));
+    if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
+    if (viterbi) {
         HOK(tehmm_run_viterbi(c, prec, A + o_la, nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
     } else {
-        HOK(tehmm_run_emission(c, prec, nullptr, nullptr, A + o_la, (double *)(A + o_rowmax)));
         HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
         HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_la, A + o_lb, nullptr, nullptr,
                                d_states, d_sc, nullptr, A + o_scratch));
@@ -385,7 +407,6 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
         HCU(cudaEventRecord(evs[i], st));
     }
-    const int nth = p->pool->size();
     int rc = TEHMM_OK;
     for (int i = 0; i < nsl; ++i) {
         const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
