@@ -1011,6 +1011,8 @@ cudaError_t tehmm_launch_xi_tile(cudaStream_t st, const TehmmModelDev &m, const 
     const int smem = TILE_WARPS * 2 * 16 * XI_LDS * 4;
     const int64_t need = (b.nchunks + TILE_WARPS - 1) / TILE_WARPS;       // a chunk at a time per warp
     const int grid = (int)(need < 1 ? 1 : (need < sms ? need : sms));
+    cudaError_t e = cudaFuncSetAttribute(xi_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
     xi_tile_kernel<<<grid, TILE_WARPS * 32, smem, st>>>(m, b, alpha, post, xi_part, gamma0);
     xi_reduce_kernel<<<(m.N * m.N + 127) / 128, 128, 0, st>>>(m, b, xi_part, grid * TILE_WARPS, gamma0, start_trans);
     return cudaGetLastError();
