@@ -1,7 +1,8 @@
 // Chunked parallel-in-time Viterbi with on-device parallel traceback
 // (hmm.py:668-676 -> _hmm.pyx:201-259).
 //
-// DP (viterbi_kernel): one warp per chunk, lane j owns column j of log A in
+// DP (viterbi_kernel; viterbi_lean_kernel for the fp32 production case, see there):
+// one warp per chunk, lane j owns column j of log A in
 // registers, delta is kept max-normalised (max = 0) and broadcast through
 // shared memory.  The kernel is issue-bound, so it computes VALUES only:
 //     delta_t[j] = max_i(delta_{t-1}[i] + logA[i][j]) + e_t[j]
@@ -165,51 +166,6 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
             for (int s = 0; s < NS; ++s) start_vec[ci * NP + lane + 32 * s] = d[s];
         }
 
-        if constexpr (sizeof(T) == 4 && NS == 1 && !RATIO) {
-            // Lean steady state (the kernel is issue bound): running pointers, the next
-            // VIT_U rows of e in flight, and -- every delta and log-probability being <= 0 --
-            // the row maximum as the unsigned MINIMUM of the bit patterns (one REDUX, no key
-            // transform; +0.0 = 0 is the smallest pattern, -inf the largest).
-            const float *ep = reinterpret_cast<const float *>(ee) + row * Nu + jc[0];
-            float *lp = reinterpret_cast<float *>(ll) + row * Nu + (unsigned)lane;
-            float dd = (float)d[0];
-            auto lean_step = [&](float et) {
-                ds[buf][lane] = dd;
-                __syncwarp();
-                float y[1];
-                matvec_maxval<1>(reinterpret_cast<const float *>(ds[buf]), A, y);
-                buf ^= 1;
-                const float v = y[0] + (own[0] ? et : -INFINITY);
-                const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
-                dd = v - (M > -INFINITY ? M : 0.f);
-                *lp = dd;                       // padding columns carry -inf (LD = 32: every lane has one)
-                lp += Nu;
-            };
-            float en[VIT_U];
-            if (row + VIT_U <= row1) {
-#pragma unroll
-                for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * Nu];
-            }
-            while (row + 2 * VIT_U <= row1) {
-                float ec[VIT_U];
-#pragma unroll
-                for (int u = 0; u < VIT_U; ++u) ec[u] = en[u];
-                ep += VIT_U * Nu;
-#pragma unroll
-                for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * Nu];
-#pragma unroll
-                for (int u = 0; u < VIT_U; ++u) lean_step(ec[u]);
-                row += VIT_U;
-            }
-            if (row + VIT_U <= row1) {
-#pragma unroll
-                for (int u = 0; u < VIT_U; ++u) lean_step(en[u]);
-                ep += VIT_U * Nu;
-                row += VIT_U;
-            }
-            for (; row < row1; ++row) { lean_step(*ep); ep += Nu; }
-            d[0] = (T)dd;
-        } else {
         T en[VIT_U][NS];
         if (row + VIT_U <= row1) {
 #pragma unroll
@@ -244,7 +200,6 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
             load_e(row, et);
             step(row, et);
             store_d(row);
-        }
         }
 #pragma unroll
         for (int s = 0; s < NS; ++s) end_vec[ci * NP + lane + 32 * s] = d[s];
