@@ -255,6 +255,18 @@ int tehmm_path_score(tehmm_ctx *ctx, const uint8_t *d_states, const double *d_ra
                      const double *d_ratios_dp, int64_t lo, int64_t hi, double *d_logprob,
                      void *d_scratch);
 
+/* Decode output path: the per-observation BED writer of teHmmEval.py:238-262
+ * (statesToBed, bedFile part): for observation i one line
+ *   chrom \t curStart \t curStart + len_i \t name(states[i]) \n
+ * with curStart = start + sum_{j<i} len_j (+ mask_off[curStart - start] when a
+ * mask is given), len_i = seg_len[i] or 1 (seg_len NULL), name = names[state] or
+ * the decimal state index (nnames 0).  Lines are NOT merged, as in the reference
+ * (teHmmEval.py:241-243).  Written to the file descriptor fd at its current
+ * offset (flush the Python file object first).  Host only, no GPU needed.     */
+int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t *states,
+                        int64_t n, const int64_t *seg_len, const int32_t *mask_off,
+                        int64_t mask_n, const char *const *names, int nnames);
+
 /* widen / convert on the device before a D2H copy */
 int tehmm_widen_states(tehmm_ctx *ctx, const uint8_t *d_in, int64_t *d_out, int64_t n);
 int tehmm_convert_lattice(tehmm_ctx *ctx, int prec, const void *d_in, double *d_out, int64_t n);

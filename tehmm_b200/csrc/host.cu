@@ -26,6 +26,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <vector>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -437,6 +438,119 @@ int64_t tehmm_decode_host_bytes(tehmm_ctx *c, int which)
     auto it = g_pipes.find(c);
     if (it == g_pipes.end()) return 0;
     return which == 0 ? it->second->h2d_bytes : it->second->d2h_bytes;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Decode output path: the per-observation BED writer of
+// teHmmEval.py:238-262 (statesToBed, bedFile part).  Once the trellis takes milliseconds the
+// reference's Python loop -- one "%s\t%d\t%d\t%s\n" per observation, 12 M lines for a genome --
+// is what a user waits for.  Same lines, same order (contiguous equal states are NOT merged,
+// teHmmEval.py:241-243): interval starts are a prefix sum of the segment lengths (plus the mask's
+// running offset), blocks of lines are formatted by a few threads and written in order.
+static int fmt_i64(char *p, int64_t v)
+{
+    static const char D2[] = "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+                             "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+    char tmp[24];
+    int n = 24;
+    uint64_t u = v < 0 ? (uint64_t)(-(v + 1)) + 1u : (uint64_t)v;
+    while (u >= 100) { const unsigned r = (unsigned)(u % 100); u /= 100; tmp[--n] = D2[2 * r + 1]; tmp[--n] = D2[2 * r]; }
+    if (u >= 10) { tmp[--n] = D2[2 * u + 1]; tmp[--n] = D2[2 * u]; }
+    else tmp[--n] = (char)('0' + u);
+    int k = 0;
+    if (v < 0) p[k++] = '-';
+    memcpy(p + k, tmp + n, (size_t)(24 - n));
+    return k + 24 - n;
+}
+
+int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t *states, int64_t n,
+                        const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n,
+                        const char *const *names, int nnames)
+{
+    if (fd < 0 || !chrom || (!states && n > 0) || n < 0) return herr(TEHMM_EINVAL, "bad argument");
+    if (n == 0) return TEHMM_OK;
+    const size_t clen = strlen(chrom);
+    std::vector<size_t> nlen((size_t)std::max(nnames, 0));
+    size_t maxname = 21;
+    for (int i = 0; i < nnames; ++i) {
+        if (!names || !names[i]) return herr(TEHMM_EINVAL, "names[%d] is NULL", i);
+        nlen[i] = strlen(names[i]);
+        maxname = std::max(maxname, nlen[i]);
+    }
+    const int64_t BLOCK = 1 << 17;
+    const int64_t nblocks = (n + BLOCK - 1) / BLOCK;
+    // start of every block: prefix sum of the segment lengths (1 per observation without segments)
+    std::vector<int64_t> bstart((size_t)nblocks + 1, 0);
+    if (seg_len) {
+        for (int64_t b = 0; b < nblocks; ++b) {
+            int64_t acc = 0;
+            const int64_t e = std::min(n, (b + 1) * BLOCK);
+            for (int64_t i = b * BLOCK; i < e; ++i) acc += seg_len[i];
+            bstart[b + 1] = bstart[b] + acc;
+        }
+    } else {
+        for (int64_t b = 0; b <= nblocks; ++b) bstart[b] = std::min(n, b * BLOCK);
+    }
+    const size_t line_max = clen + maxname + 2 * 21 + 4;
+    int nth = host_threads();
+    if ((int64_t)nth > nblocks) nth = (int)nblocks;
+    if (nth > 8) nth = 8;
+    // rounds of nth blocks: formatted in parallel, written in order
+    std::vector<std::vector<char>> buf((size_t)nth);
+    std::vector<size_t> used((size_t)nth, 0);
+    std::atomic<int> bad_state(0);
+    for (int64_t b0 = 0; b0 < nblocks; b0 += nth) {
+        const int cnt = (int)std::min<int64_t>(nth, nblocks - b0);
+        auto work = [&](int w) {
+            const int64_t b = b0 + w, lo = b * BLOCK, hi = std::min(n, lo + BLOCK);
+            std::vector<char> &out = buf[w];
+            if (out.size() < (size_t)(hi - lo) * line_max) out.resize((size_t)(hi - lo) * line_max);
+            char *p = out.data();
+            int64_t dist = bstart[b];
+            char endtxt[24];                  // without a mask an interval starts where the last one ended:
+            int endlen = 0;                   // its text is reused
+            for (int64_t i = lo; i < hi; ++i) {
+                int64_t cur = start + dist;
+                const int64_t len = seg_len ? seg_len[i] : 1;
+                dist += len;
+                if (mask_off) {
+                    const int64_t rel = cur - start;
+                    if (rel >= 0 && rel < mask_n) cur += mask_off[rel];
+                }
+                memcpy(p, chrom, clen); p += clen;
+                *p++ = '\t';
+                if (endlen && !mask_off) { memcpy(p, endtxt, (size_t)endlen); p += endlen; }
+                else p += fmt_i64(p, cur);
+                *p++ = '\t';
+                endlen = fmt_i64(endtxt, cur + len);
+                memcpy(p, endtxt, (size_t)endlen); p += endlen;
+                *p++ = '\t';
+                const int64_t st = states[i];
+                if (nnames > 0) {
+                    if (st < 0 || st >= nnames) { bad_state.store(1); p += fmt_i64(p, st); }
+                    else { memcpy(p, names[st], nlen[st]); p += nlen[st]; }
+                } else p += fmt_i64(p, st);
+                *p++ = '\n';
+            }
+            used[w] = (size_t)(p - out.data());
+        };
+        std::vector<std::thread> th;
+        for (int w = 1; w < cnt; ++w) th.emplace_back(work, w);
+        work(0);
+        for (auto &t : th) t.join();
+        for (int w = 0; w < cnt; ++w) {
+            const char *q = buf[w].data();
+            size_t left = used[w];
+            while (left) {
+                const ssize_t k = write(fd, q, left);
+                if (k <= 0) return herr(TEHMM_ESTATE, "write failed");
+                q += k; left -= (size_t)k;
+            }
+        }
+    }
+    if (bad_state.load()) return herr(TEHMM_EINVAL, "a state index has no name");
+    return TEHMM_OK;
 }
 
 }   // extern "C"
