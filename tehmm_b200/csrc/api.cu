@@ -33,7 +33,7 @@ cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const Tehm
 cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, double *, double *, int, int);
 size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
 cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
-cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int);
+cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int, int64_t);
 cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int);
 int tehmm_tile_warps(void);
 cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
@@ -108,6 +108,7 @@ struct tehmm_ctx {
     int *d_seq_flag = nullptr;
     int64_t seq_flag_n = 0;
     int64_t max_tiles_per_chunk = 1;
+    int64_t fine_len = 0;         // steps per chunk of the fine partition
 };
 
 extern "C" {
@@ -671,6 +672,7 @@ int tehmm_set_batch(tehmm_ctx *c, const void *d_obs, int obs_bytes, int64_t nseq
     c->bf.seq_chunk0 = (const int64_t *)(d + o_fsc);
     c->bf.chunks = (const TehmmChunk *)(d + o_fch);
     c->max_tiles_per_chunk = tpc;
+    c->fine_len = Lf;
     c->has_batch = true;
     return TEHMM_OK;
 }
@@ -863,7 +865,7 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     auto launch = [&](int mode) -> cudaError_t {
         if (tile) {
             c->stat_tile_passes += 1;
-            return tehmm_launch_forward_tile(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha, (float *)sv, (float *)ev, cs, bad, mode, c->sms);
+            return tehmm_launch_forward_tile(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha, (float *)sv, (float *)ev, cs, bad, mode, c->sms, c->fine_len);
         }
         return tehmm_launch_forward(st, c->m, PB, prec, d_blin, d_rowmax, d_ratios, d_alpha, sv, ev, cs, bad, mode, grid);
     };

@@ -53,8 +53,13 @@
 // Algorithmic HBM bytes per step: forward 4N read + 4N written, backward 8N read
 // (+4N posteriors, +1 MAP state).
 #include "scan.cuh"
+#include <cuda.h>
+#include <cstring>
 
 #define TILE_WARPS 8
+#ifndef TEHMM_TILE_TENSOR
+#define TEHMM_TILE_TENSOR 1     // 3-D tensor-map block loads where the batch is one regularly chunked sequence
+#endif
 // Measured on B200 (10 M x 30, forward with / without the alpha store, ms):
 //   per-lane LDGSTS + STG.128 0.887 / 0.525;  TB=2,NBL=4,NBS=2 0.845 / 0.738;
 //   TB=4,NBL=2,NBS=1 0.668 / 0.542  -- small bulk copies are TMA issue bound.
@@ -257,6 +262,7 @@ __device__ __forceinline__ void store_row8(float *p, bool on, const float (&v)[8
 #endif
 #define TMA_RS (TB * 128 + 16)        // bytes between tile rows of a block (pad: conflict-free LDS.128)
 #define TMA_BUF (16 * TMA_RS)         // bytes of one block buffer
+#define FWD_WARP_BYTES ((((FWD_NBL + FWD_NBS) * TMA_BUF + 64) + 127) & ~127)   // per warp, 128-byte aligned (tensor copies)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count)
 {
@@ -279,6 +285,20 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// One 3-D tensor-map copy moves a whole block: box {32 floats, TB steps, 16 chunks} of the lattice
+// seen as [chunk][step][32] (a single sequence cut into equal chunks IS that array).  One lane,
+// one instruction, instead of sixteen per-row bulk copies whose uniform-register operands are
+// set up in a sixteen-trip loop (40 % of this kernel's stall samples, profiles/r01_notes_v3.md).
+__device__ __forceinline__ void tensor_load3(uint32_t dst, const CUtensorMap *tm, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tensor_store3(const CUtensorMap *tm, int x, int y, int z, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 :: "l"(tm), "r"(x), "r"(y), "r"(z), "r"(src) : "memory");
 }
 __device__ __forceinline__ void bulk_store(void *dst, uint32_t src, uint32_t bytes)
 {
@@ -304,15 +324,19 @@ __global__ void __launch_bounds__(TILE_WARPS * 32, 1)
 fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
                 const double *__restrict__ rowmax, float *__restrict__ alpha,
                 float *__restrict__ start_vec, float *__restrict__ end_vec,
-                double *__restrict__ cscale, const int *__restrict__ bad, int mode)
+                double *__restrict__ cscale, const int *__restrict__ bad, int mode,
+                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
+                int tm_lf, int tm_nfull)
 {
+    // tm_lf > 0: blin is also described by tmap_b as [tm_nfull chunks][tm_lf steps][32] (one sequence,
+    // full-length chunks only); tiles inside that range load their blocks with one tensor copy
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int N = m.N, W = b.warmup;
     constexpr int LD = 32;                        // lattice row stride (TehmmModelDev::LD for N <= 32)
     // per warp: FWD_NBL load buffers, FWD_NBS store buffers, FWD_NBL mbarriers
-    constexpr int WARP_BYTES = (FWD_NBL + FWD_NBS) * TMA_BUF + 64;
+    constexpr int WARP_BYTES = FWD_WARP_BYTES;
     const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(tile_smem) + (uint32_t)(warp * WARP_BYTES);
     const uint32_t sbase = wbase + FWD_NBL * TMA_BUF;
     const uint32_t bars = sbase + FWD_NBS * TMA_BUF;
@@ -386,10 +410,26 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
             }
         }
         const int nblk = (kmax - kb + TB - 1) / TB;
+        // a tile of sixteen full-length chunks of the one sequence, first pass: tensor copies
+        const bool tens = tm_lf > 0 && mode == 0 && kb == 0 && (W % TB) == 0 && gi * 16 + 15 < (int64_t)tm_nfull;
+        const uint32_t rs = tens ? (uint32_t)(TB * 128) : (uint32_t)TMA_RS;      // bytes between tile rows in a load buffer
         // bulk-load the b rows of block j (clocks kb + j*TB ...) into buffer (nblk_done + j) % FWD_NBL
         auto issue_load = [&](int j) {
             const uint32_t slot = (nblk_done + (uint32_t)j) % FWD_NBL;
             const int k0 = kb + j * TB;
+            if (tens) {
+                // clocks before W read the tail of the chunk to the left: the same box one chunk up
+                // (chunk -1, left of the first tile, is out of bounds: zero fill for a row that has not started)
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_expect_tx(bars + 8 * slot, 16u * TB * 128u);
+                    const bool warm = k0 < W;
+                    tensor_load3(wbase + slot * TMA_BUF, &tmap_b, 0, warm ? tm_lf - W + k0 : k0 - W,
+                                 (int)(gi * 16) - (warm ? 1 : 0), bars + 8 * slot);
+                }
+                return;
+            }
             const int a = max(k0, oks), e = min(k0 + TB, oke);
             const uint32_t bytes = e > a ? (uint32_t)(e - a) * 128u : 0u;
             const uint32_t total = __reduce_add_sync(TEHMM_FULL, bytes);
@@ -406,6 +446,13 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
             const int a = max(k0, W), e = min(min(k0 + TB, oke), kmax);
             fence_async_smem();                   // st.shared above -> visible to the async proxy
             __syncwarp();
+            if (tens) {                           // every row of a regular tile is live for W <= k < W + lf:
+                if (lane == 0) {                  // one box; steps beyond the chunk are clipped by the map
+                    tensor_store3(&tmap_a, 0, k0 - W, (int)(gi * 16), sbase + (uint32_t)((j % FWD_NBS) * TMA_BUF));
+                    bulk_commit();
+                }
+                return;
+            }
             if (lane < 16) {
                 if (e > a)
                     bulk_store(alpha + ooff + (int64_t)a * LD,
@@ -438,8 +485,8 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
             if (j + FWD_NBL - 1 < nblk) issue_load(j + FWD_NBL - 1);
             const uint32_t slot = (nblk_done + (uint32_t)j) % FWD_NBL;
             mbar_wait(bars + 8 * slot, ((nblk_done + (uint32_t)j) / FWD_NBL) & 1u);
-            const uint32_t lbuf = wbase + slot * TMA_BUF + myoff;
-            const uint32_t sbuf = sbase + (uint32_t)((j % FWD_NBS) * TMA_BUF) + myoff;
+            const uint32_t lbuf = wbase + slot * TMA_BUF + (tens ? (uint32_t)(g * TB * 128 + 32 * q) : myoff);
+            const uint32_t sbuf = sbase + (uint32_t)((j % FWD_NBS) * TMA_BUF) + (tens ? (uint32_t)(g * TB * 128 + 32 * q) : myoff);
             const bool storing = alpha != nullptr && kb + j * TB + TB > W;
             if (storing && j >= FWD_NBS) {         // the bulk store that last used this buffer has read it
                 if (lane < 16) bulk_wait_read<FWD_NBS - 1>();
@@ -452,8 +499,8 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 float bt[2][8];
                 lds128(lbuf + s * 128, bt[0], 0);
                 lds128(lbuf + s * 128 + 16, bt[0], 4);
-                lds128(lbuf + s * 128 + 8 * TMA_RS, bt[1], 0);
-                lds128(lbuf + s * 128 + 8 * TMA_RS + 16, bt[1], 4);
+                lds128(lbuf + s * 128 + 8 * rs, bt[1], 0);
+                lds128(lbuf + s * 128 + 8 * rs + 16, bt[1], 4);
                 const bool ev = k == kev;             // warp uniform, rare
                 if (ev) {
 #pragma unroll
@@ -513,8 +560,8 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                     if (alpha) {                       // masked rows stage garbage that is never copied out
                         sts128(sbuf + s * 128, lo2(xp[0]), lo2(xp[1]), lo2(xp[2]), lo2(xp[3]));
                         sts128(sbuf + s * 128 + 16, lo2(xp[4]), lo2(xp[5]), lo2(xp[6]), lo2(xp[7]));
-                        sts128(sbuf + s * 128 + 8 * TMA_RS, hi2(xp[0]), hi2(xp[1]), hi2(xp[2]), hi2(xp[3]));
-                        sts128(sbuf + s * 128 + 8 * TMA_RS + 16, hi2(xp[4]), hi2(xp[5]), hi2(xp[6]), hi2(xp[7]));
+                        sts128(sbuf + s * 128 + 8 * rs, hi2(xp[0]), hi2(xp[1]), hi2(xp[2]), hi2(xp[3]));
+                        sts128(sbuf + s * 128 + 8 * rs + 16, hi2(xp[4]), hi2(xp[5]), hi2(xp[6]), hi2(xp[7]));
                     }
                 } else if (k == W - 1 && mode == 0) {
 #pragma unroll
@@ -967,16 +1014,54 @@ static int tile_grid(const TehmmBatchDev &b, int sms)
     return (int)(need < 1 ? 1 : (need < sms ? need : sms));
 }
 
+// [chunk][step][32 floats] view of a lattice holding ONE sequence cut into chunks of `lf` steps
+// (full-length chunks only).  false: no tensor map (driver entry point missing, odd shape).
+static bool make_lattice_tmap(CUtensorMap *tm, const float *base, int64_t lf, int64_t nfull)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = (encode_fn)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!encode || nfull < 1 || lf < TB || lf > (1 << 30) || nfull > (1 << 30)) return false;
+    const cuuint64_t dims[3] = {32, (cuuint64_t)lf, (cuuint64_t)nfull};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)lf * 128};
+    const cuuint32_t box[3] = {32, TB, 16}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t tehmm_launch_forward_tile(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                       const float *blin, const double *rowmax, float *alpha,
                                       float *start_vec, float *end_vec, double *cscale,
-                                      const int *bad, int mode, int sms)
+                                      const int *bad, int mode, int sms, int64_t fine_len)
 {
-    const int smem = TILE_WARPS * ((FWD_NBL + FWD_NBS) * TMA_BUF + 64);
+    const int smem = TILE_WARPS * FWD_WARP_BYTES;
     cudaError_t e = cudaFuncSetAttribute(fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
+    CUtensorMap tm, tma;
+    memset(&tm, 0, sizeof tm);
+    memset(&tma, 0, sizeof tma);
+    int lf = 0, nfull = 0;
+    if (TEHMM_TILE_TENSOR && b.nseq == 1 && fine_len > 0 && mode == 0 &&
+        make_lattice_tmap(&tm, blin, fine_len, b.total / fine_len) &&
+        (!alpha || make_lattice_tmap(&tma, alpha, fine_len, b.total / fine_len))) {
+        lf = (int)fine_len;
+        nfull = (int)(b.total / fine_len);
+    }
     fwd_tile_kernel<<<tile_grid(b, sms), TILE_WARPS * 32, smem, st>>>(m, b, blin, rowmax, alpha, start_vec,
-                                                                      end_vec, cscale, bad, mode);
+                                                                      end_vec, cscale, bad, mode, tm, tma, lf, nfull);
     return cudaGetLastError();
 }
 
