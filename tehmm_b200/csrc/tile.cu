@@ -411,7 +411,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         }
         const int nblk = (kmax - kb + TB - 1) / TB;
         // a tile of sixteen full-length chunks of the one sequence, first pass: tensor copies
-        const bool tens = tm_lf > 0 && mode == 0 && kb == 0 && (W % TB) == 0 && gi * 16 + 15 < (int64_t)tm_nfull;
+        const bool tens = tm_lf > 0 && mode == 0 && kb == 0 && (W % TB) == 0 && W <= tm_lf && gi * 16 + 15 < (int64_t)tm_nfull;   // W <= lf: the warm-up lies in ONE chunk to the left
         const uint32_t rs = tens ? (uint32_t)(TB * 128) : (uint32_t)TMA_RS;      // bytes between tile rows in a load buffer
         // bulk-load the b rows of block j (clocks kb + j*TB ...) into buffer (nblk_done + j) % FWD_NBL
         auto issue_load = [&](int j) {

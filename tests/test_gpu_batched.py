@@ -314,3 +314,28 @@ def test_xi_tensor_core_kernel_vs_scan_and_f64():
     assert_allclose(tile["obs"], scan["obs"], rtol=1e-5, atol=2e-6)
     # zero transitions of the model stay exactly zero
     assert np.all(tile["trans"][m["A"] == 0] == 0)
+
+
+@pytest.mark.parametrize("fine_len,warmup", [(0, 0), (64, 64), (96, 64), (64, 128), (200, 32)])
+def test_forward_tensor_map_blocks_single_sequence(oracle, fine_len, warmup):
+    """fwd_tile_kernel moves whole blocks with one 3-D tensor-map copy when the batch is ONE
+    regularly chunked sequence (warm-up clocks read the box one chunk up; the last, ragged tile
+    and warm-ups longer than a chunk take the per-row copies): log-likelihood, posteriors and
+    MAP path against the oracle and against the one-chunk-per-warp kernels."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=21)
+    T = 40_003                                      # not a multiple of any chunk length
+    obs, _ = synth.sample_obs(m, T, seed=22)
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    eng = engine(fine_len=fine_len, warmup=warmup, tile=1)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    out = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
+    assert eng.ctx.stat("tile_passes") > 0
+    assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
+    assert_allclose(out["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
+    eng2 = engine(fine_len=fine_len, warmup=warmup, tile=0)
+    eng2.upload_batch([obs])
+    scan = eng2.posteriors(renorm_eps=False, want_map=True, precision="f32")
+    assert scan["logprob"][0] == pytest.approx(out["logprob"][0], rel=1e-6)
+    assert np.mean(scan["map_states"][0] == out["map_states"][0]) > 0.999
