@@ -339,3 +339,45 @@ def test_forward_tensor_map_blocks_single_sequence(oracle, fine_len, warmup):
     scan = eng2.posteriors(renorm_eps=False, want_map=True, precision="f32")
     assert scan["logprob"][0] == pytest.approx(out["logprob"][0], rel=1e-6)
     assert np.mean(scan["map_states"][0] == out["map_states"][0]) > 0.999
+
+
+def test_full_size_c2_properties(oracle):
+    """BASELINE.json configs[1] at FULL size (one sequence of 10 M steps, 30 states, 10 tracks):
+    the oracle cannot run this in seconds, so the checks are the size-independent ones --
+    conservation laws of the E-step, Viterbi score <= log-likelihood, the float64 score of
+    the returned path recomputed on the host, prefix consistency (paths coalesce), no repairs
+    -- plus the oracle on a 200 k prefix."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=0)
+    T = 10_000_000
+    obs, _ = synth.sample_obs(m, T, seed=1)
+    eng = engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    lps, states = eng.viterbi()
+    out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
+    st = eng.estep()
+    K, N = m["K"], m["N"]
+    path = states[0]
+    assert path.shape == (T,) and path.dtype == np.int64 and path.min() >= 0 and path.max() < N
+    assert lps[0] <= out["logprob"][0] < 0
+    assert 0.9 * T < out["map_score"][0] <= T * (1 + 1e-6)
+    assert st["logprob"] == pytest.approx(out["logprob"][0], rel=1e-9)
+    assert st["obs"].sum() == pytest.approx(T * K, rel=1e-6)          # every step adds one unit per track
+    assert st["trans"].sum() * N == pytest.approx(T - 1, rel=1e-6)    # (1/N: _hmm.pyx:179)
+    assert st["start"].sum() * 1.0 == pytest.approx(1.0, rel=1e-5)
+    assert np.all(st["trans"][m["A"] == 0] == 0)
+    for k in ("forward", "backward", "viterbi", "traceback"):
+        assert eng.ctx.stat("repaired_chunks_" + k) == 0
+    # float64 score of the returned path, recomputed on the host from the reference-layout tables
+    idx = np.arange(T)
+    e = np.zeros(T)
+    for k in range(K):
+        e += m["table"][k, path, obs[:, k]]
+    score = m["log_start"][path[0]] + e.sum() + m["log_trans"][path[:-1], path[1:]].sum()
+    assert lps[0] == pytest.approx(score, rel=1e-11)
+    # prefix: the first 150 k states of the 10 M decode == those of a stand-alone 200 k decode == the oracle's
+    n0 = 200_000
+    ref = oracle.sweep_sequence(obs[:n0], m["table"], 1.0, m["log_start"], m["log_trans"])
+    assert_array_equal(path[:150_000], ref["vit_states"][:150_000])
+    assert np.mean(out["map_states"][0][:150_000] == ref["map_states"][:150_000]) > 0.9999
