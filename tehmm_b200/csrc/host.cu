@@ -401,10 +401,14 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     // slices, so that the widening of slice i overlaps the transfer of slice i+1
     const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
     const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
-    std::vector<cudaEvent_t> evs(nsl);
+    while ((int)p->slice_ev.size() < nsl) {            // the upload's events are long complete: reuse them
+        cudaEvent_t ev;
+        HCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        p->slice_ev.push_back(ev);
+    }
+    const std::vector<cudaEvent_t> &evs = p->slice_ev;
     for (int i = 0; i < nsl; ++i) {
         const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
-        HCU(cudaEventCreateWithFlags(&evs[i], cudaEventDisableTiming));
         if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
         HCU(cudaEventRecord(evs[i], st));
     }
@@ -412,7 +416,6 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     for (int i = 0; i < nsl; ++i) {
         const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
         cudaError_t e = cudaEventSynchronize(evs[i]);
-        cudaEventDestroy(evs[i]);
         if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
         if (n <= 0 || rc != TEHMM_OK) continue;
         const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
