@@ -36,6 +36,8 @@ cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t
 cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int, int64_t);
 cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int);
 int tehmm_tile_warps(void);
+bool tehmm_forward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int64_t);
+cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, int, int64_t, int *);
 cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
 size_t tehmm_xi_tile_scratch_bytes(int sms);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
@@ -85,6 +87,9 @@ struct tehmm_ctx {
     // option "timing": CUDA events around the first (speculative) launch of each main kernel, on the
     // launching stream; read back in microseconds with tehmm_ctx_get_stat("us_<kernel>")
     int64_t opt_timing = 0;
+    int64_t opt_umma = 0;             // 1: forward pass on tcgen05 / TMEM (umma.cu) where it applies -- correct, not yet faster
+    int *d_fault = nullptr;           // raised by a kernel whose barrier protocol timed out
+    int64_t stat_umma_passes = 0;
     int64_t opt_xi_tile = 1;          // expected transition counts by xi_tile_kernel (0: one-chunk-per-warp backward)
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
     int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
@@ -137,7 +142,9 @@ int tehmm_ctx_create(int device, tehmm_ctx **out)
     c->sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    CU(cudaMallocHost((void **)&c->h_nbad, sizeof(int)));
+    CU(cudaMallocHost((void **)&c->h_nbad, 2 * sizeof(int)));
+    CU(cudaMalloc((void **)&c->d_fault, sizeof(int)));
+    CU(cudaMemset(c->d_fault, 0, sizeof(int)));
     *out = c;
     return TEHMM_OK;
 }
@@ -152,6 +159,7 @@ int tehmm_ctx_destroy(tehmm_ctx *c)
     if (c->batch_blob) cudaFree(c->batch_blob);
     if (c->d_seq_flag) cudaFree(c->d_seq_flag);
     if (c->h_nbad) cudaFreeHost(c->h_nbad);
+    if (c->d_fault) cudaFree(c->d_fault);
     for (int i = 0; i < TEHMM_NTIMED; ++i)
         for (int r = 0; r < TEHMM_TRING; ++r)
             for (int j = 0; j < 2; ++j)
@@ -191,6 +199,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "tile")) c->opt_tile = v;
     else if (!strcmp(name, "timing")) { c->opt_timing = v; for (int i = 0; i < TEHMM_NTIMED; ++i) c->ev_n[i] = 0; }
     else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
+    else if (!strcmp(name, "umma")) c->opt_umma = v;
     else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
@@ -212,6 +221,7 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
     if (!strcmp(name, "fine_chunks")) return c->has_batch ? c->bf.nchunks : 0;
     if (!strcmp(name, "tile_passes")) return c->stat_tile_passes;
+    if (!strcmp(name, "umma_passes")) return c->stat_umma_passes;
     for (int i = 0; i < TEHMM_NTIMED; ++i)
         if (!strcmp(name, tk_names[i])) {
             // average over the launches recorded since "timing" was set (at most the last TEHMM_TRING)
@@ -862,7 +872,15 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     const int grid = scan_grid(c);
     const bool tile = use_tile(c, prec, d_ratios);
     const TehmmBatchDev &PB = tile ? c->bf : c->b;       // the partition this pass runs on
+    bool umma_used = false;
     auto launch = [&](int mode) -> cudaError_t {
+        if (tile && c->opt_umma && tehmm_forward_umma_ok(c->m, PB, mode, c->fine_len)) {
+            cudaError_t eu = tehmm_launch_forward_umma(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha,
+                                                       (float *)sv, (float *)ev, cs, c->sms, c->fine_len, c->d_fault);
+            if (eu == cudaSuccess) { c->stat_umma_passes += 1; umma_used = true; return eu; }
+            if (eu != cudaErrorNotSupported) return eu;
+            cudaGetLastError();          // no tensor map: the mma.sync kernel below
+        }
         if (tile) {
             c->stat_tile_passes += 1;
             return tehmm_launch_forward_tile(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha, (float *)sv, (float *)ev, cs, bad, mode, c->sms, c->fine_len);
@@ -879,7 +897,12 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
         CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, +1, 1, bad, nbad, lkap));
         c->launches += 1;
         int nb = 0;
+        if (umma_used && pass == 0) CU(cudaMemcpyAsync(c->h_nbad + 1, c->d_fault, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (umma_used && pass == 0 && c->h_nbad[1]) {
+            CU(cudaMemsetAsync(c->d_fault, 0, sizeof(int), st));
+            return fail(TEHMM_ECUDA, "fwd_umma_kernel: a barrier wait timed out (tensor-memory protocol fault)");
+        }
         if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "forward repair did not converge (%d chunks left)", nb);

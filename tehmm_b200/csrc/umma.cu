@@ -1,0 +1,418 @@
+// Forward pass on the 5th-generation tensor cores: tcgen05.mma with the accumulator AND the
+// state operand in tensor memory (hmm.py:678-713 -> _hmm.pyx:120-158).
+//
+// fwd_tile_kernel (tile.cu) advances 16 chunks per warp with mma.sync and keeps the recursion
+// in registers; it runs at ~40 % of the (legacy) tensor pipe and 36 % issue utilisation, and
+// neither more warps nor fewer registers move it.  Here a CTA of four warps advances ONE TILE
+// OF 128 CHUNKS (thread = chunk = TMEM lane) per step:
+//
+//     D[128 x 32] = X_lo A_hi + X_hi A_lo + X_hi A_hi        12 tcgen05.mma (M128 N32 K8, kind::tf32),
+//                                                             issued by one thread, D and X in TMEM,
+//                                                             A (hi / lo parts) in shared memory
+//     x' = D .* b_t * 2^-shift                                epilogue: tcgen05.ld of the thread's row,
+//                                                             its own maximum (no shuffles), power-of-two
+//                                                             scale with a one-step lag, mask split into
+//                                                             hi / lo, tcgen05.st back as the next X
+//
+// b rows arrive and alpha rows leave as 3-D tensor-map boxes {32 floats, TB steps, 128 chunks}
+// (SWIZZLE_128B, so that a thread reading "its" 128-byte row does not collide with its
+// neighbours), double buffered, one elected thread issuing.  Same chunk partition, same
+// speculate / verify / repair protocol, same start_vec / end_vec / cscale conventions as
+// fwd_tile_kernel, whose alpha lattice this one's is interchangeable with (everything downstream
+// is scale free).  Used for a batch that is ONE sequence (first pass); everything else takes
+// fwd_tile_kernel.
+//
+// STATUS (measured on B200, 10 M x 30): results agree with fwd_tile_kernel (log-likelihood to
+// 5e-9 relative, identical MAP paths, no repairs) but a step of one 128-row tile takes ~2 450
+// cycles, 0.77 ms in all against 0.55 ms: the twelve MMAs cost ~190 cycles of it (dropping eight
+// of them saves 35 us); the rest is the serial round trip issue -> commit -> mbarrier ->
+// tcgen05.ld (16 KB at 64 B/cycle) -> ~310 instructions per thread with one warp per sub-partition
+// -> tcgen05.st -> CTA barrier.  Two or three CTAs per SM (TB = 1, own chunk partition) reach
+// 0.68 ms, no further: an SM-wide resource saturates near 2 000 cycles per tile step.  It is
+// therefore opt-in (context option "umma"); the next steps are packed fp32 in the epilogue, two
+// threads per row, and a second tile in flight per CTA so that the tensor core never waits.
+#include "scan.cuh"
+#include <cuda.h>
+#include <cstring>
+
+#ifndef UM_TB
+#define UM_TB 2                       // time steps per box
+#endif
+#ifndef UM_CTAS
+#define UM_CTAS 1                     // resident CTAs per SM
+#endif
+#define UM_ROWS 128
+#define UM_BOX (UM_ROWS * UM_TB * 128)            // bytes of one box: 32 KB
+#define UM_NLD 2                      // load buffers
+#define UM_NST 2                      // store buffers
+#define UM_SMEM (1024 + (UM_NLD + UM_NST) * UM_BOX + 2 * 4096 + 256)
+
+__device__ __forceinline__ void um_mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void um_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error must not hang the GPU.  After ~0.1 s without the phase
+// completing the kernel-wide fault flag is raised; once it is up every wait returns at once, so
+// all threads keep walking the same barrier sequence to the end and the host reports the error.
+__device__ __forceinline__ void um_mbar_wait(uint32_t bar, uint32_t parity, volatile int *fault)
+{
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if ((spin & 1023u) == 1023u && *fault) return;
+    }
+    *fault = 1;
+}
+__device__ __forceinline__ void um_tensor_load3(uint32_t dst, const CUtensorMap *tm, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void um_tensor_store3(const CUtensorMap *tm, int x, int y, int z, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                 :: "l"(tm), "r"(x), "r"(y), "r"(z), "r"(src) : "memory");
+}
+__device__ __forceinline__ void um_tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void um_tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0],"
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                 :: "r"(taddr),
+                    "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                    "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                    "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; one thread issues on behalf of the CTA
+__device__ __forceinline__ void um_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// K-major, no swizzle: core matrices of 8 rows x 16 bytes; LBO = bytes between the two 16-byte
+// K-chunks of one instruction, SBO = bytes between 8-row groups (cute/atom/mma_traits_sm100.hpp)
+__device__ __forceinline__ uint64_t um_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(UM_ROWS, UM_CTAS)
+fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
+                const double *__restrict__ rowmax, float *__restrict__ alpha,
+                float *__restrict__ start_vec, float *__restrict__ end_vec, double *__restrict__ cscale,
+                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
+                int lf, int nfull, int *__restrict__ fault)
+{
+    extern __shared__ unsigned char um_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(um_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B boxes: 1024-byte aligned
+    unsigned char *gbase = um_raw + (base - raw);
+    const uint32_t ldbuf = base, stbuf = base + UM_NLD * UM_BOX, bhi = stbuf + UM_NST * UM_BOX, blo = bhi + 4096;
+    const uint32_t bars = blo + 4096;                             // ld[UM_NLD], mma
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + 2 * 4096 + 64);
+    int *esum_s = reinterpret_cast<int *>(gbase);                 // reused after the main loop (load buffer 0)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = m.N, W = b.warmup;
+
+    // ---- transition matrix, hi / lo TF32 parts, canonical K-major layout: B[n = j][k = i] = A[i][j]
+    for (int e = tid; e < 32 * 32; e += UM_ROWS) {
+        const int n = e >> 5, k = e & 31;
+        const double v = m.lin_trans[(int64_t)k * 32 + n];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"((float)v));
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"((float)(v - (double)__uint_as_float(h))));
+        const uint32_t off = (uint32_t)((k >> 2) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
+        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + off) = h;
+        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + 4096 + off) = l;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < UM_NLD + 1; ++i) um_mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // B parts (generic writes) -> tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_d = tmem, t_hi = tmem + 32, t_lo = tmem + 64;              // column offsets
+    const uint32_t my_lane = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lanes
+    const uint32_t bar_mma = bars + 8 * UM_NLD;
+    // kind::tf32, F32 accumulate, A and B K-major, N = 32, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+    uint32_t mma_phase = 0, ld_phase = 0;                         // bit i of ld_phase: parity of load barrier i
+    volatile int *vfault = fault;
+    for (int64_t tile = blockIdx.x; tile * UM_ROWS < b.nchunks; tile += gridDim.x) {
+        // ---- this thread's chunk
+        const int64_t c = tile * UM_ROWS + tid;
+        const bool valid = c < b.nchunks;
+        TehmmChunk ch = b.chunks[valid ? c : b.nchunks - 1];
+        const int64_t dist = ch.t0 - ch.s0;
+        const bool first = valid && dist == 0, pred = valid && dist > 0;
+        const int len = valid ? (int)(ch.t1 - ch.t0) : 0;
+        const int ks = first ? W : 0, ke = W + len;
+        const bool boxed = valid && len == lf && c < nfull;      // its rows travel in the boxes
+        const int kmax = W + lf;
+        const int nblk = (kmax + UM_TB - 1) / UM_TB;
+        const int c0 = (int)(tile * UM_ROWS);
+        const float *brow0 = blin + (ch.t0 - W) * 32;            // row of clock 0 (direct path only)
+        float *arow0 = alpha ? alpha + (ch.t0 - W) * 32 : nullptr;
+
+        auto issue_load = [&](int j) {                           // thread 0
+            const int k0 = j * UM_TB;
+            const bool warm = k0 < W;
+            const uint32_t bar = bars + 8 * (j % UM_NLD);
+            um_mbar_expect_tx(bar, UM_BOX);
+            um_tensor_load3(ldbuf + (j % UM_NLD) * UM_BOX, &tmap_b, 0, warm ? lf - W + k0 : k0 - W, c0 - (warm ? 1 : 0), bar);
+        };
+        if (tid == 0)
+            for (int j = 0; j < UM_NLD && j < nblk; ++j) issue_load(j);
+
+        // ---- initial operand: a flat vector (a row that starts its sequence stays empty until clock W)
+        uint32_t xh[32], xl[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            xh[i] = (valid && !first && i < N) ? __float_as_uint(1.f) : 0u;
+            xl[i] = 0u;
+        }
+        um_tmem_st32(t_hi + my_lane, xh);
+        um_tmem_st32(t_lo + my_lane, xl);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        float scp = 1.f;
+        int shp = 0, esum = 0;
+
+        auto issue_mma = [&]() {                                 // thread 0, after the CTA barrier
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                um_mma_tf32_ts(t_d, t_lo + kk * 8, um_smem_desc(bhi + kk * 1024, 512, 128), idesc, kk > 0);
+#ifndef UM_EXP_ONE_PRODUCT
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(blo + kk * 1024, 512, 128), idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(bhi + kk * 1024, 512, 128), idesc, 1);
+#endif
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_mma) : "memory");
+        };
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) issue_mma();
+
+        for (int j = 0; j < nblk; ++j) {
+            const uint32_t lb = ldbuf + (j % UM_NLD) * UM_BOX, sb = stbuf + (j % UM_NST) * UM_BOX;
+            um_mbar_wait(bars + 8 * (j % UM_NLD), (ld_phase >> (j % UM_NLD)) & 1u, vfault);
+            ld_phase ^= 1u << (j % UM_NLD);
+            const bool storing = alpha != nullptr && j * UM_TB + UM_TB > W;
+            if (storing && j >= UM_NST) {                        // the store that last used this buffer has read it
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(UM_NST - 1) : "memory");
+                __syncthreads();
+            }
+#pragma unroll
+            for (int s = 0; s < UM_TB; ++s) {
+                const int k = j * UM_TB + s;
+                if (k >= kmax) break;
+                // b row of this clock: from the box (128-byte line L = row * TB + s, 16-byte chunks XOR-swizzled) or direct
+                float bt[32];
+                const uint32_t line = (uint32_t)(tid * UM_TB + s);
+                if (boxed) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(bt[4 * q]), "=f"(bt[4 * q + 1]), "=f"(bt[4 * q + 2]), "=f"(bt[4 * q + 3])
+                                     : "r"(lb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
+                } else {
+                    const bool on = valid && k >= ks && k < ke;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = on ? *reinterpret_cast<const float4 *>(brow0 + (int64_t)k * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        bt[4 * q] = v.x; bt[4 * q + 1] = v.y; bt[4 * q + 2] = v.z; bt[4 * q + 3] = v.w;
+                    }
+                }
+                // D of this clock
+                um_mbar_wait(bar_mma, mma_phase, vfault);
+                mma_phase ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t dv[32];
+                um_tmem_ld32(t_d + my_lane, dv);
+                float a[32];
+                float mx = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    a[i] = __uint_as_float(dv[i]) * (bt[i] * scp);
+                    mx = fmaxf(mx, a[i]);
+                }
+                int sh_now = shp;
+                if (first && k == ks) {                          // alpha_0 = pi .* b_0
+                    mx = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        a[i] = (float)m.lin_start[i] * bt[i];
+                        mx = fmaxf(mx, a[i]);
+                    }
+                    sh_now = 0;
+                }
+                if (!valid || k < ks) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a[i] = 0.f;
+                    mx = 0.f;
+                }
+                {   // exact power-of-two scale for the NEXT step (scale_of in tile.cu)
+                    const unsigned mb = __float_as_uint(mx);
+                    scp = __uint_as_float(0x7f000000u - (mb & 0x7f800000u));
+                    shp = (int)(mb >> 23) - 127;
+                }
+                if (k >= W) {
+                    esum += k < ke ? sh_now : 0;
+                    if (alpha) {
+                        if (boxed) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                             :: "r"(sb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)),
+                                                "f"(a[4 * q]), "f"(a[4 * q + 1]), "f"(a[4 * q + 2]), "f"(a[4 * q + 3]) : "memory");
+                        } else if (valid && k < ke) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4 *>(arow0 + (int64_t)k * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                        }
+                    }
+                } else if (k == W - 1 && pred) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(start_vec + c * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                }
+                if (valid && k + 1 == ke) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(end_vec + c * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                }
+                // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    xh[i] = __float_as_uint(a[i]) & 0xffffe000u;
+                    xl[i] = __float_as_uint(a[i] - __uint_as_float(xh[i]));
+                }
+                um_tmem_st32(t_hi + my_lane, xh);
+                um_tmem_st32(t_lo + my_lane, xl);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (s == UM_TB - 1 || k + 1 >= kmax) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // alpha rows -> TMA store
+                __syncthreads();
+                if (tid == 0 && k + 1 < kmax) issue_mma();
+            }
+            if (tid == 0) {
+                if (storing) {
+                    const int k0 = j * UM_TB;
+                    um_tensor_store3(&tmap_a, 0, k0 - W, c0, sb);       // clocks before W are never in a storing block: W % TB == 0
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (j + UM_NLD < nblk) issue_load(j + UM_NLD);           // every thread has passed the barrier after reading lb
+            }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- log of everything taken out of each chunk: exponents and row maxima
+        esum_s[tid] = esum;
+        __syncthreads();
+        for (int rr = warp; rr < UM_ROWS; rr += UM_ROWS / 32) {
+            const int64_t cc = tile * UM_ROWS + rr;
+            if (cc >= b.nchunks) break;
+            const TehmmChunk c2 = b.chunks[cc];
+            double ms = 0.0;
+            for (int64_t tt = c2.t0 + lane; tt < c2.t1; tt += 32) ms += rowmax[tt];
+            ms = warp_sum(ms);
+            if (lane == 0) cscale[cc] = (double)esum_s[rr] * 0.6931471805599453094 + ms;
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+}
+
+// [chunk][step][32 floats] view, boxes {32, UM_TB, 128}, 128-byte swizzle
+static bool um_make_tmap(CUtensorMap *tm, const float *base, int64_t lf, int64_t nfull)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = (encode_fn)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!encode || nfull < 1 || lf < UM_TB) return false;
+    const cuuint64_t dims[3] = {32, (cuuint64_t)lf, (cuuint64_t)nfull};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)lf * 128};
+    const cuuint32_t box[3] = {32, UM_TB, UM_ROWS}, estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// whether this batch / pass can take the tcgen05 kernel
+bool tehmm_forward_umma_ok(const TehmmModelDev &m, const TehmmBatchDev &b, int mode, int64_t fine_len)
+{
+    return m.NS == 1 && m.LD == 32 && b.nseq == 1 && mode == 0 && fine_len >= b.warmup && (b.warmup % UM_TB) == 0 &&
+           b.total / fine_len >= 1;
+}
+
+cudaError_t tehmm_launch_forward_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                                      const float *blin, const double *rowmax, float *alpha,
+                                      float *start_vec, float *end_vec, double *cscale, int sms,
+                                      int64_t fine_len, int *fault)
+{
+    CUtensorMap tb, ta;
+    memset(&tb, 0, sizeof tb);
+    memset(&ta, 0, sizeof ta);
+    const int64_t nfull = b.total / fine_len;
+    if (!um_make_tmap(&tb, blin, fine_len, nfull) || (alpha && !um_make_tmap(&ta, alpha, fine_len, nfull)))
+        return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (b.nchunks + UM_ROWS - 1) / UM_ROWS;
+    const int grid = (int)(tiles < (int64_t)sms * UM_CTAS ? tiles : (int64_t)sms * UM_CTAS);
+    fwd_umma_kernel<<<grid, UM_ROWS, UM_SMEM, st>>>(m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, tb, ta,
+                                                    (int)fine_len, (int)nfull, fault);
+    return cudaGetLastError();
+}

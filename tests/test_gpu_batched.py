@@ -383,3 +383,30 @@ def test_full_size_c2_properties(oracle):
     ref = oracle.sweep_sequence(obs[:n0], m["table"], 1.0, m["log_start"], m["log_trans"])
     assert_array_equal(path[:150_000], ref["vit_states"][:150_000])
     assert np.mean(out["map_states"][0][:150_000] == ref["map_states"][:150_000]) > 0.9999
+
+
+def test_forward_tcgen05_kernel_matches(oracle):
+    """csrc/umma.cu (context option "umma"): the forward pass of a single-sequence batch on
+    tcgen05.mma with accumulator and state in tensor memory, b / alpha rows as swizzled 3-D
+    tensor-map boxes.  Same log-likelihood, posteriors and MAP path as the oracle and as the
+    mma.sync kernel, including a ragged last chunk handled outside the boxes."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=31)
+    T = 150_007
+    obs, _ = synth.sample_obs(m, T, seed=32)
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    eng = engine(fine_len=200)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    base = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
+    before = eng.ctx.stat("umma_passes")
+    eng.ctx.set_option("umma", 1)
+    try:
+        out = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
+    finally:
+        eng.ctx.set_option("umma", 0)
+    assert eng.ctx.stat("umma_passes") == before + 1
+    assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
+    assert_allclose(out["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
+    assert out["logprob"][0] == pytest.approx(base["logprob"][0], rel=1e-7)
+    assert np.mean(out["map_states"][0] == base["map_states"][0]) > 0.9999
