@@ -34,6 +34,7 @@
 #include "scan.cuh"
 #include <cuda.h>
 #include <cstring>
+#include <cstdio>
 
 #ifndef UM_TB
 #define UM_TB 2                       // time steps per box
@@ -45,6 +46,11 @@
 #define UM_BOX (UM_ROWS * UM_TB * 128)            // bytes of one box: 32 KB
 #define UM_NLD 2                      // load buffers
 #define UM_NST 2                      // store buffers
+#ifdef UM_PROFILE
+#define UM_T(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define UM_T(i) do { } while (0)
+#endif
 #define UM_SMEM (1024 + (UM_NLD + UM_NST) * UM_BOX + 2 * 4096 + 256)
 
 __device__ __forceinline__ void um_mbar_init(uint32_t bar, int count)
@@ -110,6 +116,12 @@ __device__ __forceinline__ void um_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
                  :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ u64 um_fmul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 // K-major, no swizzle: core matrices of 8 rows x 16 bytes; LBO = bytes between the two 16-byte
 // K-chunks of one instruction, SBO = bytes between 8-row groups (cute/atom/mma_traits_sm100.hpp)
@@ -229,10 +241,14 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         __syncthreads();
         if (tid == 0) issue_mma();
 
+#ifdef UM_PROFILE
+        long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#endif
         for (int j = 0; j < nblk; ++j) {
             const uint32_t lb = ldbuf + (j % UM_NLD) * UM_BOX, sb = stbuf + (j % UM_NST) * UM_BOX;
             um_mbar_wait(bars + 8 * (j % UM_NLD), (ld_phase >> (j % UM_NLD)) & 1u, vfault);
             ld_phase ^= 1u << (j % UM_NLD);
+            UM_T(0);
             const bool storing = alpha != nullptr && j * UM_TB + UM_TB > W;
             if (storing && j >= UM_NST) {                        // the store that last used this buffer has read it
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(UM_NST - 1) : "memory");
@@ -260,31 +276,39 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                     }
                 }
                 // D of this clock
+                UM_T(1);
                 um_mbar_wait(bar_mma, mma_phase, vfault);
                 mma_phase ^= 1u;
+                UM_T(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t dv[32];
                 um_tmem_ld32(t_d + my_lane, dv);
-                float a[32];
-                float mx = 0.f;
+                UM_T(3);
+                // x' = D .* b * scale in packed fp32 (FMUL2), maximum as a 3-input tree
+                const u64 sc2 = pk2(scp, scp);
+                u64 a2[16];
+                float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    a[i] = __uint_as_float(dv[i]) * (bt[i] * scp);
-                    mx = fmaxf(mx, a[i]);
+                for (int i = 0; i < 16; ++i) {
+                    const u64 d2 = ((u64)dv[2 * i + 1] << 32) | (u64)dv[2 * i];
+                    a2[i] = um_fmul2(d2, um_fmul2(pk2(bt[2 * i], bt[2 * i + 1]), sc2));
+                    if (i & 1) m1 = fmax3(m1, lo2(a2[i]), hi2(a2[i])); else m0 = fmax3(m0, lo2(a2[i]), hi2(a2[i]));
                 }
+                float mx = fmaxf(m0, m1);
                 int sh_now = shp;
                 if (first && k == ks) {                          // alpha_0 = pi .* b_0
                     mx = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        a[i] = (float)m.lin_start[i] * bt[i];
-                        mx = fmaxf(mx, a[i]);
+                    for (int i = 0; i < 16; ++i) {
+                        const float p0 = (float)m.lin_start[2 * i] * bt[2 * i], p1 = (float)m.lin_start[2 * i + 1] * bt[2 * i + 1];
+                        a2[i] = pk2(p0, p1);
+                        mx = fmax3(mx, p0, p1);
                     }
                     sh_now = 0;
                 }
                 if (!valid || k < ks) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) a[i] = 0.f;
+                    for (int i = 0; i < 16; ++i) a2[i] = 0ull;
                     mx = 0.f;
                 }
                 {   // exact power-of-two scale for the NEXT step (scale_of in tile.cu)
@@ -298,38 +322,44 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                         if (boxed) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
-                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
-                                             :: "r"(sb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)),
-                                                "f"(a[4 * q]), "f"(a[4 * q + 1]), "f"(a[4 * q + 2]), "f"(a[4 * q + 3]) : "memory");
+                                asm volatile("st.shared.v2.u64 [%0], {%1,%2};"
+                                             :: "r"(sb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)), "l"(a2[2 * q]), "l"(a2[2 * q + 1]) : "memory");
                         } else if (valid && k < ke) {
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<float4 *>(arow0 + (int64_t)k * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                                *reinterpret_cast<ulonglong2 *>(arow0 + (int64_t)k * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                         }
                     }
                 } else if (k == W - 1 && pred) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4 *>(start_vec + c * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                        *reinterpret_cast<ulonglong2 *>(start_vec + c * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                 }
                 if (valid && k + 1 == ke) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4 *>(end_vec + c * 32 + 4 * q) = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                        *reinterpret_cast<ulonglong2 *>(end_vec + c * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                 }
-                // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly
+                // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly (FFMA2: a - hi)
+                const u64 neg1 = pk2(-1.f, -1.f);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    xh[i] = __float_as_uint(a[i]) & 0xffffe000u;
-                    xl[i] = __float_as_uint(a[i] - __uint_as_float(xh[i]));
+                for (int i = 0; i < 16; ++i) {
+                    const u64 h2 = a2[i] & 0xffffe000ffffe000ull;
+                    const u64 l2 = ffma2(h2, neg1, a2[i]);
+                    xh[2 * i] = (uint32_t)h2; xh[2 * i + 1] = (uint32_t)(h2 >> 32);
+                    xl[2 * i] = (uint32_t)l2; xl[2 * i + 1] = (uint32_t)(l2 >> 32);
                 }
+                UM_T(4);
                 um_tmem_st32(t_hi + my_lane, xh);
                 um_tmem_st32(t_lo + my_lane, xl);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                UM_T(5);
                 if (s == UM_TB - 1 || k + 1 >= kmax) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // alpha rows -> TMA store
                 __syncthreads();
+                UM_T(6);
                 if (tid == 0 && k + 1 < kmax) issue_mma();
+                UM_T(7);
             }
             if (tid == 0) {
                 if (storing) {
@@ -340,6 +370,11 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 if (j + UM_NLD < nblk) issue_load(j + UM_NLD);           // every thread has passed the barrier after reading lb
             }
         }
+#ifdef UM_PROFILE
+        if (blockIdx.x == 3 && (tid == 0 || tid == 64))
+            printf("umma tid %d cycles/step: ldwait %lld  b-load %lld  mmawait %lld  ldtm %lld  math %lld  sttm %lld  barrier %lld  issue %lld\n", tid,
+                   tacc[0] / kmax, tacc[1] / kmax, tacc[2] / kmax, tacc[3] / kmax, tacc[4] / kmax, tacc[5] / kmax, tacc[6] / kmax, tacc[7] / kmax);
+#endif
         if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         __syncthreads();
 
