@@ -81,7 +81,10 @@ class _ResultPool(object):
                     block = self._free.pop(i)
                     break
         if block is None:
-            block = mmap.mmap(-1, (nbytes + (2 << 20) - 1) & ~((2 << 20) - 1))
+            # PRIVATE: like ordinary heap memory, a forked child (teHmm's --proc workers) gets its own
+            # copy-on-write view (mmap's default for fd -1 is a SHARED mapping)
+            block = mmap.mmap(-1, (nbytes + (2 << 20) - 1) & ~((2 << 20) - 1),
+                              flags=mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS)
             try:                                  # first touch in 2 MB pages where the kernel allows it
                 block.madvise(mmap.MADV_HUGEPAGE)
             except (AttributeError, OSError, ValueError):
