@@ -327,7 +327,7 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     const bool piecewise = tehmm_emission_rows_supported(c, prec) == 1;
     const size_t row_bytes = (size_t)K * obs_bytes;
     int64_t slice_rows = (int64_t)(SLICE / row_bytes) & ~(int64_t)31;
-    if (slice_rows < 32) slice_rows = 32;
+    if (slice_rows < 32) return herr(TEHMM_ELIMIT, "a row of %zu bytes does not fit the staging slices", row_bytes);
     const int nth = p->pool->size();
     size_t si = 0;                                       // first segment that reaches into the slice
     int64_t slot = 0;
