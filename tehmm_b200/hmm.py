@@ -17,6 +17,7 @@ import string
 import numpy as np
 from numpy.testing import assert_array_almost_equal
 
+from . import _hmm as _strict_hmm
 from . import _lib, parallel
 from .common import EPSILON, logger, logsumexp, myLog, normalize
 from .engine import as_obs_array, get_engine
@@ -164,6 +165,81 @@ class MultitrackHmm(BaseHMM):
     def _seg_ratios(self, obs):
         return self.emissionModel.getSegmentRatios(obs)
 
+    # ------------------------------------------------------------ more than 64 states
+    # The batched kernels hold a lane's slice of the transition matrix in registers, which stops
+    # at 64 states.  Wider models take the reference's own per-sequence flow (basehmm.py:238-359,
+    # 507-522; hmm.py:545-574, 668-729) on the strict float64 kernels of tehmm_b200._hmm /
+    # _emission -- still on the GPU, one sequence and one (T, N) float64 lattice at a time.
+    def _wide(self):
+        return self.emissionModel.getNumStates() > _lib.MAX_STATES
+
+    def _wide_lattices(self, frame, ratios):
+        T, N = frame.shape
+        fwd, bwd = np.zeros((T, N)), np.zeros((T, N))
+        _strict_hmm._forward(T, N, self._log_startprob, self._log_transmat, frame, ratios, fwd)
+        _strict_hmm._backward(T, N, self._log_startprob, self._log_transmat, frame, ratios, bwd)
+        return fwd, bwd
+
+    @staticmethod
+    def _wide_posteriors(fwd, bwd):
+        gamma = fwd + bwd
+        return np.exp(gamma.T - logsumexp(gamma, axis=1)).T
+
+    def _wide_score_samples(self, obs):
+        # basehmm.py:261-272: np.asarray(obs) drops the TrackTable, so no segment ratios anywhere
+        frame = self.emissionModel.allLogProbs(as_obs_array(obs))
+        fwd, bwd = self._wide_lattices(frame, None)
+        lp = float(logsumexp(fwd[-1]))
+        self._note_forward_logprob(lp)
+        post = self._wide_posteriors(fwd, bwd)
+        post += np.finfo(np.float32).eps
+        post /= np.sum(post, axis=1).reshape((-1, 1))
+        return lp, post
+
+    def _wide_decode(self, obs, algorithm):
+        if algorithm == "viterbi":
+            # basehmm.py:327 / hmm.py:668-676: emission without ratios, DP with the table's
+            frame = self.emissionModel.allLogProbs(as_obs_array(obs))
+            T, N = frame.shape
+            states, lp = _strict_hmm._viterbi(T, N, self._log_startprob, self._log_transmat,
+                                              self._seg_ratios(obs), frame)
+            return float(lp), states
+        _, post = self._wide_score_samples(obs)
+        return float(np.max(post, axis=1).sum()), np.argmax(post, axis=1)
+
+    def _wide_estep(self, obs, stats, params, n_total, slots):
+        """the E-step of fit() for this rank's sequences; one all-reduce like _device_estep"""
+        N = self.n_components
+        local = {'start': np.zeros(N), 'trans': np.zeros((N, N)), 'obs': np.zeros_like(stats['obs'])}
+        lps = np.zeros(n_total)
+        for slot, seq in zip(slots, obs):
+            ratios = self._seg_ratios(seq)
+            frame = self.emissionModel.allLogProbs(seq)
+            fwd, bwd = self._wide_lattices(frame, ratios)
+            lps[slot] = logsumexp(fwd[-1])
+            post = self._wide_posteriors(fwd, bwd)
+            if 's' in params:
+                local['start'] += post[0]
+            if 't' in params and frame.shape[0] > 1:
+                logsum = np.zeros((N, N))
+                _strict_hmm._log_sum_lneta(frame.shape[0], N, fwd, self._log_transmat, bwd, frame,
+                                           float(lps[slot]), ratios, logsum)
+                local['trans'] += np.exp(logsum)
+            if 'e' in params:
+                self.emissionModel.accumulateStats(seq, local['obs'], post)
+        packed = np.concatenate([[float(len(obs))], local['start'], local['trans'].ravel(), local['obs'].ravel(), lps])
+        n, _ = parallel.world()
+        if n > 1:
+            import torch
+            t = torch.from_numpy(packed)
+            packed = parallel.all_reduce_stats(t.cuda() if parallel._dist().get_backend() == "nccl" else t).cpu().numpy()
+        o = 1
+        stats['nobs'] += int(round(packed[0]))
+        stats['start'] += packed[o:o + N]; o += N
+        stats['trans'] += packed[o:o + N * N].reshape(N, N); o += N * N
+        stats['obs'] += packed[o:o + stats['obs'].size].reshape(stats['obs'].shape); o += stats['obs'].size
+        return packed[o:]
+
     @staticmethod
     def _gt(a, b):
         """a > b with Python 2 ordering of None (None sorts below every number):
@@ -200,6 +276,8 @@ class MultitrackHmm(BaseHMM):
 
     def score_samples_batch(self, obs_list):
         """score_samples for many sequences in one device batch."""
+        if self._wide():
+            return [self._wide_score_samples(o) for o in obs_list]
         eng = self._engine()
         eng.upload_batch(obs_list)
         # basehmm.py:261-264: obs = np.asarray(obs) drops the TrackTable, so no
@@ -219,6 +297,14 @@ class MultitrackHmm(BaseHMM):
 
     def score(self, obs):
         """forward log-likelihood (basehmm.py:275-299)."""
+        if self._wide():
+            frame = self.emissionModel.allLogProbs(as_obs_array(obs))
+            T, N = frame.shape
+            fwd = np.zeros((T, N))
+            _strict_hmm._forward(T, N, self._log_startprob, self._log_transmat, frame, None, fwd)
+            lp = float(logsumexp(fwd[-1]))
+            self._note_forward_logprob(lp)
+            return lp
         eng = self._engine()
         eng.upload_batch([obs])
         lp = float(eng.score()[0])
@@ -229,6 +315,8 @@ class MultitrackHmm(BaseHMM):
         # basehmm.py:389-392: the model's own algorithm wins over the argument
         if self._algorithm in decoder_algorithms:
             algorithm = self._algorithm
+        if self._wide():
+            return [self._wide_decode(o, algorithm) for o in obs_list]
         eng = self._engine()
         ratios_dp = [self._seg_ratios(o) for o in obs_list] if algorithm == "viterbi" else None
         if algorithm in ("viterbi", "map") and (ratios_dp is None or all(r is None for r in ratios_dp)):
@@ -386,6 +474,8 @@ class MultitrackHmm(BaseHMM):
         """All sequences of this rank in one device batch; returns the per-sequence
         log-probabilities of the WHOLE job, in the caller's sequence order.
         Replaces basehmm.py:509-522 + hmm.py:545-574."""
+        if self._wide():
+            return self._wide_estep(obs, stats, params, n_total, slots)
         eng = self._engine()
         # the observations do not change between EM iterations: they cross PCIe once per fit()
         token = getattr(self, "_fit_batch_token", None)

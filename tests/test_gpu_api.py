@@ -201,3 +201,46 @@ def test_emission_model_api():
     assert stats[0][1][0] == 0.02 + 0.02
     assert stats[0][0][1] == 0.3
     assert stats[0][1][1] == 0.4
+
+
+def test_more_than_64_states_takes_the_strict_kernels(oracle):
+    """The batched kernels stop at 64 states; wider models run the reference's per-sequence flow on
+    the strict float64 kernels (MultitrackHmm._wide_*).  decode / score / score_samples / fit
+    against the oracle for a 70-state model."""
+    from test_host_logic import oracle_estep
+    from tehmm_b200 import synth
+    from tehmm_b200.emission import IndependentMultinomialEmissionModel
+    from tehmm_b200.hmm import MultitrackHmm
+    N, syms = 70, (5, 3, 9)
+    m = synth.make_model(N=N, syms=syms, seed=13)
+    seqs = [synth.sample_obs(m, T, seed=20 + i)[0] for i, T in enumerate([400, 1, 257])]
+
+    def model(**kw):
+        em = IndependentMultinomialEmissionModel(N, list(syms), zeroAsMissingData=True)
+        em.logProbs = m["table"].copy()
+        return MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy(), **kw), em
+
+    hmm, _ = model()
+    assert hmm._wide()
+    for obs in seqs:
+        ref = oracle.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+        lp, st = hmm.decode(obs)
+        assert_array_equal(st, ref["vit_states"])
+        assert lp == pytest.approx(ref["vit_logprob"], rel=1e-12)
+        assert hmm.score(obs) == pytest.approx(ref["logprob"], rel=1e-10)
+        lp2, post = hmm.score_samples(obs)
+        assert lp2 == pytest.approx(ref["logprob"], rel=1e-10)
+        assert_allclose(post.sum(axis=1), 1.0, rtol=1e-12)
+        sc, ms = model(algorithm="map")[0].decode(obs)
+        assert_array_equal(ms, ref["map_states"])
+        assert sc == pytest.approx(ref["map_score"], rel=1e-9)
+    # two EM iterations: strict-kernel E-step == oracle E-step
+    a, ema = model(n_iter=3, thresh=0.0)
+    a.fit(seqs)
+    b, emb = model(n_iter=3, thresh=0.0)
+    b._device_estep = lambda obs, stats, params, n_total, slots: oracle_estep(oracle)(b, obs, stats, params, n_total, slots)
+    b.fit(seqs)
+    assert_allclose(a.transmat_, b.transmat_, rtol=1e-9, atol=1e-300)
+    assert_allclose(a.startprob_, b.startprob_, rtol=1e-9, atol=1e-300)
+    assert_allclose(ema.getLogProbs(), emb.getLogProbs(), rtol=1e-9, atol=1e-300)
+    assert a.getLastLogProb() == pytest.approx(b.getLastLogProb(), rel=1e-10)
