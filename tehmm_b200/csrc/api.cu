@@ -451,10 +451,10 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     // needs as few table look-ups as possible within the shared-memory budget.  Greedy:
     // repeatedly merge the two groups whose merge adds the fewest rows.
     struct Grp { std::vector<int> trk; int64_t rows; };
-    auto make_groups = [&](int64_t row_budget, int max_groups, std::vector<Grp> &grp) -> int64_t {
+    auto make_groups = [&](int64_t row_budget, int max_groups, std::vector<Grp> &grp, bool wide_ok) -> int64_t {
         int64_t total_rows = 0;
         grp.clear();
-        if (NS != 1) return 0;
+        if (NS != 1 && !wide_ok) return 0;
         for (int k = 0; k < K; ++k) { grp.push_back(Grp{{k}, nsym[k]}); total_rows += nsym[k]; }
         for (;;) {
             int bi = -1, bj = -1;
@@ -491,12 +491,13 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
         }
     };
     std::vector<Grp> grp, sgrp;
-    const int64_t grows = make_groups(TEHMM_GROWS_MAX, TEHMM_GMAX, grp);
+    // 33..64 states: a merged row is 256 bytes, so half the rows fit (emission_merged_kernel<.., NS = 2>)
+    const int64_t grows = make_groups(TEHMM_GROWS_MAX / NS, TEHMM_GMAX, grp, true);
     // second grouping for the emission histograms (stats.cu): a merged row costs 256 bytes there
-    const int64_t srows = make_groups(TEHMM_SROWS_MAX, 8, sgrp);
+    const int64_t srows = make_groups(TEHMM_SROWS_MAX, 8, sgrp, false);
     const int SG = (int)sgrp.size();
     const int G = (int)grp.size();
-    size_t o_gtab = o_end, o_gc = align_up(o_gtab + (size_t)grows * 32 * 4);
+    size_t o_gtab = o_end, o_gc = align_up(o_gtab + (size_t)grows * NP * 4);
     size_t o_gd = align_up(o_gc + (size_t)grows * 8), o_sgd = align_up(o_gd + (size_t)std::max(G, 1) * TEHMM_GDESC * 4);
     size_t total = align_up(o_sgd + (size_t)std::max(SG, 1) * TEHMM_GDESC * 4);
     std::vector<unsigned char> h(total, 0);
@@ -531,7 +532,7 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
                 for (int j = 0; j < N; ++j) { acc[j] *= normalize; mx = std::max(mx, acc[j]); }
                 if (!(mx > -INFINITY)) mx = 0.0;
                 gc[base + row] = mx;
-                for (int j = 0; j < 32; ++j) gtab[(size_t)(base + row) * 32 + j] = j < N ? (float)(acc[j] - mx) : -INFINITY;   // padding never wins a maximum
+                for (int j = 0; j < NP; ++j) gtab[(size_t)(base + row) * NP + j] = j < N ? (float)(acc[j] - mx) : -INFINITY;   // padding never wins a maximum
             }
             base += gr.rows;
         }

@@ -265,11 +265,21 @@ backward_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const T *__restrict
                 // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
                 T best;
                 int arg;
-                if (sizeof(T) == 4 && NS == 1) {
+                if (sizeof(T) == 4) {
                     // posteriors are >= 0: their bit patterns order like the values
-                    const unsigned bits = own[0] ? __float_as_uint((float)g[0]) : 0u;
-                    const unsigned mx = __reduce_max_sync(TEHMM_FULL, bits);
-                    arg = __ffs(__ballot_sync(TEHMM_FULL, bits == mx)) - 1;
+                    unsigned bits[NS], mxl = 0u;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        bits[s] = own[s] ? __float_as_uint((float)g[s]) : 0u;
+                        mxl = max(mxl, bits[s]);
+                    }
+                    const unsigned mx = __reduce_max_sync(TEHMM_FULL, mxl);
+                    arg = -1;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {       // lowest state among the maxima
+                        const unsigned vote = __ballot_sync(TEHMM_FULL, bits[s] == mx);
+                        if (arg < 0 && vote) arg = 32 * s + __ffs(vote) - 1;
+                    }
                     best = (T)__uint_as_float(mx);
                 } else {
                     best = g[0];

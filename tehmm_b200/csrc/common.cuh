@@ -49,9 +49,9 @@ struct TehmmModelDev {
     // tracks are grouped, a group's table has one row per COMBINATION of its
     // tracks' symbols, holding normalize * sum of the tracks' log-probs, split
     // into the row's maximum over states (gc, float64) and the remainder
-    // (gtab, float32, <= 0, 32 floats per row).  G = 0: not available.
+    // (gtab, float32, <= 0, NP = 32 * NS floats per row).  G = 0: not available.
     int G, grows;
-    const float *gtab;          // [grows][32]
+    const float *gtab;          // [grows][NP]
     const double *gc;           // [grows]
     const int32_t *gdesc;       // [G][TEHMM_GDESC]: ntracks, first row, track[4], stride[4]
     // Merged rows of the emission HISTOGRAMS (stats.cu, emission_stats_merged_kernel): the same

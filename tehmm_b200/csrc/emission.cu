@@ -194,8 +194,10 @@ __device__ __forceinline__ void emg_flag_row(int64_t t, const int64_t *seq_off, 
     seq_flag[lo] = 1;
 }
 
-// GT = number of groups when 1..8 (look-ups fully unrolled), 0 = any (loop)
-template <typename OBS, int GT, bool RATIO>
+// GT = number of groups when 1..8 (look-ups fully unrolled), 0 = any (loop).
+// NS = 1: N <= 32 (LD = 32); NS = 2: 33..64 states (LD = N, table rows of 64 floats,
+// lane owns columns lane and lane + 32).
+template <typename OBS, int GT, bool RATIO, int NS>
 __global__ void __launch_bounds__(EMG_WARPS * 32, 1)
 emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                        const double *__restrict__ ratios, float *__restrict__ elog,
@@ -206,18 +208,20 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = m.K, N = m.N, LD = m.LD;
     const int G = GT ? GT : m.G;
+    constexpr int NP = 32 * NS;
+    constexpr int ROWB = NP * 4;            // bytes of a merged table row
+    constexpr int ROWSH = NS == 1 ? 7 : 8;  // log2(ROWB)
     // layout: gtab | gc | gdesc | nsym | per warp { csum[16], offs[16][16] }
     float *tab_s = reinterpret_cast<float *>(em_smem);
-    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * 32);
+    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * NP);
     int32_t *gd_s = reinterpret_cast<int32_t *>(gc_s + m.grows);
     int32_t *nsym_s = gd_s + TEHMM_GMAX * TEHMM_GDESC;
     const size_t per_warp = (size_t)EMG_ROWS * 8 + (size_t)EMG_ROWS * 16 * 4;
-    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
+    const size_t head = ((size_t)m.grows * (ROWB + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
     unsigned char *wbase = em_smem + head + (size_t)warp * per_warp;
-    double *csum_s = reinterpret_cast<double *>(wbase);
     int32_t *offs = reinterpret_cast<int32_t *>(wbase + EMG_ROWS * 8);
 
-    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * 32; e += blockDim.x) tab_s[e] = m.gtab[e];
+    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * NP; e += blockDim.x) tab_s[e] = m.gtab[e];
     for (int e = threadIdx.x; e < m.grows; e += blockDim.x) gc_s[e] = m.gc[e];
     for (int e = threadIdx.x; e < G * TEHMM_GDESC; e += blockDim.x) gd_s[e] = m.gdesc[e];
     for (int e = threadIdx.x; e < K; e += blockDim.x) nsym_s[e] = m.track_nsym[e];
@@ -226,11 +230,14 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
     // shared-space address of this lane's column of table row 0; offs holds byte offsets of rows
     const uint32_t lane_tab = (uint32_t)__cvta_generic_to_shared(tab_s) + (uint32_t)lane * 4u;
     const uint32_t offs_a = (uint32_t)__cvta_generic_to_shared(offs);
-    const bool is_state = lane < N;
+    bool is_state[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) is_state[s] = lane + 32 * s < N;
 
     // state-dependent part of row r of the staged batch: sum of the groups' table rows (all <= 0)
-    auto gather = [&](int r) -> float {
-        float v = 0.f;
+    auto gather = [&](int r, float (&v)[NS]) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) v[s] = 0.f;
         if (GT) {
             int o[8];
             asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(offs_a + r * 64));
@@ -238,32 +245,43 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
                 asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]) : "r"(offs_a + r * 64 + 16));
 #pragma unroll
             for (int gq = 0; gq < GT; ++gq) {
-                float x;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)o[gq]));
-                v += x;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    float x;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)o[gq] + 128u * s));
+                    v[s] += x;
+                }
             }
         } else {
             for (int gq = 0; gq < G; ++gq) {
-                float x;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)offs[r * 16 + gq]));
-                v += x;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    float x;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(lane_tab + (uint32_t)offs[r * 16 + gq] + 128u * s));
+                    v[s] += x;
+                }
             }
         }
-        return v;
     };
-    // normalised row out; returns the maximum over states taken out of v
-    auto emit_row = [&](float *pe, float *pb, float v, float rf) -> float {
+    // normalised row out (pe / pb: this lane's first column of the row); returns the maximum
+    // over states taken out of v
+    auto emit_row = [&](float *pe, float *pb, const float (&v)[NS], float rf) -> float {
         // v <= 0 everywhere: the bit patterns of non-positive floats grow with the magnitude,
         // so the maximum is the unsigned minimum (+0.0 = 0 included; -inf is the largest)
-        const unsigned bits = is_state ? __float_as_uint(v) : 0xff800000u;
+        unsigned bits = 0xff800000u;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) bits = min(bits, is_state[s] ? __float_as_uint(v[s]) : 0xff800000u);
         const float Mf = __uint_as_float(__reduce_min_sync(TEHMM_FULL, bits));
-        float d = Mf > -INFINITY ? v - Mf : 0.f;
-        if (RATIO) d *= rf;
-        float bl = __expf(d);
-        if (!is_state) { d = 0.f; bl = 0.f; }          // padding columns
-        if (lane < LD) {
-            if (pe) *pe = d;
-            if (pb) *pb = bl;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            float d = Mf > -INFINITY ? v[s] - Mf : 0.f;
+            if (RATIO) d *= rf;
+            float bl = __expf(d);
+            if (!is_state[s]) { d = 0.f; bl = 0.f; }          // padding columns
+            if (lane + 32 * s < LD) {
+                if (pe) pe[32 * s] = d;
+                if (pb) pb[32 * s] = bl;
+            }
         }
         return Mf;
     };
@@ -286,7 +304,7 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
                 bad |= (unsigned)sym >= (unsigned)nsym_s[k];
                 idx += sym * d[6 + i];
             }
-            offs[r * 16 + gq] = idx * 128;
+            offs[r * 16 + gq] = idx * ROWB;
         }
         const bool any_slow = __any_sync(TEHMM_FULL, bad);
         __syncwarp();
@@ -295,7 +313,7 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
         if (!any_slow) {
             if (lane < rows) {
                 double c = 0.0;
-                for (int gq = 0; gq < G; ++gq) c += gc_s[offs[lane * 16 + gq] >> 7];
+                for (int gq = 0; gq < G; ++gq) c += gc_s[offs[lane * 16 + gq] >> ROWSH];
                 c_keep = c;
             }
             float *pe = elog ? elog + tb * LD + lane : nullptr;
@@ -303,7 +321,9 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
             if (rows == EMG_ROWS) {
 #pragma unroll
                 for (int r = 0; r < EMG_ROWS; r += 2) {          // two rows in flight
-                    const float v0 = gather(r), v1 = gather(r + 1);
+                    float v0[NS], v1[NS];
+                    gather(r, v0);
+                    gather(r + 1, v1);
                     const float r0 = RATIO ? (float)ratios[tb + r] : 1.f, r1 = RATIO ? (float)ratios[tb + r + 1] : 1.f;
                     const float M0 = emit_row(pe ? pe + r * LD : nullptr, pb ? pb + r * LD : nullptr, v0, r0);
                     const float M1 = emit_row(pe ? pe + (r + 1) * LD : nullptr, pb ? pb + (r + 1) * LD : nullptr, v1, r1);
@@ -312,7 +332,9 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
                 }
             } else {
                 for (int r = 0; r < rows; ++r) {
-                    const float Mr = emit_row(pe ? pe + r * LD : nullptr, pb ? pb + r * LD : nullptr, gather(r),
+                    float v[NS];
+                    gather(r, v);
+                    const float Mr = emit_row(pe ? pe + r * LD : nullptr, pb ? pb + r * LD : nullptr, v,
                                               RATIO ? (float)ratios[tb + r] : 1.f);
                     if (lane == r) mf_keep = Mr;
                 }
@@ -321,13 +343,21 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
             // a symbol outside its track's table: index the dense float64 table exactly as the
             // reference does (rare)
             for (int r = 0; r < rows; ++r) {
-                double v = 0.0;
-                if (is_state)
-                    for (int k = 0; k < K; ++k) v += m.table[((int64_t)k * N + lane) * m.S + (int64_t)obs[(tb + r) * K + k]];
-                v *= m.normalize;
-                const double M = warp_max(is_state ? v : -INFINITY);
+                double v[NS], vm = -INFINITY;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    v[s] = 0.0;
+                    if (is_state[s])
+                        for (int k = 0; k < K; ++k) v[s] += m.table[((int64_t)k * N + lane + 32 * s) * m.S + (int64_t)obs[(tb + r) * K + k]];
+                    v[s] *= m.normalize;
+                    if (is_state[s]) vm = fmax(vm, v[s]);
+                }
+                const double M = warp_max(vm);
+                float vf[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) vf[s] = M > -INFINITY ? (float)(v[s] - M) : 0.f;
                 emit_row(elog ? elog + (tb + r) * LD + lane : nullptr, blin ? blin + (tb + r) * LD + lane : nullptr,
-                         M > -INFINITY ? (float)(v - M) : 0.f, RATIO ? (float)ratios[tb + r] : 1.f);
+                         vf, RATIO ? (float)ratios[tb + r] : 1.f);
                 if (lane == r) { mf_keep = 0.f; c_keep = M; }
             }
         }
@@ -344,23 +374,23 @@ emission_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t tot
 static size_t emg_smem_bytes(const TehmmModelDev &m)
 {
     const size_t per_warp = (size_t)EMG_ROWS * 8 + (size_t)EMG_ROWS * 16 * 4;
-    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
+    const size_t head = ((size_t)m.grows * (128 * m.NS + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
     return head + EMG_WARPS * per_warp;
 }
 
-template <typename OBS, int GT, bool RATIO>
+template <typename OBS, int GT, bool RATIO, int NS>
 static cudaError_t launch_emg3(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                const double *ratios, float *elog, float *blin, double *rowmax,
                                int *seq_flag, int sms)
 {
     const size_t smem = emg_smem_bytes(m);
-    cudaError_t e = cudaFuncSetAttribute(emission_merged_kernel<OBS, GT, RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(emission_merged_kernel<OBS, GT, RATIO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t need = ((b.total + EMG_ROWS - 1) / EMG_ROWS + EMG_WARPS - 1) / EMG_WARPS;
     if (need < 1) need = 1;
     const int grid = (int)(need < sms ? need : sms);
-    emission_merged_kernel<OBS, GT, RATIO><<<grid, EMG_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
-                                                                               rowmax, seq_flag, b.seq_off, b.nseq);
+    emission_merged_kernel<OBS, GT, RATIO, NS><<<grid, EMG_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, b.total, ratios, elog, blin,
+                                                                                   rowmax, seq_flag, b.seq_off, b.nseq);
     return cudaGetLastError();
 }
 
@@ -369,8 +399,9 @@ static cudaError_t launch_emg(cudaStream_t st, const TehmmModelDev &m, const Teh
                               const double *ratios, float *elog, float *blin, double *rowmax,
                               int *seq_flag, int sms)
 {
-#define EMG_GO(GT) (ratios ? launch_emg3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms) \
-                           : launch_emg3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms))
+#define EMG_GO1(GT, NS_) (ratios ? launch_emg3<OBS, GT, true, NS_>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms) \
+                                 : launch_emg3<OBS, GT, false, NS_>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms))
+#define EMG_GO(GT) (m.NS == 1 ? EMG_GO1(GT, 1) : EMG_GO1(GT, 2))
     switch (m.G) {
     case 1: return EMG_GO(1);
     case 2: return EMG_GO(2);
@@ -383,6 +414,7 @@ static cudaError_t launch_emg(cudaStream_t st, const TehmmModelDev &m, const Teh
     default: return EMG_GO(0);
     }
 #undef EMG_GO
+#undef EMG_GO1
 }
 
 // ---------------------------------------------------------------------------

@@ -196,6 +196,49 @@ def test_wide_model_50_states(oracle):
     assert_allclose(st["obs"], ob, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("N", [33, 50, 64])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_wide_emission_merged_tables(oracle, N, dtype):
+    """33..64 states, float32: the merged-table emission kernel with 64-float rows
+    (emission_merged_kernel<.., NS = 2>) against _emission.pyx:20-144 -- elog + rowmax must
+    give the reference frame, blin = exp(elog); also with an out-of-table symbol in the
+    batch (dense float64 table fallback) and with segment ratios."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=N, seed=300 + N)
+    lens = [700, 1, 37, 1200]
+    obs = [synth.sample_obs(m, T, seed=310 + i, dtype=dtype)[0] for i, T in enumerate(lens)]
+    # a symbol beyond its track's table but inside the dense table's width (log-prob LOGZERO rows exist there)
+    k_small = int(np.argmin(m["syms"]))
+    if m["syms"][k_small] + 1 < m["table"].shape[2]:
+        obs[3][600, k_small] = m["syms"][k_small] + 1
+    rng = np.random.RandomState(5)
+    ratios = [np.where(rng.rand(T) < 0.3, rng.uniform(1.0, 3.0, size=T), 1.0) for T in lens]
+    eng = engine(chunk_tiles=4, warmup=64)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    prec, tdt = eng._prec("f32")
+    LD = eng.LD
+    for use_ratios in (False, True):
+        d_r = eng.upload_ratios(ratios) if use_ratios else None
+        elog, blin, rowmax = eng.run_emission(prec, tdt, d_r, True, True)
+        elog = elog.cpu().numpy().reshape(-1, LD)[:, :N].astype(np.float64)
+        blin = blin.cpu().numpy().reshape(-1, LD)[:, :N].astype(np.float64)
+        rowmax = rowmax.cpu().numpy()
+        a = 0
+        for o, r in zip(obs, ratios):
+            T = o.shape[0]
+            frame = np.zeros((T, N))
+            oracle.fastAllLogProbs(o, m["table"], frame, 1.0, r if use_ratios else None)
+            got = elog[a:a + T] + rowmax[a:a + T, None]
+            live = frame > -1e50                     # LOGZERO entries: only "far below the maximum" matters
+            assert_allclose(got[live], frame[live], rtol=2e-6, atol=2e-5)
+            assert np.all(got[~live] < -1e30) or np.all(elog[a:a + T][~live] < -80)
+            # the maximum taken out: float32 merged-table rounding (6e-8 relative) on top of the float64 common part
+            assert_allclose(rowmax[a:a + T], frame.max(axis=1), rtol=1e-6, atol=2e-5)
+            assert_allclose(blin[a:a + T], np.exp(elog[a:a + T]), rtol=2e-6, atol=1e-30)
+            a += T
+
+
 def test_f32_vs_f64_at_scale():
     """T = 2e6 (oracle would take minutes): float32 production path against the
     float64 verification path on the GPU, plus size-independent invariants."""
