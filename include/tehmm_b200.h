@@ -99,7 +99,8 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
  * "umma_passes" counts its launches), "xi_tile" (0 = expected transition
  * counts by the one-chunk-per-warp backward kernel instead of the tensor-core
  * xi kernel), "timing" (1 = bracket the first
- * launch of each main kernel with CUDA events on the context's stream).
+ * launch of each main kernel with CUDA events on the context's stream), "defer" (see
+ * tehmm_ctx_check).
  * stats: "launches", "chunks", "fine_chunks", "repaired_chunks_<pass>",
  * "repair_passes_<pass>", "tile_passes", and with "timing" the mean duration in
  * microseconds (over the launches since "timing" was set, at most 32) of "us_emission", "us_forward", "us_backward",
@@ -107,6 +108,15 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
  * (blocks until that launch has finished; -1 if it never ran). */
 int tehmm_ctx_set_option(tehmm_ctx *ctx, const char *name, int64_t value);
 int64_t tehmm_ctx_get_stat(tehmm_ctx *ctx, const char *name);
+/* Deferred verification.  With option "defer" = 1 the tehmm_run_* calls do not stall the
+ * stream after each stage to read how many chunk boundaries failed verification (the
+ * speculate / verify / repair scheme that replaces the serial recursions of
+ * _hmm.pyx:120-259): the count goes to a pinned slot behind the queued kernels and the
+ * call carries on as if nothing had to be repaired.  tehmm_ctx_check waits for the stream
+ * and returns in *unverified the number of failed boundaries since the last check: 0 =
+ * every result stands (the common case); > 0 = recompute those results with "defer" = 0
+ * (tehmm_decode_host does both steps itself).  Stats: "deferred_checks", "deferred_bad". */
+int tehmm_ctx_check(tehmm_ctx *ctx, int64_t *unverified);
 
 /* ------------------------------------------------------------------ L0 strict
  * obs is (T,K) row-major, obs_bytes = 1 (uint8), 2 (uint16) or 4 (int32)

@@ -38,6 +38,7 @@ SIGNATURES = {
     "tehmm_ctx_launch_count": (_c_i64, [_c_void]),
     "tehmm_ctx_set_option": (_c_int, [_c_void, ctypes.c_char_p, _c_i64]),
     "tehmm_ctx_get_stat": (_c_i64, [_c_void, ctypes.c_char_p]),
+    "tehmm_ctx_check": (_c_int, [_c_void, ctypes.POINTER(_c_i64)]),
     "tehmm_strict_all_log_probs": (_c_int, [_c_void, _c_void, _c_int, _c_i64, _c_int, _c_void, _c_int, _c_int, _c_void, _c_dbl, _c_void]),
     "tehmm_strict_forward": (_c_int, [_c_void, _c_i64, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_strict_backward": (_c_int, [_c_void, _c_i64, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void]),
@@ -149,6 +150,26 @@ class Context(object):
 
     def stat(self, name):
         return int(self.lib.tehmm_ctx_get_stat(self.handle, name.encode()))
+
+    def check(self):
+        """deferred verification (option "defer"): wait for the stream; number of chunk
+        boundaries that failed verification since the last check (0 = results stand)"""
+        n = _c_i64(0)
+        check(self.lib.tehmm_ctx_check(self.handle, ctypes.byref(n)))
+        return int(n.value)
+
+    def optimistic(self, fn):
+        """run fn() with deferred verification; if any boundary failed, run it again with the
+        synchronous verify / repair loop.  fn must be a pure function of device state it does
+        not overwrite (every engine pass is)."""
+        self.set_option("defer", 1)
+        try:
+            out = fn()
+        finally:
+            self.set_option("defer", 0)
+        if self.check() != 0:
+            out = fn()
+        return out
 
     @property
     def launches(self):

@@ -72,6 +72,7 @@ struct DevBuf {   // RAII device allocation for the strict host-pointer entry po
 };
 
 #define TEHMM_TRING 32
+#define TEHMM_NPENDING 64
 enum { TK_EMISSION, TK_FORWARD, TK_BACKWARD, TK_VITERBI_DP, TK_TRACEBACK, TK_RESCORE, TK_STATS, TK_XI, TEHMM_NTIMED };
 static const char *const tk_names[TEHMM_NTIMED] = {"us_emission", "us_forward", "us_backward", "us_viterbi_dp",
                                                     "us_traceback", "us_rescore", "us_emission_stats", "us_xi"};
@@ -97,6 +98,12 @@ struct tehmm_ctx {
     int64_t stat_tile_passes = 0;
     int64_t stat_bad_fwd = 0, stat_bad_bwd = 0, stat_bad_vit = 0, stat_bad_tb = 0, stat_repair_tb = 0;
     int *h_nbad = nullptr;            // pinned
+    // option "defer": the verification count of a pass is copied to a pinned slot and read at the
+    // next tehmm_ctx_check instead of stalling the stream after every stage (api: tehmm_ctx_check)
+    int64_t opt_defer = 0;
+    int *h_pending = nullptr;         // pinned, TEHMM_NPENDING slots
+    int npending = 0;
+    int64_t stat_deferred_checks = 0, stat_deferred_bad = 0;
     // model
     bool has_model = false;
     TehmmModelDev m{};
@@ -143,6 +150,7 @@ int tehmm_ctx_create(int device, tehmm_ctx **out)
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaMallocHost((void **)&c->h_nbad, 2 * sizeof(int)));
+    CU(cudaMallocHost((void **)&c->h_pending, TEHMM_NPENDING * sizeof(int)));
     CU(cudaMalloc((void **)&c->d_fault, sizeof(int)));
     CU(cudaMemset(c->d_fault, 0, sizeof(int)));
     *out = c;
@@ -159,6 +167,7 @@ int tehmm_ctx_destroy(tehmm_ctx *c)
     if (c->batch_blob) cudaFree(c->batch_blob);
     if (c->d_seq_flag) cudaFree(c->d_seq_flag);
     if (c->h_nbad) cudaFreeHost(c->h_nbad);
+    if (c->h_pending) cudaFreeHost(c->h_pending);
     if (c->d_fault) cudaFree(c->d_fault);
     for (int i = 0; i < TEHMM_NTIMED; ++i)
         for (int r = 0; r < TEHMM_TRING; ++r)
@@ -201,6 +210,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
     else if (!strcmp(name, "umma")) c->opt_umma = v;
     else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
+    else if (!strcmp(name, "defer")) c->opt_defer = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -218,6 +228,8 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "repaired_chunks_traceback")) return c->stat_bad_tb;
     if (!strcmp(name, "repair_passes_traceback")) return c->stat_repair_tb;
     if (!strcmp(name, "sms")) return c->sms;
+    if (!strcmp(name, "deferred_checks")) return c->stat_deferred_checks;
+    if (!strcmp(name, "deferred_bad")) return c->stat_deferred_bad;
     if (!strcmp(name, "chunks")) return c->has_batch ? c->b.nchunks : 0;
     if (!strcmp(name, "fine_chunks")) return c->has_batch ? c->bf.nchunks : 0;
     if (!strcmp(name, "tile_passes")) return c->stat_tile_passes;
@@ -780,11 +792,37 @@ static void tk_end(tehmm_ctx *c, int which)
     c->ev_n[which] += 1;
 }
 
-static int read_nbad(tehmm_ctx *c, const int *d_nbad, int *out)
+static int read_nbad(tehmm_ctx *c, const int *d_nbad, int *out, bool may_defer = true)
 {
+    if (may_defer && c->opt_defer && c->npending < TEHMM_NPENDING) {
+        // optimistic: the count travels to a pinned slot behind the kernels already queued and
+        // the caller carries on as if nothing had to be repaired; tehmm_ctx_check tells
+        CU(cudaMemcpyAsync(c->h_pending + c->npending, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        c->npending += 1;
+        *out = 0;
+        return TEHMM_OK;
+    }
     CU(cudaMemcpyAsync(c->h_nbad, d_nbad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     *out = *c->h_nbad;
+    return TEHMM_OK;
+}
+
+// Deferred verification (option "defer"): waits for the stream and returns in *unverified the
+// number of chunks whose speculated boundary failed verification in any pass run since the last
+// check.  0: every result produced since then stands.  > 0: those results must be recomputed
+// with the option off (the synchronous verify / repair loop); nothing else is invalidated.
+int tehmm_ctx_check(tehmm_ctx *c, int64_t *unverified)
+{
+    if (!c || !unverified) return fail(TEHMM_EINVAL, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    int64_t n = 0;
+    for (int i = 0; i < c->npending; ++i) n += c->h_pending[i];
+    c->stat_deferred_checks += c->npending;
+    c->stat_deferred_bad += n;
+    c->npending = 0;
+    *unverified = n;
     return TEHMM_OK;
 }
 
@@ -899,7 +937,7 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
         c->launches += 1;
         int nb = 0;
         if (umma_used && pass == 0) CU(cudaMemcpyAsync(c->h_nbad + 1, c->d_fault, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (read_nbad(c, nbad, &nb, !umma_used)) return TEHMM_ECUDA;
         if (umma_used && pass == 0 && c->h_nbad[1]) {
             CU(cudaMemsetAsync(c->d_fault, 0, sizeof(int), st));
             return fail(TEHMM_ECUDA, "fwd_umma_kernel: a barrier wait timed out (tensor-memory protocol fault)");

@@ -142,6 +142,7 @@ struct HostPipe {
     size_t pin_out_bytes = 0;
     Pool *pool = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int64_t redone = 0;                     // calls whose deferred verification failed and ran twice
 
     ~HostPipe()
     {
@@ -376,59 +377,76 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     p->h2d_bytes = (int64_t)obs_bytes_total;
     tr.mark("h2d+emission", true);
 
-    // ---- the trellis
-    if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
-    if (viterbi) {
-        HOK(tehmm_run_viterbi(c, prec, A + o_la, nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
-    } else {
-        HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
-        HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_la, A + o_lb, nullptr, nullptr,
-                               d_states, d_sc, nullptr, A + o_scratch));
-    }
-
-    tr.mark("trellis", true);
-    // ---- device -> host: one byte per step over PCIe, widened by the host's cores
-    const size_t out_bytes = up256((size_t)total) + (size_t)nseq * 16;
-    if (p->pin_out_bytes < out_bytes) {
-        HCU(cudaStreamSynchronize(st));
-        if (p->pin_out) cudaFreeHost(p->pin_out);
-        p->pin_out = nullptr; p->pin_out_bytes = 0;
-        HCU(cudaMallocHost((void **)&p->pin_out, out_bytes + out_bytes / 8));
-        p->pin_out_bytes = out_bytes + out_bytes / 8;
-    }
-    double *pin_lp = (double *)(p->pin_out + up256((size_t)total));
-    HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 16, cudaMemcpyDeviceToHost, st));
-    // slices, so that the widening of slice i overlaps the transfer of slice i+1
-    const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
-    const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
-    while ((int)p->slice_ev.size() < nsl) {            // the upload's events are long complete: reuse them
-        cudaEvent_t ev;
-        HCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        p->slice_ev.push_back(ev);
-    }
-    const std::vector<cudaEvent_t> &evs = p->slice_ev;
-    for (int i = 0; i < nsl; ++i) {
-        const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
-        if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
-        HCU(cudaEventRecord(evs[i], st));
-    }
+    // Two attempts at most.  The first runs the stages with deferred verification (option "defer":
+    // no stall of the stream after each stage to read the repair count); the counts are looked at
+    // once everything has arrived.  If a speculated chunk boundary failed -- rare -- the trellis and
+    // the download run again with the synchronous verify / repair loop.
+    struct DeferGuard { tehmm_ctx *c; ~DeferGuard() { tehmm_ctx_set_option(c, "defer", 0); } } defer_guard{c};
+    double *pin_lp = nullptr;
     int rc = TEHMM_OK;
-    for (int i = 0; i < nsl; ++i) {
-        const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
-        cudaError_t e = cudaEventSynchronize(evs[i]);
-        if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
-        if (n <= 0 || rc != TEHMM_OK) continue;
-        const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
-        const uint8_t *src = p->pin_out + a;
-        int64_t *dst = h_states + a;
-        p->pool->parallel_for(nth, [&](int t) {
-            const int64_t b0 = (int64_t)t * per;
-            if (b0 < n) widen_u8_i64(src + b0, dst + b0, std::min(per, n - b0));
-        });
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        HOK(tehmm_ctx_set_option(c, "defer", attempt == 0 ? 1 : 0));
+        // ---- the trellis
+        if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
+        if (viterbi) {
+            HOK(tehmm_run_viterbi(c, prec, A + o_la, nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
+        } else {
+            HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
+            HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_la, A + o_lb, nullptr, nullptr,
+                                   d_states, d_sc, nullptr, A + o_scratch));
+        }
+
+        tr.mark("trellis", true);
+        // ---- device -> host: one byte per step over PCIe, widened by the host's cores
+        const size_t out_bytes = up256((size_t)total) + (size_t)nseq * 16;
+        if (p->pin_out_bytes < out_bytes) {
+            HCU(cudaStreamSynchronize(st));
+            if (p->pin_out) cudaFreeHost(p->pin_out);
+            p->pin_out = nullptr; p->pin_out_bytes = 0;
+            HCU(cudaMallocHost((void **)&p->pin_out, out_bytes + out_bytes / 8));
+            p->pin_out_bytes = out_bytes + out_bytes / 8;
+        }
+        pin_lp = (double *)(p->pin_out + up256((size_t)total));
+        HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 16, cudaMemcpyDeviceToHost, st));
+        // slices, so that the widening of slice i overlaps the transfer of slice i+1
+        const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
+        const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
+        while ((int)p->slice_ev.size() < nsl) {            // the upload's events are long complete: reuse them
+            cudaEvent_t ev;
+            HCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            p->slice_ev.push_back(ev);
+        }
+        const std::vector<cudaEvent_t> &evs = p->slice_ev;
+        for (int i = 0; i < nsl; ++i) {
+            const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+            if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
+            HCU(cudaEventRecord(evs[i], st));
+        }
+        rc = TEHMM_OK;
+        for (int i = 0; i < nsl; ++i) {
+            const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+            cudaError_t e = cudaEventSynchronize(evs[i]);
+            if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
+            if (n <= 0 || rc != TEHMM_OK) continue;
+            const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
+            const uint8_t *src = p->pin_out + a;
+            int64_t *dst = h_states + a;
+            p->pool->parallel_for(nth, [&](int t) {
+                const int64_t b0 = (int64_t)t * per;
+                if (b0 < n) widen_u8_i64(src + b0, dst + b0, std::min(per, n - b0));
+            });
+        }
+        if (rc != TEHMM_OK) return rc;
+        HCU(cudaStreamSynchronize(st));
+        tr.mark("d2h+widen", false);
+        if (attempt == 0) {
+            int64_t unverified = 0;
+            HOK(tehmm_ctx_set_option(c, "defer", 0));
+            HOK(tehmm_ctx_check(c, &unverified));
+            if (unverified == 0) break;
+            p->redone += 1;
+        }
     }
-    if (rc != TEHMM_OK) return rc;
-    HCU(cudaStreamSynchronize(st));
-    tr.mark("d2h+widen", false);
     memcpy(h_logprob, pin_lp, (size_t)nseq * 8);
     if (h_score) memcpy(h_score, pin_lp + nseq, (size_t)nseq * 8);
     p->d2h_bytes = (int64_t)total + nseq * 16;

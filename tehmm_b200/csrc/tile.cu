@@ -703,6 +703,51 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             stage_commit();
         };
 
+        // Posterior output of ONE clock from its products pr = alpha_t .* beta'_t (both tile rows packed).
+        // Called one clock late (`back` = 1: the output pointers have moved on by one row), between the
+        // issue of the next clock's MMAs and the first use of their accumulators: the shuffles, the
+        // reciprocal, the arg-max and the stores then overlap the tensor-core latency instead of adding to it.
+        u64 prq[8];
+        bool actq[2] = {false, false}, pend = false;
+        auto post_out = [&](const u64 (&pr)[8], const bool (&actr)[2], int back) {
+            u64 zs = 0ull;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) zs = fadd2(zs, pr[c]);
+            const float Z0 = quad_sum(lo2(zs)), Z1 = quad_sum(hi2(zs));
+            const float invZ[2] = {__frcp_rn(Z0), __frcp_rn(Z1)};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const bool act = actr[r];
+                float p[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) p[c] = r ? hi2(pr[c]) : lo2(pr[c]);
+                if constexpr (want_map) {
+                    // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
+                    const float best = quad_max(fmaxf(fmax3(fmax3(p[0], p[1], p[2]), p[3], p[4]), fmax3(p[5], p[6], p[7])));
+                    int idx = 99;
+#pragma unroll
+                    for (int i = 7; i >= 0; --i)
+                        if (p[i] == best) idx = 8 * q + i;
+                    idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
+                    idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
+                    if (act && q == 0) {
+                        mp_[r][back] = (uint8_t)(idx < N ? idx : 0);
+                        const float bg = best * invZ[r];
+                        mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
+                    }
+                }
+                if constexpr (want_post) {
+                    float gv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        gv[i] = p[i] * invZ[r];
+                        if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf * ones[i];   // padding stays zero
+                    }
+                    store_row8(pp_[r] + (int64_t)back * LD, act, gv);
+                }
+            }
+        };
+
 #pragma unroll
         for (int v = 0; v < BWD_STAGES - 1; ++v) issue(kb + v, v);
         int rs = 0, ws = BWD_STAGES - 1;
@@ -750,6 +795,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             }
             float acc[4][4];
             tile_matmul(wp, A, acc);
+            if (pend) post_out(prq, actq, 1);        // the previous clock's posterior, behind this clock's MMAs
             float m0 = 0.f, m1 = 0.f;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
@@ -773,47 +819,14 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 scale_of(quad_max(m1), scp[1], dummy);
             }
             if (k >= W) {
-                // posterior of time t: gamma = alpha_t .* beta'_t / Z
-                u64 pr[8];
-                u64 zs = 0ull;
+                // posterior of time t: gamma = alpha_t .* beta'_t / Z.  Only the products are formed
+                // here; the reductions, the arg-max and the stores of this clock are issued behind
+                // the NEXT clock's MMAs (post_out above), off the recursion's critical path.
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    pr[c] = fmul2(up[c], pk2(at[0][c], at[1][c]));
-                    zs = fadd2(zs, pr[c]);
-                }
-                const float Z0 = quad_sum(lo2(zs)), Z1 = quad_sum(hi2(zs));
-                const float invZ[2] = {__frcp_rn(Z0), __frcp_rn(Z1)};
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const bool act = k < ke[r];
-                    float p[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) p[c] = r ? hi2(pr[c]) : lo2(pr[c]);
-                    if constexpr (want_map) {
-                        // argmax with the lowest state winning ties (np.argmax, basehmm.py:357)
-                        const float best = quad_max(fmaxf(fmax3(fmax3(p[0], p[1], p[2]), p[3], p[4]), fmax3(p[5], p[6], p[7])));
-                        int idx = 99;
-#pragma unroll
-                        for (int i = 7; i >= 0; --i)
-                            if (p[i] == best) idx = 8 * q + i;
-                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
-                        idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
-                        if (act && q == 0) {
-                            *mp_[r] = (uint8_t)(idx < N ? idx : 0);
-                            const float bg = best * invZ[r];
-                            mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
-                        }
-                    }
-                    if constexpr (want_post) {
-                        float gv[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            gv[i] = p[i] * invZ[r];
-                            if (renorm) gv[i] = (gv[i] + eps32) * renorm_invf * ones[i];   // padding stays zero
-                        }
-                        store_row8(pp_[r], act, gv);
-                    }
-                }
+                for (int c = 0; c < 8; ++c) prq[c] = fmul2(up[c], pk2(at[0][c], at[1][c]));
+                actq[0] = k < ke[0];
+                actq[1] = k < ke[1];
+                pend = true;
             } else if (k == W - 1 && mode == 0) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
@@ -834,6 +847,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             ws = ws + 1 == BWD_STAGES ? 0 : ws + 1;
         }
         stage_wait<0>();
+        if (pend) post_out(prq, actq, 1);            // the last clock's posterior
         if constexpr (want_map) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)

@@ -384,7 +384,8 @@ class Engine(object):
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
         _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
-        _, logprob = self.run_forward(prec, tdt, blin, rowmax, d_rd, want_alpha=False)
+        # deferred verification (tehmm_ctx_check): one wait per call instead of one per stage
+        _, logprob = self.ctx.optimistic(lambda: self.run_forward(prec, tdt, blin, rowmax, d_rd, want_alpha=False))
         return logprob.cpu().numpy()
 
     def posteriors(self, ratios_em=None, ratios_dp=None, renorm_eps=True, want_map=False,
@@ -393,10 +394,13 @@ class Engine(object):
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
         _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
-        alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_rd)
         flags = (_lib.BWD_POSTERIORS if want_post else 0) | (_lib.BWD_MAP if want_map else 0) | \
                 (_lib.BWD_RENORM_EPS if renorm_eps else 0)
-        post, mstates, mscore = self.run_backward(prec, tdt, flags, blin, alpha, d_rd)
+
+        def stages():
+            alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_rd)
+            return (logprob,) + tuple(self.run_backward(prec, tdt, flags, blin, alpha, d_rd))
+        logprob, post, mstates, mscore = self.ctx.optimistic(stages)
         out = {"logprob": logprob.cpu().numpy()}
         if want_post:
             out["post"] = self.split(self.lattice_to_host(prec, post))
@@ -410,7 +414,7 @@ class Engine(object):
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
         elog, _, _ = self.run_emission(prec, tdt, d_re, True, False)
-        states, _, logprob = self.run_viterbi(prec, elog, d_re, d_rd, want64=False)
+        states, _, logprob = self.ctx.optimistic(lambda: self.run_viterbi(prec, elog, d_re, d_rd, want64=False))
         return logprob.cpu().numpy(), self.split(self.states_to_host(states))
 
     # ------------------------------------------------------------ one window of a time-sharded sequence
@@ -502,19 +506,24 @@ class Engine(object):
         n_total, slots = seq_slots if seq_slots is not None else (self.nseq, list(range(self.nseq)))
         d_r = ratios if (ratios is None or torch.is_tensor(ratios)) else self.upload_ratios(ratios)
         _, blin, rowmax = self.run_emission(prec, tdt, d_r, False, True)
-        alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_r)
         base = 2 + N + N * N + K * N * S
-        packed = torch.zeros(base + n_total, dtype=torch.float64, device=self.device)
         flags = 0
         if want_trans or want_start:
             flags |= _lib.BWD_TRANS
         if want_obs:
             flags |= _lib.BWD_POSTERIORS
-        if flags:
-            post, _, _ = self.run_backward(prec, tdt, flags, blin, alpha, d_r,
-                                           start_trans=packed[2:2 + N + N * N])
-            if want_obs:
-                self.run_emission_stats(prec, post, d_r, packed[2 + N + N * N:base], S)
+
+        def stages():
+            alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_r)
+            packed = torch.zeros(base + n_total, dtype=torch.float64, device=self.device)
+            if flags:
+                post, _, _ = self.run_backward(prec, tdt, flags, blin, alpha, d_r,
+                                               start_trans=packed[2:2 + N + N * N])
+                if want_obs:
+                    self.run_emission_stats(prec, post, d_r, packed[2 + N + N * N:base], S)
+            return packed, logprob
+        # deferred verification: the stages are queued back to back and checked once
+        packed, logprob = self.ctx.optimistic(stages)
         packed[0] = logprob.sum()
         packed[1] = float(self.nseq)
         packed[base:].index_copy_(0, torch.as_tensor(slots, dtype=torch.int64, device=self.device), logprob)

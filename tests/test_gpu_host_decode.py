@@ -132,3 +132,57 @@ def test_decode_host_list_of_sequences_without_concatenation():
         lp1, _, st1 = eng.decode_host([s], _lib.DECODE_VITERBI)
         assert_array_equal(st[i], st1[0])
         assert lp[i] == pytest.approx(lp1[0], rel=1e-12)
+
+
+def test_deferred_verification_falls_back_to_the_repair_loop(oracle):
+    """tehmm_ctx_check / option "defer": the stages are queued without waiting for their
+    verification counts; with a warm-up of ONE step almost every speculated chunk boundary
+    is wrong, so the check must fail and the synchronous verify / repair loop must produce
+    the reference's answers (_hmm.pyx:120-259) all the same -- through the host-buffer decode
+    and through the engine passes."""
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=5)
+    lens = [9000, 3, 26000]
+    seqs = [synth.sample_obs(m, n, seed=40 + i)[0] for i, n in enumerate(lens)]
+    eng = _engine()
+    eng.ctx.set_option("chunk_tiles", 2)
+    eng.ctx.set_option("fine_len", 48)
+    eng.ctx.set_option("warmup", 1)
+    try:
+        eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+        bad0 = eng.ctx.stat("deferred_bad")
+        lp, _, states = eng.decode_host(seqs, _lib.DECODE_VITERBI, precision="f64")
+        flp, score, mstates = eng.decode_host(seqs, _lib.DECODE_MAP, precision="f64")
+        assert eng.ctx.stat("deferred_bad") > bad0               # the optimistic attempt was refused
+        assert eng.ctx.check() == 0                              # and nothing is left pending
+        for i, obs in enumerate(seqs):
+            ref = oracle.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+            assert_array_equal(states[i], ref["vit_states"])
+            assert_array_equal(mstates[i], ref["map_states"])
+            assert lp[i] == pytest.approx(ref["vit_logprob"], rel=1e-10)
+            assert flp[i] == pytest.approx(ref["logprob"], rel=1e-10)
+        # engine passes (fp32 production kernels): optimistic attempt, refused, repaired
+        eng.upload_batch(seqs)
+        bad1 = eng.ctx.stat("deferred_bad")
+        out = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f32")
+        vlp, vst = eng.viterbi(precision="f32")
+        st = eng.estep(precision="f32")
+        assert eng.ctx.stat("deferred_bad") > bad1
+        for i, obs in enumerate(seqs):
+            ref = oracle.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+            assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=1e-5)
+            assert vlp[i] == pytest.approx(ref["vit_logprob"], rel=1e-6)
+            assert np.mean(vst[i] == ref["vit_states"]) >= 0.98
+        assert st["obs"].sum() == pytest.approx(sum(lens) * m["K"], rel=1e-5)
+        # a healthy warm-up: the optimistic attempt stands
+        eng.ctx.set_option("warmup", 0)
+        eng.upload_batch(seqs)
+        bad2 = eng.ctx.stat("deferred_bad")
+        checks2 = eng.ctx.stat("deferred_checks")
+        vlp2, vst2 = eng.viterbi(precision="f32")
+        assert eng.ctx.stat("deferred_bad") == bad2 and eng.ctx.stat("deferred_checks") > checks2
+        for i in range(len(seqs)):
+            assert_array_equal(vst2[i], vst[i])
+    finally:
+        for k in ("chunk_tiles", "warmup", "fine_len"):
+            eng.ctx.set_option(k, 0)
