@@ -100,7 +100,8 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
  * counts by the one-chunk-per-warp backward kernel instead of the tensor-core
  * xi kernel), "timing" (1 = bracket the first
  * launch of each main kernel with CUDA events on the context's stream), "defer" (see
- * tehmm_ctx_check).
+ * tehmm_ctx_check), "bwd_tmap" (1 = the regular tiles of a single-sequence batch take the
+ * tensor-map block kernel in the backward pass; experimental: bit-identical results, not faster).
  * stats: "launches", "chunks", "fine_chunks", "repaired_chunks_<pass>",
  * "repair_passes_<pass>", "tile_passes", and with "timing" the mean duration in
  * microseconds (over the launches since "timing" was set, at most 32) of "us_emission", "us_forward", "us_backward",

@@ -34,7 +34,7 @@ cudaError_t tehmm_launch_emission_stats(cudaStream_t, const TehmmModelDev &, con
 size_t tehmm_stats_smem_bytes(int tab_rows, int N, int K, int prec);
 cudaError_t tehmm_launch_widen(cudaStream_t, const uint8_t *, int64_t *, int64_t);
 cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, const int *, int, int, int64_t);
-cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int);
+cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int, int64_t, int);
 int tehmm_tile_warps(void);
 bool tehmm_forward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int64_t);
 cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, int, int64_t, int *);
@@ -91,6 +91,7 @@ struct tehmm_ctx {
     int64_t opt_umma = 0;             // 1: forward pass on tcgen05 / TMEM (umma.cu) where it applies -- correct, not yet faster
     int *d_fault = nullptr;           // raised by a kernel whose barrier protocol timed out
     int64_t stat_umma_passes = 0;
+    int64_t opt_bwd_tmap = 0;         // 1: backward pass of the regular tiles by bwd_tile_tmap_kernel (tensor-map blocks) -- correct, not faster (profiles/r01_notes_v4.md)
     int64_t opt_xi_tile = 1;          // expected transition counts by xi_tile_kernel (0: one-chunk-per-warp backward)
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
     int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
@@ -211,6 +212,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "umma")) c->opt_umma = v;
     else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
     else if (!strcmp(name, "defer")) c->opt_defer = v;
+    else if (!strcmp(name, "bwd_tmap")) c->opt_bwd_tmap = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -980,7 +982,7 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     auto launch = [&](int mode) -> cudaError_t {
         if (tile) {
             c->stat_tile_passes += 1;
-            return tehmm_launch_backward_tile(st, c->m, PB, flags, (const float *)d_blin, (const float *)d_alpha, (float *)d_post, d_map_states, mp, (float *)sv, (float *)ev, bad, mode, c->sms);
+            return tehmm_launch_backward_tile(st, c->m, PB, flags, (const float *)d_blin, (const float *)d_alpha, (float *)d_post, d_map_states, mp, (float *)sv, (float *)ev, bad, mode, c->sms, c->fine_len, (int)c->opt_bwd_tmap);
         }
         return tehmm_launch_backward(st, c->m, PB, prec, flags, d_blin, d_alpha, d_ratios, d_post, d_map_states, mp, xi, xd, g0, sv, ev, bad, mode, grid);
     };

@@ -385,6 +385,35 @@ def test_forward_tensor_map_blocks_single_sequence(oracle, fine_len, warmup):
     assert np.mean(scan["map_states"][0] == out["map_states"][0]) > 0.999
 
 
+@pytest.mark.parametrize("fine_len,warmup", [(0, 0), (96, 64), (200, 32), (64, 64), (66, 2), (128, 126)])
+def test_backward_tensor_map_blocks_single_sequence(oracle, fine_len, warmup):
+    """bwd_tile_tmap_kernel (context option "bwd_tmap", off by default): the regular tiles of ONE regularly chunked sequence get their
+    b_{t+1} / alpha_t rows as tensor-map boxes (the b map starts one row in); ragged tiles, the
+    sequence end and warm-ups that do not fit a chunk stay with bwd_tile_kernel.  Same arithmetic:
+    posteriors, MAP path and score must be BIT-identical to the per-lane-copy kernel, and agree
+    with the oracle (basehmm.py:265-272,332-359)."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=30, seed=23)
+    T = 70_011
+    obs, _ = synth.sample_obs(m, T, seed=24)
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    res = {}
+    for tm in (1, 0):
+        eng = engine(fine_len=fine_len, warmup=warmup, tile=1)
+        eng.ctx.set_option("bwd_tmap", tm)
+        eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+        eng.upload_batch([obs])
+        res[tm] = (eng.posteriors(renorm_eps=False, want_map=True, precision="f32"),
+                   eng.posteriors(renorm_eps=True, want_map=True, want_post=False, precision="f32"))
+    engine().ctx.set_option("bwd_tmap", 0)
+    for a, b in zip(res[1], res[0]):
+        assert_array_equal(a["map_states"][0], b["map_states"][0])
+        assert a["map_score"][0] == b["map_score"][0]
+        assert a["logprob"][0] == b["logprob"][0]
+    assert_array_equal(res[1][0]["post"][0], res[0][0]["post"][0])
+    assert_allclose(res[1][0]["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
+
+
 def test_full_size_c2_properties(oracle):
     """BASELINE.json configs[1] at FULL size (one sequence of 10 M steps, 30 states, 10 tracks):
     the oracle cannot run this in seconds, so the checks are the size-independent ones --
