@@ -162,13 +162,27 @@ class Context(object):
         """run fn() with deferred verification; if any boundary failed, run it again with the
         synchronous verify / repair loop.  fn must be a pure function of device state it does
         not overwrite (every engine pass is)."""
+        # a refused attempt costs the stages twice, and batches that need repairs tend to need them
+        # again (same model, same chunk boundaries): back off to the synchronous loop for a growing
+        # number of calls after a refusal, come back when attempts stand again
+        skip = getattr(self, "_defer_skip", 0)
+        if os.environ.get("TEHMM_NO_DEFER"):      # measurement switch: always the synchronous loop
+            return fn()
+        if skip > 0:
+            self._defer_skip = skip - 1
+            return fn()
         self.set_option("defer", 1)
         try:
             out = fn()
         finally:
             self.set_option("defer", 0)
+        penalty = getattr(self, "_defer_penalty", 0)
         if self.check() != 0:
+            self._defer_penalty = min(256, max(4, 2 * penalty))
+            self._defer_skip = self._defer_penalty
             out = fn()
+        else:
+            self._defer_penalty = penalty // 2
         return out
 
     @property

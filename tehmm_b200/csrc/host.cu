@@ -143,6 +143,7 @@ struct HostPipe {
     Pool *pool = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int64_t redone = 0;                     // calls whose deferred verification failed and ran twice
+    int defer_skip = 0, defer_penalty = 0;  // back-off after a refusal
 
     ~HostPipe()
     {
@@ -384,7 +385,11 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     struct DeferGuard { tehmm_ctx *c; ~DeferGuard() { tehmm_ctx_set_option(c, "defer", 0); } } defer_guard{c};
     double *pin_lp = nullptr;
     int rc = TEHMM_OK;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // (after a refusal the next calls go straight to the synchronous loop: a refused attempt costs the
+    //  trellis twice, and a model / batch that needed repairs tends to need them again)
+    int attempt = 0;
+    if (p->defer_skip > 0) { p->defer_skip -= 1; attempt = 1; }
+    for (; attempt < 2; ++attempt) {
         HOK(tehmm_ctx_set_option(c, "defer", attempt == 0 ? 1 : 0));
         // ---- the trellis
         if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
@@ -443,8 +448,10 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
             int64_t unverified = 0;
             HOK(tehmm_ctx_set_option(c, "defer", 0));
             HOK(tehmm_ctx_check(c, &unverified));
-            if (unverified == 0) break;
+            if (unverified == 0) { p->defer_penalty /= 2; break; }
             p->redone += 1;
+            p->defer_penalty = std::min(256, std::max(4, 2 * p->defer_penalty));
+            p->defer_skip = p->defer_penalty;
         }
     }
     memcpy(h_logprob, pin_lp, (size_t)nseq * 8);

@@ -150,6 +150,7 @@ def test_deferred_verification_falls_back_to_the_repair_loop(oracle):
     eng.ctx.set_option("warmup", 1)
     try:
         eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+        eng.ctx._defer_skip = 0
         bad0 = eng.ctx.stat("deferred_bad")
         lp, _, states = eng.decode_host(seqs, _lib.DECODE_VITERBI, precision="f64")
         flp, score, mstates = eng.decode_host(seqs, _lib.DECODE_MAP, precision="f64")
@@ -163,6 +164,7 @@ def test_deferred_verification_falls_back_to_the_repair_loop(oracle):
             assert flp[i] == pytest.approx(ref["logprob"], rel=1e-10)
         # engine passes (fp32 production kernels): optimistic attempt, refused, repaired
         eng.upload_batch(seqs)
+        eng.ctx._defer_skip = 0
         bad1 = eng.ctx.stat("deferred_bad")
         out = eng.posteriors(renorm_eps=False, want_map=True, want_post=False, precision="f32")
         vlp, vst = eng.viterbi(precision="f32")
@@ -174,7 +176,9 @@ def test_deferred_verification_falls_back_to_the_repair_loop(oracle):
             assert vlp[i] == pytest.approx(ref["vit_logprob"], rel=1e-6)
             assert np.mean(vst[i] == ref["vit_states"]) >= 0.98
         assert st["obs"].sum() == pytest.approx(sum(lens) * m["K"], rel=1e-5)
-        # a healthy warm-up: the optimistic attempt stands
+        # a healthy warm-up: the optimistic attempt stands (once the back-off after a refusal is over)
+        assert eng.ctx._defer_skip > 0
+        eng.ctx._defer_skip = 0
         eng.ctx.set_option("warmup", 0)
         eng.upload_batch(seqs)
         bad2 = eng.ctx.stat("deferred_bad")

@@ -80,7 +80,9 @@ def run_c3(scale):
             "cells_per_s_per_iteration": sum(lens) * 30 / (dt / n_iter),
             "logprob_first_last": [total_lp[0], total_lp[-1]] if total_lp else None,
             "logprob_monotone": bool(all(b >= a - 1e-6 * abs(a) for a, b in zip(total_lp, total_lp[1:]))) if total_lp else None,
-            "transmat_rows_sum_to_1": rows_ok, "emission_rows_sum_to_1": em_ok}
+            "transmat_rows_sum_to_1": rows_ok, "emission_rows_sum_to_1": em_ok,
+            "deferred_checks": hmm._engine().ctx.stat("deferred_checks"), "deferred_refused_chunks": hmm._engine().ctx.stat("deferred_bad"),
+            "repaired_chunks": {k: hmm._engine().ctx.stat("repaired_chunks_" + k) for k in ("forward", "backward")}}
 
 
 def run_c4(scale):
