@@ -281,6 +281,11 @@ int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t 
                         int64_t n, const int64_t *seg_len, const int32_t *mask_off,
                         int64_t mask_n, const char *const *names, int nnames);
 
+/* the posterior / emission score files of the same reference function (bin/teHmmEval.py:264-270):
+ * same intervals, fourth column = scores[i] printed as Python prints a float64 ("%s") */
+int tehmm_scores_to_bed(int fd, const char *chrom, int64_t start, const double *scores,
+                        int64_t n, const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n);
+
 /* widen / convert on the device before a D2H copy */
 int tehmm_widen_states(tehmm_ctx *ctx, const uint8_t *d_in, int64_t *d_out, int64_t n);
 int tehmm_convert_lattice(tehmm_ctx *ctx, int prec, const void *d_in, double *d_out, int64_t n);

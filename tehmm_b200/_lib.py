@@ -67,6 +67,7 @@ SIGNATURES = {
     "tehmm_model_dims": (_c_int, [_c_void, _c_void, _c_void, _c_void]),
     "tehmm_path_score": (_c_int, [_c_void, _c_void, _c_void, _c_void, _c_i64, _c_i64, _c_void, _c_void]),
     "tehmm_states_to_bed": (_c_int, [_c_int, ctypes.c_char_p, _c_i64, _c_void, _c_i64, _c_void, _c_void, _c_i64, _c_void, _c_int]),
+    "tehmm_scores_to_bed": (_c_int, [_c_int, ctypes.c_char_p, _c_i64, _c_void, _c_i64, _c_void, _c_void, _c_i64]),
     "tehmm_widen_states": (_c_int, [_c_void, _c_void, _c_void, _c_i64]),
     "tehmm_convert_lattice": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_i64]),
 }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -492,15 +493,66 @@ static int fmt_i64(char *p, int64_t v)
     return k + 24 - n;
 }
 
-int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t *states, int64_t n,
-                        const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n,
-                        const char *const *names, int nnames)
+// str() of a float64 as Python / NumPy print it ("%s" % np.float64, teHmmEval.py:266-270): the
+// shortest decimal that reads back as the same double, positional for 1e-4 <= |x| < 1e16 (always
+// with a fractional part: "1.0"), scientific otherwise ("1e-05", "1.5e+16").  At most three
+// correctly rounded conversions: 15 significant digits are unique when they round-trip (their
+// trailing zeros dropped), else 16, else 17.
+static int fmt_pyfloat(char *out, double x)
 {
-    if (fd < 0 || !chrom || (!states && n > 0) || n < 0) return herr(TEHMM_EINVAL, "bad argument");
+    if (x != x) { memcpy(out, "nan", 3); return 3; }
+    int k = 0;
+    if (std::signbit(x)) { out[k++] = '-'; x = -x; }
+    if (x == INFINITY) { memcpy(out + k, "inf", 3); return k + 3; }
+    if (x == 0.0) { memcpy(out + k, "0.0", 3); return k + 3; }
+    char tmp[40];
+    // (subnormals carry fewer bits: there the 15-digit argument does not hold, search from one digit)
+    for (int prec = x < 2.2250738585072014e-308 ? 1 : 15; prec <= 17; ++prec) {
+        snprintf(tmp, sizeof tmp, "%.*e", prec - 1, x);
+        if (prec == 17 || strtod(tmp, nullptr) == x) break;
+    }
+    // tmp = d.ddddde[+-]XX
+    char dig[24];
+    int nd = 0;
+    const char *q = tmp;
+    for (; *q && *q != 'e'; ++q)
+        if (*q >= '0' && *q <= '9') dig[nd++] = *q;
+    const int e10 = atoi(q + 1);
+    while (nd > 1 && dig[nd - 1] == '0') --nd;
+    if (e10 >= 16 || e10 < -4) {
+        out[k++] = dig[0];
+        if (nd > 1) { out[k++] = '.'; memcpy(out + k, dig + 1, (size_t)(nd - 1)); k += nd - 1; }
+        out[k++] = 'e';
+        out[k++] = e10 < 0 ? '-' : '+';
+        const int a = e10 < 0 ? -e10 : e10;
+        if (a >= 100) out[k++] = (char)('0' + a / 100);
+        out[k++] = (char)('0' + (a / 10) % 10);
+        out[k++] = (char)('0' + a % 10);
+        return k;
+    }
+    if (e10 >= 0) {
+        for (int i = 0; i <= e10; ++i) out[k++] = i < nd ? dig[i] : '0';
+        out[k++] = '.';
+        if (nd > e10 + 1) { memcpy(out + k, dig + e10 + 1, (size_t)(nd - e10 - 1)); k += nd - e10 - 1; }
+        else out[k++] = '0';
+        return k;
+    }
+    out[k++] = '0'; out[k++] = '.';
+    for (int i = 0; i < -e10 - 1; ++i) out[k++] = '0';
+    memcpy(out + k, dig, (size_t)nd);
+    return k + nd;
+}
+
+// fourth column: the state (index or name), or -- scores != NULL -- a float64 printed as Python does
+static int write_bed(int fd, const char *chrom, int64_t start, const int64_t *states, const double *scores,
+                     int64_t n, const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n,
+                     const char *const *names, int nnames)
+{
+    if (fd < 0 || !chrom || (!states && !scores && n > 0) || n < 0) return herr(TEHMM_EINVAL, "bad argument");
     if (n == 0) return TEHMM_OK;
     const size_t clen = strlen(chrom);
     std::vector<size_t> nlen((size_t)std::max(nnames, 0));
-    size_t maxname = 21;
+    size_t maxname = 32;
     for (int i = 0; i < nnames; ++i) {
         if (!names || !names[i]) return herr(TEHMM_EINVAL, "names[%d] is NULL", i);
         nlen[i] = strlen(names[i]);
@@ -554,6 +606,7 @@ int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t 
                 endlen = fmt_i64(endtxt, cur + len);
                 memcpy(p, endtxt, (size_t)endlen); p += endlen;
                 *p++ = '\t';
+                if (scores) { p += fmt_pyfloat(p, scores[i]); *p++ = '\n'; continue; }
                 const int64_t st = states[i];
                 if (nnames > 0) {
                     if (st < 0 || st >= nnames) { bad_state.store(1); p += fmt_i64(p, st); }
@@ -579,6 +632,23 @@ int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t 
     }
     if (bad_state.load()) return herr(TEHMM_EINVAL, "a state index has no name");
     return TEHMM_OK;
+}
+
+int tehmm_states_to_bed(int fd, const char *chrom, int64_t start, const int64_t *states, int64_t n,
+                        const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n,
+                        const char *const *names, int nnames)
+{
+    if (!states && n > 0) return herr(TEHMM_EINVAL, "states is NULL");
+    return write_bed(fd, chrom, start, states, nullptr, n, seg_len, mask_off, mask_n, names, nnames);
+}
+
+// The posterior / emission score files of the same function (teHmmEval.py:264-270): same intervals,
+// fourth column = one float64 per observation, printed as "%s" of a NumPy float64.
+int tehmm_scores_to_bed(int fd, const char *chrom, int64_t start, const double *scores, int64_t n,
+                        const int64_t *seg_len, const int32_t *mask_off, int64_t mask_n)
+{
+    if (!scores && n > 0) return herr(TEHMM_EINVAL, "scores is NULL");
+    return write_bed(fd, chrom, start, nullptr, scores, n, seg_len, mask_off, mask_n, nullptr, 0);
 }
 
 }   // extern "C"

@@ -103,3 +103,76 @@ def test_unnamed_state_is_an_error(tmp_path):
     with open(os.path.join(str(tmp_path), "x.bed"), "w") as f:
         with pytest.raises(AssertionError):
             statesToBed(FakeTable("c", 0, 3), [0, 1, 2], f, stateNames=["only", "two"])
+
+
+def reference_scores_to_bed(trackTable, n, posteriors, posteriorsMask, posteriorsFile, emProbs, emissionsMask,
+                            emissionsFile):
+    """teHmmEval.py:238-270, the posteriorsFile / emissionsFile branches, verbatim logic (incl. the i-1 index)"""
+    chrom, start = trackTable.getChrom(), trackTable.getStart()
+    segOffsets = trackTable.getSegmentOffsets()
+    maskOffsets = trackTable.getMaskRunningOffsets()
+    segDist = 0
+    for i in range(n):
+        curStart = start + segDist
+        intLen = 1
+        if segOffsets is not None:
+            intLen = trackTable.getSegmentLength(i)
+        segDist += intLen
+        if maskOffsets is not None:
+            curStart += maskOffsets[curStart - trackTable.getStart()]
+        curEnd = curStart + intLen
+        if posteriors is not None:
+            posteriorsFile.write("%s\t%d\t%d\t%s\n" % (chrom, curStart, curEnd,
+                                 np.sum(posteriors[i-1] * posteriorsMask)))
+        if emProbs is not None:
+            emissionsFile.write("%s\t%d\t%d\t%s\n" % (chrom, curStart, curEnd,
+                                np.log(np.sum(np.exp(emProbs[i-1]) * emissionsMask))))
+
+
+@pytest.mark.parametrize("N", [3, 8, 30, 50])
+def test_posterior_and_emission_score_files(tmp_path, N):
+    from tehmm_b200.output import statesToBed
+    rng = np.random.RandomState(N)
+    n = 4000
+    post = rng.dirichlet(np.ones(N) * 0.3, size=n)
+    post[5] = 0.0; post[5, 1] = 1.0                       # exact 1.0 / 0.0 sums
+    post[6] = 1e-7 / N                                    # scientific notation
+    em = np.log(rng.dirichlet(np.ones(N), size=n)) * rng.choice([1.0, 30.0], size=(n, 1))
+    pmask = (rng.rand(N) < 0.5).astype(np.float64)
+    pmask[1] = 1.0
+    emask = np.zeros(N); emask[[0, N - 1]] = 1.0
+    offs = np.concatenate([[0], np.cumsum(rng.randint(1, 50, size=n - 1))])
+    table = FakeTable("chr7", 1000, 1000 + int(offs[-1]) + 13, segOffsets=offs)
+    rp, re_ = io.StringIO(), io.StringIO()
+    reference_scores_to_bed(table, n, post, pmask, rp, em, emask, re_)
+    pp, pe, pb = (os.path.join(str(tmp_path), x) for x in ("p.bed", "e.bed", "s.bed"))
+    states = rng.randint(0, N, size=n)
+    with open(pp, "w") as fp, open(pe, "w") as fe, open(pb, "w") as fb:
+        statesToBed(table, states, fb, post, pmask, fp, em, emask, fe)
+    assert open(pp).read() == rp.getvalue()
+    assert open(pe).read() == re_.getvalue()
+    rb = io.StringIO()
+    reference_states_to_bed(table, states, rb)
+    assert open(pb).read() == rb.getvalue()
+    # bedFile may be None (teHmmEval.py:263)
+    with open(pp, "w") as fp:
+        statesToBed(table, states, None, post, pmask, fp)
+    assert open(pp).read() == rp.getvalue()
+
+
+def test_python_float_formatting_matches(tmp_path):
+    """fourth column == "%s" % np.float64(x) for awkward values"""
+    from tehmm_b200.output import _write_scores
+    from tehmm_b200 import _lib
+    rng = np.random.RandomState(1)
+    vals = np.concatenate([
+        [0.0, -0.0, 1.0, -1.0, 0.1, 0.2 + 0.1, 1e-4, 9.999e-5, 1e-5, 1e15, 1e16, 123456789012345678.0, 1e22, 1e23,
+         5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, np.inf, -np.inf, np.nan, 100.0, 1e5, 0.5, 2.5e-7,
+         1.0 - 2 ** -53, 1.0 + 2 ** -52, 4.35, 0.3, 1 / 3, 2 / 3, 1e-100, 123.456, 9007199254740993.0],
+        rng.rand(3000), np.exp(rng.uniform(-50, 50, size=3000)), -rng.rand(100) * 1e-6])
+    path = os.path.join(str(tmp_path), "v.bed")
+    with open(path, "w") as f:
+        _write_scores(_lib.load(), f, "c", 0, vals, None, None)
+    got = [l.split("\t")[3] for l in open(path).read().splitlines()]
+    want = ["%s" % v for v in vals]
+    assert got == want
