@@ -342,7 +342,12 @@ def run_ours(args):
     # (profiles/r01_ncu_full_v3.txt: dram__bytes_read.sum + dram__bytes_write.sum), 10 M x 30 x 10 only
     ncu_traffic = {"emission": 2.68e9, "forward": 2.79e9, "backward": 2.73e9, "viterbi_dp": 2.55e9, "traceback": 1.46e9,
                    "rescore": 0.12e9}
-    dom = max(kern_us, key=lambda k: kern_us[k])
+    # the dominant kernel: the longest one; when another is within 5 % of it and moves more algorithmic
+    # bytes, that one (backward and the Viterbi DP tie at ~0.8 ms and would swap from run to run; the
+    # DP's bound is fp32 issue, not HBM -- DESIGN.md section 5 -- so its HBM fraction says little).
+    # kernel_frac below lists every kernel either way.
+    longest = max(kern_us.values())
+    dom = max((k for k in kern_us if kern_us[k] >= 0.95 * longest), key=lambda k: (alg_bytes[k], kern_us[k]))
     dom_s = kern_us[dom] * 1e-6
     achieved = alg_bytes[dom] * T / dom_s / 1e9
     sweep_achieved = (3 * K + 9 * N_STATES + 3) * T / (total_ms / args.steps * 1e-3) / 1e9
@@ -355,6 +360,7 @@ def run_ours(args):
                 "frac": achieved / peak,
                 "traffic": ncu_traffic.get(dom) if (T == T_DEFAULT and args.precision == "f32") else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes[dom],
+                "kernel_choice": "longest kernel; within 5 % of it, the one with more algorithmic bytes",
                 "kernel_us": kern_us,
                 "kernel_frac": {k: (alg_bytes[k] * T / (v * 1e-6) / 1e9 / peak if v > 0 else None) for k, v in kern_us.items()},
                 "sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,

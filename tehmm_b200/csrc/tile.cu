@@ -53,6 +53,7 @@
 // Algorithmic HBM bytes per step: forward 4N read + 4N written, backward 8N read
 // (+4N posteriors, +1 MAP state).
 #include "scan.cuh"
+#include <type_traits>
 #include <cuda.h>
 #include <cstring>
 
@@ -731,11 +732,10 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                         if (p[i] == best) idx = 8 * q + i;
                     idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 1));
                     idx = min(idx, __shfl_xor_sync(TEHMM_FULL, idx, 2));
-                    if (act && q == 0) {
-                        mp_[r][back] = (uint8_t)(idx < N ? idx : 0);
-                        const float bg = best * invZ[r];
-                        mapsum[r] += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
-                    }
+                    // every lane of the quad keeps the (identical) running score: no divergent branch
+                    const float bg = act ? best * invZ[r] : 0.f;
+                    mapsum[r] += renorm ? (act ? ((double)bg + (double)eps32) * renorm_inv : 0.0) : (double)bg;
+                    if (act && q == 0) mp_[r][back] = (uint8_t)(idx < N ? idx : 0);
                 }
                 if constexpr (want_post) {
                     float gv[8];
@@ -753,7 +753,12 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
         for (int v = 0; v < BWD_STAGES - 1; ++v) issue(kb + v, v);
         int rs = 0, ws = BWD_STAGES - 1;
         int kev = next_event(kb);
-        for (int k = kb; k < kmax; ++k) {
+        // One clock.  EV (compile time): this clock may start or end a row.  The clocks between two
+        // events run the EV = false copy, which has no conditional update of `up` in it: with the
+        // event code inside the hot loop the compiler re-materialised `up` every clock (ncu: ~50 of
+        // 390 instructions per clock were moves and predicated-off event code).
+        auto clock_step = [&](const int k, auto evtag) {
+            constexpr bool EVC = decltype(evtag)::value;
             issue(k + BWD_STAGES - 1, ws);
             stage_wait<BWD_STAGES - 1>();
             float at[2][8], bt[2][8];
@@ -762,8 +767,8 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             stage_read(sl + 1024, bt[1]);
             stage_read(sl + TILE_STAGE_BYTES, at[0]);
             stage_read(sl + TILE_STAGE_BYTES + 1024, at[1]);
-            const bool ev = k == kev;
-            if (ev) {
+            const bool ev = EVC;
+            if constexpr (EVC) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     if (k == ks[r] && !exact[r]) {
@@ -790,8 +795,10 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 }
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    wp[2 * p] = fmul2(up[2 * p], pk2(lo2(bs[0][p]), lo2(bs[1][p])));
-                    wp[2 * p + 1] = fmul2(up[2 * p + 1], pk2(hi2(bs[0][p]), hi2(bs[1][p])));
+                    // scalar multiplies: their operands sit in an MMA accumulator quad and an LDS.128 quad,
+                    // neither pairs up as (row g, row g+8) without moves (ncu: 70 IMAD.MOV per clock before)
+                    wp[2 * p] = pk2(lo2(up[2 * p]) * lo2(bs[0][p]), hi2(up[2 * p]) * lo2(bs[1][p]));
+                    wp[2 * p + 1] = pk2(lo2(up[2 * p + 1]) * hi2(bs[0][p]), hi2(up[2 * p + 1]) * hi2(bs[1][p]));
                 }
             }
             float acc[4][4];
@@ -805,7 +812,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 m0 = fmax3(m0, acc[nt][0], acc[nt][1]);
                 m1 = fmax3(m1, acc[nt][2], acc[nt][3]);
             }
-            if (ev) {
+            if constexpr (EVC) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     if (k == ks[r] && exact[r]) {    // the sequence's last step: beta = 1
@@ -824,7 +831,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 // here; the reductions, the arg-max and the stores of this clock are issued behind
                 // the NEXT clock's MMAs (post_out above), off the recursion's critical path.
 #pragma unroll
-                for (int c = 0; c < 8; ++c) prq[c] = fmul2(up[c], pk2(at[0][c], at[1][c]));
+                for (int c = 0; c < 8; ++c) prq[c] = pk2(lo2(up[c]) * at[0][c], hi2(up[c]) * at[1][c]);
                 actq[0] = k < ke[0];
                 actq[1] = k < ke[1];
                 pend = true;
@@ -833,7 +840,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
                 for (int r = 0; r < 2; ++r)
                     if (succ[r] && k >= ks[r] && k < ke[r]) store_row_vec32(start_vec + cid[r] * 32 + 8 * q, up, r);
             }
-            if (ev) {
+            if constexpr (EVC) {
 #pragma unroll
                 for (int r = 0; r < 2; ++r)
                     if (k + 1 == ke[r]) store_row_vec32(end_vec + cid[r] * 32 + 8 * q, up, r);
@@ -846,6 +853,12 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
             }
             rs = rs + 1 == BWD_STAGES ? 0 : rs + 1;
             ws = ws + 1 == BWD_STAGES ? 0 : ws + 1;
+        };
+        for (int k = kb; k < kmax;) {
+            clock_step(k, std::true_type());          // k == kev: kb is an event, and so is every clock the inner loop stops at
+            ++k;
+            const int stop = min(kmax, kev);
+            for (; k < stop; ++k) clock_step(k, std::false_type());
         }
         stage_wait<0>();
         if (pend) post_out(prq, actq, 1);            // the last clock's posterior
