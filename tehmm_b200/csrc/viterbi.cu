@@ -672,14 +672,8 @@ __global__ void vit_rescore_kernel(TehmmModelDev m, TehmmBatchDev b, const OBS *
     for (int64_t t = max(ch.t0, lo) + lane; t < min(ch.t1, hi); t += 32) {
         const int j = states[t];
         double e = 0.0;
-        // the compact transposed table (sum of the tracks' symbol counts x N doubles, ~100 KB: stays in
-        // L1) holds the same values as the dense K x N x S one (600 KB at S = 251: every gather went to L2);
-        // symbols beyond a track's own table only exist in the dense one
-        for (int k = 0; k < m.K; ++k) {
-            const int sym = (int)obs[t * m.K + k];
-            e += sym < m.track_nsym[k] ? m.table_t[(int64_t)(m.tab_off[k] + sym) * N + j]
-                                       : m.table[((int64_t)k * N + j) * m.S + (int64_t)sym];
-        }
+        for (int k = 0; k < m.K; ++k)
+            e += m.table[((int64_t)k * N + j) * m.S + (int64_t)obs[t * m.K + k]];
         e *= m.normalize;
         if (ratios_em) e *= ratios_em[t];
         const double ajj = m.log_trans[(int64_t)j * N + j];
