@@ -482,7 +482,10 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
 
         for (int j = 0; j < FWD_NBL - 1 && j < nblk; ++j) issue_load(j);
         int kev = next_event(kb);
-        for (int j = 0; j < nblk; ++j) {
+        // One block of TB clocks.  EVC (compile time): a row may start or end inside this block; the
+        // blocks in between run the copy without that code (see bwd_tile_kernel's clock_step).
+        auto block_step = [&](const int j, auto evtag) {
+            constexpr bool EVC = decltype(evtag)::value;
             if (j + FWD_NBL - 1 < nblk) issue_load(j + FWD_NBL - 1);
             const uint32_t slot = (nblk_done + (uint32_t)j) % FWD_NBL;
             mbar_wait(bars + 8 * slot, ((nblk_done + (uint32_t)j) / FWD_NBL) & 1u);
@@ -502,7 +505,7 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 lds128(lbuf + s * 128 + 16, bt[0], 4);
                 lds128(lbuf + s * 128 + 8 * rs, bt[1], 0);
                 lds128(lbuf + s * 128 + 8 * rs + 16, bt[1], 4);
-                const bool ev = k == kev;             // warp uniform, rare
+                const bool ev = EVC && k == kev;      // warp uniform, rare
                 if (ev) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
@@ -577,6 +580,10 @@ fwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 }
             }
             if (storing) issue_store(j);
+        };
+        for (int j = 0; j < nblk; ++j) {
+            if (kev < kb + (j + 1) * TB) block_step(j, std::true_type());
+            else block_step(j, std::false_type());
         }
         nblk_done += (uint32_t)nblk;
         if (alpha) {
