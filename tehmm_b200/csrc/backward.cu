@@ -450,7 +450,10 @@ cudaError_t tehmm_launch_trans_reduce(cudaStream_t st, const TehmmModelDev &m, c
 cudaError_t tehmm_launch_map_reduce(cudaStream_t st, const TehmmBatchDev &b, const double *map_part,
                                     double *map_score)
 {
-    const int th = b.nchunks / b.nseq >= 256 ? 256 : 64;
+    // one block per sequence; its chunks are read in a strided loop of dependent-latency loads, so long
+    // sequences get the widest block (24 us -> a few at 18 944 chunks)
+    const int64_t cps = b.nchunks / b.nseq;
+    const int th = cps >= 2048 ? 1024 : cps >= 256 ? 256 : 64;
     map_reduce_kernel<<<(int)b.nseq, th, 0, st>>>(b, map_part, map_score);
     return cudaGetLastError();
 }

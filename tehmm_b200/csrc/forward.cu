@@ -348,7 +348,10 @@ cudaError_t tehmm_launch_forward_logprob(cudaStream_t st, const TehmmBatchDev &b
                                          const void *end_vec, const double *cscale,
                                          const double *logkappa, double *logprob)
 {
-    const int th = b.nchunks / b.nseq >= 256 ? 256 : 64;
+    // one block per sequence; its chunks are read in a strided loop of dependent-latency loads, so long
+    // sequences get the widest block (24 us -> a few at 18 944 chunks)
+    const int64_t cps = b.nchunks / b.nseq;
+    const int th = cps >= 2048 ? 1024 : cps >= 256 ? 256 : 64;
     if (prec == TEHMM_F32)
         forward_logprob_kernel<float><<<(int)b.nseq, th, 0, st>>>(b, NP, (const float *)end_vec, cscale, logkappa, logprob);
     else

@@ -798,6 +798,7 @@ cudaError_t tehmm_launch_rescore(cudaStream_t st, const TehmmModelDev &m, const 
     if (b.obs_bytes == 1) vit_rescore_kernel<uint8_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint8_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
     else if (b.obs_bytes == 2) vit_rescore_kernel<uint16_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const uint16_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
     else vit_rescore_kernel<int32_t><<<rgrid, warps * 32, 0, st>>>(m, b, (const int32_t *)b.obs, states, ratios_em, ratios_dp, score_part, lo, hi);
-    vit_score_reduce_kernel<<<(int)b.nseq, b.nchunks / b.nseq >= 256 ? 256 : 64, 0, st>>>(b, score_part, logprob);
+    const int64_t cps = b.nchunks / b.nseq;
+    vit_score_reduce_kernel<<<(int)b.nseq, cps >= 2048 ? 1024 : cps >= 256 ? 256 : 64, 0, st>>>(b, score_part, logprob);
     return cudaGetLastError();
 }
