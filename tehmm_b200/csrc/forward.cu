@@ -227,57 +227,87 @@ forward_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ blin,
 // (beta for alpha, alpha for beta) may weight it up in the posterior.
 // Log-space vectors (Viterbi) are compared by the spread of the differences.
 // A bad chunk gets the true vector copied into its start slot for the repair.
+// One warp per chunk, lane = state (and state + 32 for 33..64 states): the vectors are read as
+// coalesced rows and min / max / sums are warp reductions (with one thread per chunk walking 32
+// float64 divisions the kernel took 15 us per pass, four passes per sweep).
+__device__ __forceinline__ double vwarp_fmax(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(TEHMM_FULL, v, o));   // fmax / fmin skip NaNs
+    return v;
+}
+__device__ __forceinline__ double vwarp_fmin(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(TEHMM_FULL, v, o));
+    return v;
+}
 template <typename T>
 __global__ void verify_kernel(TehmmBatchDev b, int NP, T *start_vec, const T *end_vec,
                               double tol, int dir, int linear, int *bad, int *nbad,
                               double *logkappa)
 {
-    int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= b.nchunks) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ci >= b.nchunks) return;                       // the whole warp leaves together
     const TehmmChunk ch = b.chunks[ci];
-    bool has = dir > 0 ? (ch.t0 > ch.s0) : (ch.t1 < ch.s1);
+    const bool has = dir > 0 ? (ch.t0 > ch.s0) : (ch.t1 < ch.s1);
     int flag = 0;
     double lk = 0.0;
     if (has) {
         const T *tv = end_vec + (ci - dir) * NP;
         T *sv = start_vec + ci * NP;
+        const int nj = NP >> 5;                        // 1 or 2 components per lane
+        double a[2] = {0.0, 0.0}, t[2] = {0.0, 0.0};
+        for (int u = 0; u < nj; ++u) { a[u] = (double)sv[lane + 32 * u]; t[u] = (double)tv[lane + 32 * u]; }
         double lo = INFINITY, hi = -INFINITY;
+        int mismatch = 0;
         if (linear) {
             double ma = 0.0, mt = 0.0;
-            for (int j = 0; j < NP; ++j) { ma = fmax(ma, (double)sv[j]); mt = fmax(mt, (double)tv[j]); }
+            for (int u = 0; u < nj; ++u) { ma = fmax(ma, a[u]); mt = fmax(mt, t[u]); }
+            ma = vwarp_fmax(ma);
+            mt = vwarp_fmax(mt);
             const double floor_rel = sizeof(T) == 4 ? 1e-30 : 1e-250;
-            for (int j = 0; j < NP; ++j) {
-                const double a = (double)sv[j], t = (double)tv[j];
-                const bool az = !(a > floor_rel * ma), tz = !(t > floor_rel * mt);
+            for (int u = 0; u < nj; ++u) {
+                const bool az = !(a[u] > floor_rel * ma), tz = !(t[u] > floor_rel * mt);
                 if (az && tz) continue;
-                if (az != tz) { flag = 1; break; }
-                const double r = a / t;
+                if (az != tz) { mismatch = 1; continue; }
+                const double r = a[u] / t[u];
                 lo = fmin(lo, r); hi = fmax(hi, r);
             }
+            lo = vwarp_fmin(lo);
+            hi = vwarp_fmax(hi);
+            flag = __any_sync(TEHMM_FULL, mismatch) ? 1 : 0;
             if (!flag && hi > -INFINITY && !(hi / lo - 1.0 <= tol)) flag = 1;   // NaN counts as bad
         } else {
-            for (int j = 0; j < NP; ++j) {
-                const double a = (double)sv[j], t = (double)tv[j];
-                const bool az = !(a > -1e30), tz = !(t > -1e30);
+            for (int u = 0; u < nj; ++u) {
+                const bool az = !(a[u] > -1e30), tz = !(t[u] > -1e30);
                 if (az && tz) continue;
-                if (az != tz) { flag = 1; break; }
-                const double d = a - t;
+                if (az != tz) { mismatch = 1; continue; }
+                const double d = a[u] - t[u];
                 lo = fmin(lo, d); hi = fmax(hi, d);
             }
+            lo = vwarp_fmin(lo);
+            hi = vwarp_fmax(hi);
+            flag = __any_sync(TEHMM_FULL, mismatch) ? 1 : 0;
             if (!flag && hi > -INFINITY && !(hi - lo <= tol)) flag = 1;
         }
         if (flag) {
-            for (int j = 0; j < NP; ++j) sv[j] = tv[j];
+            for (int u = 0; u < nj; ++u) sv[lane + 32 * u] = tv[lane + 32 * u];
         } else if (linear && logkappa) {
             // scale of the speculated vector relative to the true one (see forward_logprob_kernel)
             double ss = 0.0, se = 0.0;
-            for (int j = 0; j < NP; ++j) { ss += (double)sv[j]; se += (double)tv[j]; }
+            for (int u = 0; u < nj; ++u) { ss += a[u]; se += t[u]; }
+            ss = warp_sum(ss);
+            se = warp_sum(se);
             lk = log(ss / se);
         }
     }
-    bad[ci] = flag;
-    if (logkappa) logkappa[ci] = lk;
-    if (flag) atomicAdd(nbad, 1);
+    if (lane == 0) {
+        bad[ci] = flag;
+        if (logkappa) logkappa[ci] = lk;
+        if (flag) atomicAdd(nbad, 1);
+    }
 }
 
 // logprob[seq] = sum of chunk scales + log(sum_j alpha_hat[T-1][j])
@@ -336,7 +366,7 @@ cudaError_t tehmm_launch_verify(cudaStream_t st, const TehmmBatchDev &b, int pre
 {
     cudaError_t e = cudaMemsetAsync(nbad, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    int grid = (int)((b.nchunks + 127) / 128);
+    int grid = (int)((b.nchunks + 3) / 4);             // one warp per chunk, four warps per block
     if (prec == TEHMM_F32)
         verify_kernel<float><<<grid, 128, 0, st>>>(b, NP, (float *)start_vec, (const float *)end_vec, tol, dir, linear, bad, nbad, logkappa);
     else
