@@ -12,12 +12,10 @@ import pytest
 from numpy.testing import assert_allclose, assert_array_equal
 
 from conftest import golden, golden_names, ratios_of
+from parity import (ATOL, TOL, assert_map_near_ties_only, assert_near_ties_only, min_rtol, oracle_all,
+                    oracle_frame, trans_counts_extended)
 
 pytestmark = pytest.mark.gpu
-
-TOL = {"f32": 1e-5, "f64": 1e-10}
-# absolute floor for posteriors / counts: values below it are rounding of zero
-ATOL = {"f32": 2e-6, "f64": 1e-12}
 
 
 def engine(chunk_tiles=0, warmup=0, fine_len=0, tile=1):
@@ -30,26 +28,6 @@ def engine(chunk_tiles=0, warmup=0, fine_len=0, tile=1):
     eng.ctx.set_option("fine_len", fine_len)
     eng.ctx.set_option("tile", tile)
     return eng
-
-
-def oracle_all(oracle, obs, m_table, normalize, log_start, log_trans, r_em=None, r_dp=None):
-    T, N = obs.shape[0], log_start.shape[0]
-    frame = np.zeros((T, N))
-    oracle.fastAllLogProbs(obs, m_table, frame, normalize, r_em)
-    fwd, bwd = np.zeros((T, N)), np.zeros((T, N))
-    oracle._forward(T, N, log_start, log_trans, frame, r_dp, fwd)
-    oracle._backward(T, N, log_start, log_trans, frame, r_dp, bwd)
-    lp = oracle.logsumexp(fwd[-1])
-    post = oracle.posteriors(fwd, bwd)
-    states, vlp = oracle._viterbi(T, N, log_start, log_trans, r_dp, frame)
-    return dict(frame=frame, fwd=fwd, bwd=bwd, logprob=lp, post=post, vit_states=states, vit_logprob=vlp)
-
-
-def path_score(oracle, frame, log_start, log_trans, states):
-    """float64 score of a path (no ratios)"""
-    s = log_start[states[0]] + frame[0, states[0]]
-    s += np.sum(log_trans[states[:-1], states[1:]] + frame[np.arange(1, len(states)), states[1:]])
-    return s
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
@@ -73,15 +51,15 @@ def test_golden_batched(name, prec):
     if prec == "f64":
         assert_array_equal(states[0], g["vit_states"])
     else:
-        assert np.mean(states[0] == g["vit_states"]) >= 0.98
+        assert_near_ties_only(states[0], g["vit_states"], g["frame"], g["log_start"], g["log_trans"], r, label=name)
     assert lps[0] == pytest.approx(float(g["vit_logprob"]), rel=1e-6 if prec == "f32" else 1e-10)
     st = eng.estep(ratios=rl, precision=prec)
     T = g["obs"].shape[0]
     assert st["logprob"] == pytest.approx(float(g["logprob"]), rel=TOL[prec])
     assert_allclose(st["start"], g["post"][0], rtol=TOL[prec], atol=ATOL[prec])
     if T > 1:
-        assert_allclose(st["trans"], np.exp(g["lneta"]), rtol=10 * TOL[prec], atol=ATOL[prec])
-    assert_allclose(st["obs"], g["obs_stats"], rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+        assert_allclose(st["trans"], np.exp(g["lneta"]), rtol=TOL[prec], atol=ATOL[prec])
+    assert_allclose(st["obs"], g["obs_stats"], rtol=TOL[prec], atol=ATOL[prec])
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
@@ -102,16 +80,15 @@ def test_multi_sequence_ragged(oracle, prec, warmup):
         assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=TOL[prec])
         post = oracle.posteriors(ref["fwd"], ref["bwd"], renorm_eps=True)
         assert_allclose(out["post"][i], post, rtol=TOL[prec], atol=ATOL[prec])
-        ref_map = np.argmax(post, axis=1)
-        agree = np.mean(out["map_states"][i] == ref_map)
-        assert agree >= (1.0 if prec == "f64" else 0.995)
+        if prec == "f64":
+            assert_array_equal(out["map_states"][i], np.argmax(post, axis=1))
+        else:
+            assert_map_near_ties_only(out["map_states"][i], post)
         assert out["map_score"][i] == pytest.approx(np.max(post, axis=1).sum(), rel=TOL[prec])
         if prec == "f64":
             assert_array_equal(states[i], ref["vit_states"])
         else:
-            mine = path_score(oracle, ref["frame"], m["log_start"], m["log_trans"], states[i])
-            assert mine == pytest.approx(ref["vit_logprob"], rel=1e-6)       # near-tie rule
-            assert np.mean(states[i] == ref["vit_states"]) >= 0.97
+            assert_near_ties_only(states[i], ref["vit_states"], ref["frame"], m["log_start"], m["log_trans"])
         assert lps[i] == pytest.approx(ref["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
     if warmup == 1:
         assert eng.ctx.stat("repair_passes_forward") > 0      # the repair path really ran
@@ -136,8 +113,19 @@ def test_estep_matches_oracle(oracle, prec):
     assert st["logprob"] == pytest.approx(lp, rel=TOL[prec])
     assert st["nobs"] == len(obs)
     assert_allclose(st["start"], s0, rtol=TOL[prec], atol=ATOL[prec])
-    assert_allclose(st["trans"], tr, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
-    assert_allclose(st["obs"], ob, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+    if prec == "f32":
+        assert_allclose(st["trans"], tr, rtol=TOL[prec], atol=ATOL[prec])
+    else:
+        # Documented divergence: at T = 3000 the REFERENCE's float64 log-space lattices
+        # carry ulp(|log alpha|) absolute rounding, 4.0e-10 relative on these counts against an
+        # extended-precision (64-bit mantissa) evaluation; our scaled-space float64 kernels meet the 1e-10
+        # contract against that arbiter and are within the reference's own error of the reference.
+        truth = trans_counts_extended([oracle_frame(oracle, o, m["table"]) for o in obs],
+                                      m["log_start"], m["log_trans"])
+        assert_allclose(st["trans"], truth, rtol=TOL[prec], atol=ATOL[prec])
+        assert min_rtol(tr, truth, ATOL[prec]) > TOL[prec]         # the reference itself is outside 1e-10 here
+        assert_allclose(st["trans"], tr, rtol=1e-9, atol=ATOL[prec])
+    assert_allclose(st["obs"], ob, rtol=TOL[prec], atol=ATOL[prec])
     # size-independent properties: posterior mass is conserved
     assert st["obs"].sum() == pytest.approx(sum(lens) * K, rel=1e-6)
     assert st["trans"].sum() * N == pytest.approx(sum(lens) - len(lens), rel=1e-6)
@@ -157,19 +145,22 @@ def test_segment_ratios(oracle, prec):
     ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"], r_em=r, r_dp=r)
     out = eng.posteriors(ratios_em=[r], ratios_dp=[r], renorm_eps=False, precision=prec)
     assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL[prec])
-    assert_allclose(out["post"][0], ref["post"], rtol=10 * TOL[prec], atol=ATOL[prec])
+    assert_allclose(out["post"][0], ref["post"], rtol=TOL[prec], atol=ATOL[prec])
     # decode(): emission WITHOUT ratios, DP with ratios (basehmm.py:327, hmm.py:674)
     ref2 = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"], r_em=None, r_dp=r)
     lps, states = eng.viterbi(ratios_em=None, ratios_dp=[r], precision=prec)
     assert lps[0] == pytest.approx(ref2["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
-    assert np.mean(states[0] == ref2["vit_states"]) >= (1.0 if prec == "f64" else 0.97)
+    if prec == "f64":
+        assert_array_equal(states[0], ref2["vit_states"])
+    else:
+        assert_near_ties_only(states[0], ref2["vit_states"], ref2["frame"], m["log_start"], m["log_trans"], r)
     # E-step with ratios
     K, N, S = m["table"].shape
     s0, tr, ob = np.zeros(N), np.zeros((N, N)), np.zeros((K, N, S))
     oracle.estep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"], r, s0, tr, ob)
     st = eng.estep(ratios=[r], precision=prec)
-    assert_allclose(st["trans"], tr, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
-    assert_allclose(st["obs"], ob, rtol=10 * TOL[prec], atol=10 * ATOL[prec])
+    assert_allclose(st["trans"], tr, rtol=TOL[prec], atol=ATOL[prec])
+    assert_allclose(st["obs"], ob, rtol=TOL[prec], atol=ATOL[prec])
 
 
 def test_wide_model_50_states(oracle):
@@ -187,13 +178,16 @@ def test_wide_model_50_states(oracle):
         assert_allclose(out["post"][0], ref["post"], rtol=TOL[prec], atol=ATOL[prec])
         lps, states = eng.viterbi(precision=prec)
         assert lps[0] == pytest.approx(ref["vit_logprob"], rel=1e-6)
-        assert np.mean(states[0] == ref["vit_states"]) >= (1.0 if prec == "f64" else 0.97)
+        if prec == "f64":
+            assert_array_equal(states[0], ref["vit_states"])
+        else:
+            assert_near_ties_only(states[0], ref["vit_states"], ref["frame"], m["log_start"], m["log_trans"])
     st = eng.estep(precision="f32")
     K, N, S = m["table"].shape
     s0, tr, ob = np.zeros(N), np.zeros((N, N)), np.zeros((K, N, S))
     oracle.estep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"], None, s0, tr, ob)
-    assert_allclose(st["trans"], tr, rtol=1e-4, atol=1e-5)
-    assert_allclose(st["obs"], ob, rtol=1e-4, atol=1e-5)
+    assert_allclose(st["trans"], tr, rtol=TOL["f32"], atol=ATOL["f32"])
+    assert_allclose(st["obs"], ob, rtol=TOL["f32"], atol=ATOL["f32"])
 
 
 @pytest.mark.parametrize("N", [33, 50, 64])
@@ -293,8 +287,7 @@ def test_tile_kernels_ragged(oracle, N, warmup, fine_len):
         assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=TOL["f32"])
         post = oracle.posteriors(ref["fwd"], ref["bwd"], renorm_eps=True)
         assert_allclose(out["post"][i], post, rtol=TOL["f32"], atol=ATOL["f32"])
-        ref_map = np.argmax(post, axis=1)
-        assert np.mean(out["map_states"][i] == ref_map) >= 0.995
+        assert_map_near_ties_only(out["map_states"][i], post)
         assert out["map_score"][i] == pytest.approx(np.max(post, axis=1).sum(), rel=TOL["f32"])
     if warmup == 1 and N >= 5:
         assert eng.ctx.stat("repair_passes_forward") > 0

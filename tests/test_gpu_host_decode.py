@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 from numpy.testing import assert_array_equal
 
+from parity import assert_map_near_ties_only, assert_near_ties_only, oracle_all, oracle_frame
+
 pytestmark = pytest.mark.gpu
 
 
@@ -38,8 +40,9 @@ def test_decode_host_matches_oracle(oracle, dtype, prec):
             assert_array_equal(states[i], ref["vit_states"])
             assert_array_equal(mstates[i], ref["map_states"])
         else:
-            assert np.mean(states[i] == ref["vit_states"]) >= 0.98
-            assert np.mean(mstates[i] == ref["map_states"]) >= 0.98
+            full = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+            assert_near_ties_only(states[i], ref["vit_states"], full["frame"], m["log_start"], m["log_trans"])
+            assert_map_near_ties_only(mstates[i], full["post"])
         tol = 1e-10 if prec == "f64" else 1e-5
         assert lp[i] == pytest.approx(ref["vit_logprob"], rel=1e-6 if prec == "f32" else 1e-10)
         assert flp[i] == pytest.approx(ref["logprob"], rel=tol)
@@ -174,7 +177,8 @@ def test_deferred_verification_falls_back_to_the_repair_loop(oracle):
             ref = oracle.sweep_sequence(obs, m["table"], 1.0, m["log_start"], m["log_trans"])
             assert out["logprob"][i] == pytest.approx(ref["logprob"], rel=1e-5)
             assert vlp[i] == pytest.approx(ref["vit_logprob"], rel=1e-6)
-            assert np.mean(vst[i] == ref["vit_states"]) >= 0.98
+            assert_near_ties_only(vst[i], ref["vit_states"], oracle_frame(oracle, obs, m["table"]),
+                                  m["log_start"], m["log_trans"])
         assert st["obs"].sum() == pytest.approx(sum(lens) * m["K"], rel=1e-5)
         # a healthy warm-up: the optimistic attempt stands (once the back-off after a refusal is over)
         assert eng.ctx._defer_skip > 0
