@@ -56,23 +56,29 @@ public:
     {
         if (n <= 0) return;
         if (workers_.empty() || n == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+        uint64_t gen;
         {
             std::lock_guard<std::mutex> l(mu_);
-            fn_ = &fn; ntasks_ = n; pending_ = n; next_.store(0); ++gen_;
+            fn_ = &fn; ntasks_ = n; pending_ = n; gen = ++gen_;
+            next_.store(gen << 32);               // generation in the high half: stale fetches are rejected
         }
         cv_.notify_all();
-        work();
+        work(gen, n, &fn);
         std::unique_lock<std::mutex> l(mu_);
         done_.wait(l, [this] { return pending_ == 0; });
         fn_ = nullptr;
     }
 private:
-    void work()
+    // A job is (generation, task count, function), snapshotted under the lock by whoever runs it.
+    // The task counter carries the generation in its high 32 bits, so a worker left over from
+    // generation g that fetches after parallel_for g+1 has reset the counter sees a foreign
+    // generation and leaves without running (or double counting) a task of the new job.
+    void work(uint64_t gen, int ntasks, const std::function<void(int)> *fn)
     {
         for (;;) {
-            const int i = next_.fetch_add(1);
-            if (i >= ntasks_) return;
-            (*fn_)(i);
+            const uint64_t v = next_.fetch_add(1);
+            if ((v >> 32) != (gen & 0xffffffffu) || (int)(v & 0xffffffffu) >= ntasks) return;
+            (*fn)((int)(v & 0xffffffffu));
             std::lock_guard<std::mutex> l(mu_);
             if (--pending_ == 0) done_.notify_all();
         }
@@ -81,13 +87,17 @@ private:
     {
         uint64_t seen = 0;
         for (;;) {
+            int ntasks;
+            const std::function<void(int)> *fn;
             {
                 std::unique_lock<std::mutex> l(mu_);
                 cv_.wait(l, [&] { return gen_ != seen; });
                 seen = gen_;
                 if (stop_) return;
+                ntasks = ntasks_; fn = fn_;
+                if (fn == nullptr) continue;      // the job finished before this worker woke up
             }
-            work();
+            work(seen, ntasks, fn);
         }
     }
     std::vector<std::thread> workers_;
@@ -96,7 +106,7 @@ private:
     bool stop_;
     uint64_t gen_;
     int pending_, ntasks_;
-    std::atomic<int> next_;
+    std::atomic<uint64_t> next_;
     const std::function<void(int)> *fn_ = nullptr;
 };
 

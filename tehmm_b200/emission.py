@@ -390,24 +390,3 @@ class IndependentMultinomialAndGaussianEmissionModel(IndependentMultinomialEmiss
         self.gaussParams[track.getNumber(), state] = (float(toks[2]), float(toks[3]))
         self.applyGaussian(track, state, logProbs)
         mask[track.getNumber(), state, :] = 1
-
-
-class PairEmissionModel(object):
-    """Pair priors for the CFG model; kept only so pickled models load (emission.py:621-650)."""
-
-    def __init__(self, emissionModel, pairPriors):
-        self.em = emissionModel
-        pp = []
-        for i in pairPriors:
-            if i is None:
-                pp.append([0, 0])
-            elif i == 1:
-                pp.append([NEGINF, 0.])
-            else:
-                pp.append([np.log(1. - i), np.log(i)])
-        self.logPriors = np.array(pp, dtype=np.float64)
-        assert self.logPriors.shape == (self.em.getNumStates(), 2)
-
-    def pairLogProb(self, state, logProb1, logProb2, match):
-        assert match == 0 or match == 1
-        return logProb1 + logProb2 + self.logPriors[state, int(match)]

@@ -62,6 +62,7 @@ class _ResultPool(object):
     only when the last of them is unreachable -- the caller sees ordinary, writable,
     independent int64 arrays."""
     MAX_FREE = 4
+    MAX_FREE_BYTES = 512 << 20       # what the pool may keep mapped between calls (a 250 M-step path is 2 GB)
 
     def __init__(self):
         self._free = []
@@ -69,8 +70,11 @@ class _ResultPool(object):
 
     def _put(self, block):
         with self._lock:
-            if len(self._free) < self.MAX_FREE:
+            held = sum(len(b) for b in self._free)
+            if len(self._free) < self.MAX_FREE and held + len(block) <= self.MAX_FREE_BYTES:
                 self._free.append(block)
+        # over the cap: the block is simply not kept -- it is unmapped when the dying array releases
+        # its buffer export (closing it here would raise: the export is still counted in a finalizer)
 
     def empty_int64(self, n):
         nbytes = max(8, int(n) * 8)

@@ -315,6 +315,8 @@ class MultitrackHmm(BaseHMM):
         # basehmm.py:389-392: the model's own algorithm wins over the argument
         if self._algorithm in decoder_algorithms:
             algorithm = self._algorithm
+        if algorithm not in decoder_algorithms:
+            raise KeyError(algorithm)                # basehmm.py:393-395: decoder[algorithm]
         if self._wide():
             return [self._wide_decode(o, algorithm) for o in obs_list]
         eng = self._engine()
@@ -470,12 +472,10 @@ class MultitrackHmm(BaseHMM):
         return {'nobs': 0, 'start': np.zeros(N), 'trans': np.zeros((N, N)),
                 'obs': self.emissionModel.initStats()}
 
-    def _device_estep(self, obs, stats, params, n_total, slots):
-        """All sequences of this rank in one device batch; returns the per-sequence
-        log-probabilities of the WHOLE job, in the caller's sequence order.
-        Replaces basehmm.py:509-522 + hmm.py:545-574."""
-        if self._wide():
-            return self._wide_estep(obs, stats, params, n_total, slots)
+    def _local_estep(self, obs, params, n_total, slots, stats_S):
+        """This rank's sequences in one device batch -> the packed float64 DEVICE tensor
+        [sum logprob | nseq | start N | trans N*N | obs K*N*S | per-sequence logprob of the whole job]
+        (Engine.estep).  Replaces basehmm.py:509-522 + hmm.py:545-574 for the shard."""
         eng = self._engine()
         # the observations do not change between EM iterations: they cross PCIe once per fit()
         token = getattr(self, "_fit_batch_token", None)
@@ -483,19 +483,36 @@ class MultitrackHmm(BaseHMM):
             eng.upload_batch(obs)
             eng.batch_ratios = eng.upload_ratios([self._seg_ratios(o) for o in obs])
             eng.batch_token = token
-        packed = eng.estep(ratios=eng.batch_ratios, want_start='s' in params, want_trans='t' in params,
-                           want_obs='e' in params, device_result=True, seq_slots=(n_total, slots),
-                           stats_S=stats['obs'].shape[2])
+        return eng.estep(ratios=eng.batch_ratios, want_start='s' in params, want_trans='t' in params,
+                         want_obs='e' in params, device_result=True, seq_slots=(n_total, slots),
+                         stats_S=stats_S)
+
+    def _device_estep(self, obs, stats, params, n_total, slots):
+        """E-step of one EM iteration over the ranks; returns the per-sequence log-probabilities of
+        the WHOLE job, in the caller's sequence order.  A rank whose shard is EMPTY (fewer sequences
+        than ranks, e.g. single-chromosome training on 8 GPUs) skips the device work and contributes
+        zeros to the all-reduce, so that every rank reaches the collective."""
+        if self._wide():
+            return self._wide_estep(obs, stats, params, n_total, slots)
+        N = self.n_components
+        K, _, S = stats['obs'].shape
+        base = 2 + N + N * N + K * N * S
+        if len(obs) > 0:
+            packed = self._local_estep(obs, params, n_total, slots, S)
+        else:
+            import torch
+            nccl = parallel._dist() is not None and parallel._dist().get_backend() == "nccl"
+            packed = torch.zeros(base + n_total, dtype=torch.float64, device="cuda" if nccl else "cpu")
         packed = parallel.all_reduce_stats(packed)       # the one collective of an EM iteration
-        res = eng.unpack_stats(packed.cpu().numpy())
-        stats['nobs'] += res['nobs']
+        host = packed.cpu().numpy()
+        stats['nobs'] += int(round(host[1]))
         if 's' in params:
-            stats['start'] += res['start']
+            stats['start'] += host[2:2 + N]
         if 't' in params:
-            stats['trans'] += res['trans']
+            stats['trans'] += host[2 + N:2 + N + N * N].reshape(N, N)
         if 'e' in params:
-            stats['obs'] += res['obs']
-        return res['logprobs']
+            stats['obs'] += host[2 + N + N * N:base].reshape(K, N, S)
+        return host[base:].copy()
 
     def fit(self, obs, **kwargs):
         """EM (basehmm.py:475-541, hmm.py:618-620).  `obs` is a list of TrackTables /

@@ -302,7 +302,53 @@ def counts_case():
     print("counts: total=%.1f" % stats.sum())
 
 
+def gaussian_case():
+    """emission.py:483-615: IndependentMultinomialAndGaussianEmissionModel -- constructor
+    (makeGaussian on the initial table), maximize() on posterior-weighted counts, and a user
+    `STATE TRACK MEAN STDEV` line.  Track 1 is gaussian over the values 0..11 (scaled category
+    map, track.py:668-760), tracks 0 and 2 stay multinomial."""
+    rng = np.random.RandomState(31)
+    N, syms = 3, [4, 12, 2]
+    tracks = []
+    for k, ns in enumerate(syms):
+        t = R.track.Track(number=k)
+        t.name = "t%d" % k
+        t.dist = "gaussian" if k == 1 else "multinomial"
+        t.valMap = R.track.CategoryMap(reserved=1)
+        for v in range(ns):
+            t.valMap.update(str(v) if k != 1 else str(float(3 * v)))     # values 0, 3, 6, ... for the gaussian track
+        tracks.append(t)
+    _, _, params = rand_model(rng, N, syms, zero_frac=0.0)
+    em = R.emission.IndependentMultinomialAndGaussianEmissionModel(
+        N, list(syms), tracks, params, zeroAsMissingData=True, fudge=0.0)
+    out = dict(N=N, syms=np.array(syms), init_params_0=np.array(params[0]), init_params_1=np.array(params[1]),
+               init_params_2=np.array(params[2]),
+               values_1=np.array([float(tracks[1].valMap.getMapBack(s)) for s in range(1, syms[1] + 1)]),
+               table0=em.getLogProbs().copy(), gauss0=em.gaussParams.copy())
+    stats = em.initStats()
+    T = 500
+    obs = rand_obs(rng, T, syms, np.uint8)
+    post = rng.dirichlet(np.ones(N), size=T)
+    em.accumulateStats(obs, stats, post)
+    out["obs"] = obs
+    out["post"] = post
+    out["stats"] = np.array(stats)
+    em.maximize(stats, tracks)
+    out["table1"] = em.getLogProbs().copy()
+    out["gauss1"] = em.gaussParams.copy()
+    logProbs = em.getLogProbs().copy()
+    mask = np.zeros(logProbs.shape, dtype=np.int8)
+    em.applyUserEmissionLine(tracks[1], 2, ["2", "t1", "7.5", "2.25"], logProbs, mask)
+    out["table_user"] = logProbs
+    out["mask_user"] = mask
+    out["gauss_user"] = em.gaussParams.copy()
+    np.savez_compressed(os.path.join(HERE, "gaussian.npz"), **out)
+    print("gaussian: mu/sigma state 0 = %s -> %s" % (out["gauss0"][1, 0], out["gauss1"][1, 0]))
+
+
 def main():
+    if "--only-gaussian" in sys.argv:
+        return gaussian_case()
     wikipedia_case()
     impossible_rows_case()
     dpbench_case()
@@ -323,6 +369,7 @@ def main():
     fit_case("fit_n4_k3", 21, 4, [3, 5, 2], [120, 1, 77, 300], 4)
     fit_case("fit_n30_k10", 22, 30, [4, 8, 16, 32, 64, 250, 2, 2, 2, 2], [400, 250, 90], 3)
     fit_case("fit_n5_k2_seg", 23, 5, [4, 6], [150, 80], 3, seg=True)
+    gaussian_case()
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def test_lpt_partition_is_balanced_and_complete():
     assert lpt_partition([5], 4) == [[0], [], [], []]
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, single=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -38,26 +38,22 @@ def _worker(rank, world, port, out_path):
 
     inner = oracle_estep(orc)
 
-    def estep(self, obs, stats, params, n_total, slots):
-        # same packing as engine.estep, on a CPU tensor, through the real all-reduce
-        local = {'nobs': 0, 'start': np.zeros_like(stats['start']), 'trans': np.zeros_like(stats['trans']),
-                 'obs': np.zeros_like(stats['obs'])}
+    def local_estep(self, obs, params, n_total, slots, stats_S):
+        # same packing as Engine.estep, on a CPU tensor; the real MultitrackHmm._device_estep around it
+        # does the all-reduce (gloo here, NCCL on the GPU box) and the empty-shard handling
+        N, K = self.n_components, self.emissionModel.getNumTracks()
+        local = {'nobs': 0, 'start': np.zeros(N), 'trans': np.zeros((N, N)), 'obs': np.zeros((K, N, stats_S))}
         lps = inner(self, obs, local, params, n_total, slots)
-        packed = torch.from_numpy(np.concatenate([[lps.sum(), local['nobs']], local['start'],
-                                                  local['trans'].ravel(), local['obs'].ravel(), lps]))
-        packed = parallel.all_reduce_stats(packed).numpy()
-        N = self.n_components
-        K, _, S = stats['obs'].shape
-        base = 2 + N + N * N + K * N * S
-        stats['nobs'] += int(round(packed[1]))
-        stats['start'] += packed[2:2 + N]
-        stats['trans'] += packed[2 + N:2 + N + N * N].reshape(N, N)
-        stats['obs'] += packed[2 + N + N * N:base].reshape(K, N, S)
-        return packed[base:]
+        return torch.from_numpy(np.concatenate([[lps.sum(), local['nobs']], local['start'],
+                                                local['trans'].ravel(), local['obs'].ravel(), lps]))
 
-    MultitrackHmm._device_estep = estep
+    MultitrackHmm._local_estep = local_estep
     g, hmm, em, tables = load_fit_case("fit_n4_k3")
-    assert len(parallel.shard(tables)) < len(tables)
+    if single:
+        tables = tables[:1]          # fewer sequences than ranks: one rank's shard is EMPTY
+        assert sorted(len(b) for b in parallel.lpt_partition([len(t) for t in tables], world)) == [0, 1]
+    else:
+        assert len(parallel.shard(tables)) < len(tables)
     hmm.fit(tables)
     np.savez(out_path % rank, transmat=hmm.transmat_, startprob=hmm.startprob_, table=em.getLogProbs(),
              last=hmm.getLastLogProb())
@@ -78,6 +74,31 @@ def test_two_rank_fit_equals_reference(tmp_path):
     np.testing.assert_allclose(r0["startprob"], g["fit_startprob"], rtol=1e-10)
     np.testing.assert_allclose(r0["table"], g["fit_table"], rtol=1e-10)
     assert float(r0["last"]) == pytest.approx(float(g["fit_last_logprob"]), rel=1e-12)
+
+
+def test_two_rank_fit_with_an_empty_shard(oracle, tmp_path):
+    """ONE sequence on two ranks (single-chromosome training on a multi-GPU box): the rank without
+    work must still reach the all-reduce of every iteration (it used to raise in upload_batch while
+    the other rank waited forever) and end with the same parameters as a single-process fit."""
+    import torch.multiprocessing as mp
+    from tehmm_b200.hmm import MultitrackHmm
+    from test_gpu_api import load_fit_case
+    from test_host_logic import oracle_estep
+    port = 31500 + (os.getpid() % 2000)
+    out = str(tmp_path / "single%d.npz")
+    mp.spawn(_worker, args=(2, port, out, True), nprocs=2, join=True)
+    r0, r1 = np.load(out % 0), np.load(out % 1)
+    g, hmm, em, tables = load_fit_case("fit_n4_k3")
+    hmm._device_estep = lambda obs, stats, params, n_total, slots: oracle_estep(oracle)(
+        hmm, obs, stats, params, n_total, slots)
+    hmm.fit(tables[:1])
+    for r in (r0, r1):
+        np.testing.assert_allclose(r["transmat"], hmm.transmat_, rtol=1e-12)
+        np.testing.assert_allclose(r["startprob"], hmm.startprob_, rtol=1e-12)
+        np.testing.assert_allclose(r["table"], em.getLogProbs(), rtol=1e-12)
+        assert float(r["last"]) == pytest.approx(hmm.getLastLogProb(), rel=1e-12)
+    for key in ("transmat", "startprob", "table"):
+        np.testing.assert_array_equal(r0[key], r1[key])
 
 
 # ---------------------------------------------------------------------------
