@@ -271,7 +271,7 @@ def run_ours(args):
         mark(2)
         _, mstates, mscore = eng.run_backward(prec, tdt, _lib.BWD_MAP, blin, alpha, None)
         mark(3)
-        states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False)
+        states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False, rowmax=rowmax)
         mark(4)
         return logprob, mscore, vlp, states, mstates
 

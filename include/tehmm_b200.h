@@ -223,13 +223,18 @@ int tehmm_run_emission_stats(tehmm_ctx *ctx, int prec, const void *d_post,
 
 /* Viterbi with traceback (hmm.py:668-676 -> _hmm.pyx:201-259).
  * d_states total uint8 (required), d_states64 total int64 (optional, NULL to
- * skip), d_logprob nseq float64 (fp64 re-score of the returned path).
+ * skip), d_logprob nseq float64: the reference's viterbi_lattice[T-1, argmax]
+ * (_hmm.pyx:252-254).  Where the fp32 production DP runs (<= 32 states, no DP
+ * ratios) and d_rowmax (tehmm_run_emission's output; may be NULL) is given, it is
+ * the DP's own value -- the row maxima it takes out, summed in float64 across
+ * steps, plus rowmax; otherwise, and always with context option "rescore" = 1,
+ * a float64 re-score of the returned path against the float64 tables.
  * d_lattice: workspace of tehmm_viterbi_workspace_bytes() for the delta lattice.
  * d_ratios_emission: the ratios the emission was computed with (only used by
  * the re-score); d_ratios_dp: the ratios the DP applies (basehmm.py:327 vs
  * hmm.py:674 use different ones).                                            */
 int64_t tehmm_viterbi_workspace_bytes(tehmm_ctx *ctx, int prec);
-int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog,
+int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog, const double *d_rowmax,
                       const double *d_ratios_emission, const double *d_ratios_dp,
                       void *d_lattice, uint8_t *d_states, int64_t *d_states64,
                       double *d_logprob, void *d_scratch);

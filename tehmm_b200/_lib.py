@@ -60,7 +60,7 @@ SIGNATURES = {
     "tehmm_run_backward": (_c_int, [_c_void, _c_int, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_run_emission_stats": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_int, _c_void]),
     "tehmm_viterbi_workspace_bytes": (_c_i64, [_c_void, _c_int]),
-    "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_decode_host": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_i64, _c_void, _c_int, _c_int, _c_void, _c_void, _c_void]),
     "tehmm_decode_host_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_ctx_device": (_c_int, [_c_void]),

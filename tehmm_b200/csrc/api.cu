@@ -26,7 +26,9 @@ cudaError_t tehmm_launch_forward_logprob(cudaStream_t, const TehmmBatchDev &, in
 cudaError_t tehmm_launch_backward(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, int, const void *, const void *, const double *, void *, uint8_t *, double *, void *, void *, void *, void *, void *, const int *, int, int);
 cudaError_t tehmm_launch_trans_reduce(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const void *, const void *, double *);
 cudaError_t tehmm_launch_map_reduce(cudaStream_t, const TehmmBatchDev &, const double *, double *);
-cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, void *, void *, void *, const int *, int, int);
+cudaError_t tehmm_launch_viterbi(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, void *, void *, void *, const int *, int, int, const double *, double *);
+bool tehmm_viterbi_dp_scores(const TehmmModelDev &, int, const double *);
+cudaError_t tehmm_launch_vit_score_reduce(cudaStream_t, const TehmmBatchDev &, const double *, double *);
 cudaError_t tehmm_launch_traceback(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const void *, const double *, uint8_t *, int64_t *, uint8_t *, uint8_t *, const uint8_t *, const int *, int, int);
 cudaError_t tehmm_launch_tb_verify(cudaStream_t, const TehmmBatchDev &, uint8_t *, const uint8_t *, uint8_t *, int *, int *);
 cudaError_t tehmm_launch_rescore(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const uint8_t *, const double *, const double *, double *, double *, int64_t, int64_t);
@@ -91,6 +93,7 @@ struct tehmm_ctx {
     int64_t opt_umma = 0;             // 1: forward pass on tcgen05 / TMEM (umma.cu) where it applies -- correct, not yet faster
     int *d_fault = nullptr;           // raised by a kernel whose barrier protocol timed out
     int64_t stat_umma_passes = 0;
+    int64_t opt_rescore = 0;          // 1: the Viterbi log-probability is always the float64 re-score of the returned path (default: the fp32 DP's own normaliser sum where the lean kernel runs)
     int64_t opt_bwd_tmap = 0;         // 1: backward pass of the regular tiles by bwd_tile_tmap_kernel (tensor-map blocks) -- correct, not faster (profiles/r01_notes_v4.md)
     int64_t opt_xi_tile = 1;          // expected transition counts by xi_tile_kernel (0: one-chunk-per-warp backward)
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
@@ -213,6 +216,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
     else if (!strcmp(name, "defer")) c->opt_defer = v;
     else if (!strcmp(name, "bwd_tmap")) c->opt_bwd_tmap = v;
+    else if (!strcmp(name, "rescore")) c->opt_rescore = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -1030,9 +1034,9 @@ int tehmm_run_emission_stats(tehmm_ctx *c, int prec, const void *d_post, const d
     return TEHMM_OK;
 }
 
-int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *d_ratios_emission,
-                      const double *d_ratios_dp, void *d_lattice, uint8_t *d_states,
-                      int64_t *d_states64, double *d_logprob, void *d_scratch)
+int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *d_rowmax,
+                      const double *d_ratios_emission, const double *d_ratios_dp, void *d_lattice,
+                      uint8_t *d_states, int64_t *d_states64, double *d_logprob, void *d_scratch)
 {
     RUN_PROLOGUE();
     if (!d_elog || !d_lattice || !d_states || !d_logprob || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument (d_states is required; d_states64 is optional)");
@@ -1049,9 +1053,14 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     const int tb_grid = (int)std::max<int64_t>(1, std::min<int64_t>((TBP.nchunks + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA, (int64_t)c->sms * 5));
     const TehmmBatchDev &PB = c->b;
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : c->b.nchunks + 1;
+    // The log-probability: the DP's own value (sum of the row maxima it takes out, float64 across steps,
+    // plus rowmax) where the lean fp32 kernel runs and the caller passed rowmax; otherwise -- float64
+    // mode, segment ratios, more than 32 states, option "rescore" -- the float64 re-score of the path.
+    const bool dp_score = d_rowmax != nullptr && c->opt_rescore == 0 && tehmm_viterbi_dp_scores(c->m, prec, d_ratios_dp);
+    double *dsp = dp_score ? (double *)(w + s.cscale) : nullptr;
     // ---- DP: delta lattice, chunk starts speculated / verified / repaired
     tk_begin(c, TK_VITERBI_DP);
-    CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid));
+    CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid, d_rowmax, dsp));
     tk_end(c, TK_VITERBI_DP);
     c->launches += 1;
     const double tol = tolerance(prec, true);
@@ -1064,7 +1073,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
         c->stat_repair_vit += 1; c->stat_bad_vit += nb;
-        CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 1, grid));
+        CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 1, grid, d_rowmax, dsp));
         c->launches += 1;
     }
     // ---- traceback: chunk end states speculated / verified / repaired
@@ -1086,9 +1095,14 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         c->launches += 1;
     }
     tk_begin(c, TK_RESCORE);
-    CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob, 0, TBP.total));   // latency bound too: fine partition
+    if (dp_score) {
+        CU(tehmm_launch_vit_score_reduce(st, c->b, dsp, d_logprob));
+        c->launches += 1;
+    } else {
+        CU(tehmm_launch_rescore(st, c->m, TBP, d_states, d_ratios_emission, d_ratios_dp, sp, d_logprob, 0, TBP.total));   // latency bound too: fine partition
+        c->launches += 2;
+    }
     tk_end(c, TK_RESCORE);
-    c->launches += 2;
     return TEHMM_OK;
 }
 

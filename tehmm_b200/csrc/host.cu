@@ -405,7 +405,7 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         // ---- the trellis
         if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
         if (viterbi) {
-            HOK(tehmm_run_viterbi(c, prec, A + o_la, nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
+            HOK(tehmm_run_viterbi(c, prec, A + o_la, (const double *)(A + o_rowmax), nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
         } else {
             HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
             HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_la, A + o_lb, nullptr, nullptr,

@@ -224,8 +224,15 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 3)
 viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ elog,
                     float *__restrict__ lattice, float *__restrict__ start_vec,
-                    float *__restrict__ end_vec, const int *__restrict__ bad, int mode)
+                    float *__restrict__ end_vec, const int *__restrict__ bad, int mode,
+                    const double *__restrict__ rowmax, double *__restrict__ score_part)
 {
+    // score_part != nullptr: the chunk also returns its share of the Viterbi log-probability,
+    //     sum over its rows of (the maximum M_t taken out of the delta row + rowmax[t]),
+    // i.e. the reference's viterbi_lattice[T-1, argmax] (_hmm.pyx:252-254) telescoped over the
+    // max-normalised rows (the last row's maximum is 0).  M_t is summed in fp32 over VIT_U steps
+    // and then in float64; the chunks' shares add up because a verified start vector is the true
+    // normalised row (both have maximum 0).  This replaces the float64 re-score pass.
     __shared__ __align__(16) float ds_all[TEHMM_WARPS_PER_CTA][2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane & 1, a2 = lane & ~1;
@@ -256,7 +263,8 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         float *lp = lattice + tw * 32 + lane;
         unsigned row = 0;
         const unsigned row0 = (unsigned)(ch.t0 - tw), row1 = (unsigned)(ch.t1 - tw);
-        float dd;
+        float dd, msum = 0.f;
+        double macc = 0.0;
 
         // one DP step from dd (all lanes) with emission value et.  wr / rd: shared-space
         // addresses of this lane's slot and of its half of the vector in the buffer used by
@@ -289,6 +297,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             // all -inf row gives -inf - -inf = NaN, which the max turns back into -inf.
             const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
             dd = fmaxf(v - M, -INFINITY);
+            msum += M;
         };
         uint32_t wrA = ds_wr, wrB = ds_wr + 128u, rdA = ds_rd, rdB = ds_rd + 128u;
         auto step1 = [&](float et) {       // single step, then swap the buffers
@@ -303,7 +312,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             const float v = ls + (own ? *ep : -INFINITY);
             const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
             dd = v - (M > -INFINITY ? M : 0.f);
-            if (row0 == 0) *lp = dd;
+            if (row0 == 0) { *lp = dd; macc = (double)M; }
             ep += 32; lp += 32;
             row = 1;
         } else {
@@ -312,6 +321,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         if (mode == 0 && row0 > 0) {
             for (; row < row0; ++row) { step1(*ep); ep += 32; lp += 32; }
             start_vec[ci * 32 + lane] = dd;
+            msum = 0.f;                   // warm-up rows belong to the chunk on the left
         }
         // steady state: the next VIT_U rows of e in flight; VIT_U is even, so the buffer
         // parity is the same at the top of every iteration
@@ -334,6 +344,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             }
             lp += VIT_U * 32;
             row += VIT_U;
+            macc += (double)msum; msum = 0.f;
         }
         if (row + VIT_U <= row1) {
 #pragma unroll
@@ -346,6 +357,13 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         }
         for (; row < row1; ++row) { step1(*ep); *lp = dd; ep += 32; lp += 32; }
         end_vec[ci * 32 + lane] = dd;
+        if (score_part != nullptr) {
+            double rs = 0.0;
+            for (int64_t t = ch.t0 + lane; t < ch.t1; t += 32) rs += rowmax[t];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(TEHMM_FULL, rs, o);
+            if (lane == 0) score_part[ci] = macc + (double)msum + rs;
+        }
     }
 }
 
@@ -723,13 +741,20 @@ static cudaError_t launch_vit(cudaStream_t st, const TehmmModelDev &m, const Teh
     return cudaGetLastError();
 }
 
+// the DP that can return the log-probability itself (viterbi_lean_kernel's score_part)
+bool tehmm_viterbi_dp_scores(const TehmmModelDev &m, int prec, const double *ratios)
+{
+    return prec == TEHMM_F32 && m.NS == 1 && m.LD == 32 && !ratios;
+}
+
 cudaError_t tehmm_launch_viterbi(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                  int prec, const void *elog, const double *ratios, void *lattice,
-                                 void *start_vec, void *end_vec, const int *bad, int mode, int grid)
+                                 void *start_vec, void *end_vec, const int *bad, int mode, int grid,
+                                 const double *rowmax, double *score_part)
 {
     if (prec == TEHMM_F32) {
         if (m.NS == 1 && m.LD == 32 && !ratios) {
-            viterbi_lean_kernel<<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode);
+            viterbi_lean_kernel<<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, rowmax, rowmax ? score_part : nullptr);
             return cudaGetLastError();
         }
         if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
@@ -784,6 +809,15 @@ cudaError_t tehmm_launch_tb_verify(cudaStream_t st, const TehmmBatchDev &b, uint
     cudaError_t e = cudaMemsetAsync(nbad, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     vit_tb_verify_kernel<<<(int)((b.nchunks + 127) / 128), 128, 0, st>>>(b, spec_end, pred, forced_end, bad, nbad);
+    return cudaGetLastError();
+}
+
+// per-sequence sum of the chunks' shares of the log-probability (viterbi_lean_kernel's score_part)
+cudaError_t tehmm_launch_vit_score_reduce(cudaStream_t st, const TehmmBatchDev &b, const double *score_part,
+                                          double *logprob)
+{
+    const int64_t cps = b.nchunks / b.nseq;
+    vit_score_reduce_kernel<<<(int)b.nseq, cps >= 2048 ? 1024 : cps >= 256 ? 256 : 64, 0, st>>>(b, score_part, logprob);
     return cudaGetLastError();
 }
 

@@ -343,15 +343,15 @@ class Engine(object):
         _lib.check(self.lib.tehmm_run_emission_stats(self.ctx.handle, prec, self._p(post), self._p(d_ratios),
                                                      self._p(obs_stats), int(stats_S), self._p(sc)))
 
-    def run_viterbi(self, prec, elog, d_ratios_em, d_ratios_dp, want64=True):
+    def run_viterbi(self, prec, elog, d_ratios_em, d_ratios_dp, want64=True, rowmax=None):
         torch = self.torch
         bp = self.empty(int(self.lib.tehmm_viterbi_workspace_bytes(self.ctx.handle, prec)), torch.uint8)
         states = self.empty(self.total, torch.uint8)
         states64 = self.empty(self.total, torch.int64) if want64 else None
         logprob = self.empty(self.nseq, torch.float64)
         sc = self.scratch(prec)
-        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), self._p(d_ratios_em),
-                                              self._p(d_ratios_dp), self._p(bp), self._p(states),
+        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), self._p(rowmax),
+                                              self._p(d_ratios_em), self._p(d_ratios_dp), self._p(bp), self._p(states),
                                               self._p(states64), self._p(logprob), self._p(sc)))
         return states, states64, logprob
 
@@ -417,8 +417,9 @@ class Engine(object):
         """decode(algorithm='viterbi') for the batch (basehmm.py:301-330, hmm.py:668-676)."""
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
-        elog, _, _ = self.run_emission(prec, tdt, d_re, True, False)
-        states, _, logprob = self.ctx.optimistic(lambda: self.run_viterbi(prec, elog, d_re, d_rd, want64=False))
+        elog, _, rowmax = self.run_emission(prec, tdt, d_re, True, False)
+        states, _, logprob = self.ctx.optimistic(
+            lambda: self.run_viterbi(prec, elog, d_re, d_rd, want64=False, rowmax=rowmax))
         return logprob.cpu().numpy(), self.split(self.states_to_host(states))
 
     # ------------------------------------------------------------ one window of a time-sharded sequence
@@ -436,8 +437,8 @@ class Engine(object):
         states = self.empty(self.total, torch.uint8)
         logprob = self.empty(1, torch.float64)
         sc = self.scratch(prec)
-        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), None, None, self._p(lattice),
-                                              self._p(states), None, self._p(logprob), self._p(sc)))
+        _lib.check(self.lib.tehmm_run_viterbi(self.ctx.handle, prec, self._p(elog), None, None, None,
+                                              self._p(lattice), self._p(states), None, self._p(logprob), self._p(sc)))
         part = self.empty(1, torch.float64)
         _lib.check(self.lib.tehmm_path_score(self.ctx.handle, self._p(states), None, None, a - w0, b - w0,
                                              self._p(part), self._p(sc)))

@@ -139,8 +139,8 @@ def run_c5(scale):
     prec, tdt = eng._prec("f32")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record()
-    elog, _, _ = eng.run_emission(prec, tdt, None, True, False)
-    states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False)
+    elog, _, rm = eng.run_emission(prec, tdt, None, True, False)
+    states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False, rowmax=rm)
     ev[1].record()
     del elog
     _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
