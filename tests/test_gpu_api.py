@@ -49,24 +49,26 @@ def test_wikipedia_example(prec):
     hmm, em = make_hmm([3], [EMISSIONPROB])
     obs = np.asarray([[0], [1], [2]])
     assert_array_equal(hmm._compute_log_likelihood(obs), g["v1_frame"])
+    # fp32: the log-probability is the fp32 DP's own value (viterbi_lean_kernel), contract 1e-5
+    rel = 1e-9 if prec == "f64" else 1e-6
     lp, st = hmm.decode(obs)
-    assert math.exp(lp) == pytest.approx(0.01344, rel=1e-9)
+    assert math.exp(lp) == pytest.approx(0.01344, rel=rel)
     assert_array_equal(st, [1, 0, 0])
     assert st.dtype == np.int64
     hmm3, _ = make_hmm([3, 1, 1], [EMISSIONPROB, [[1.], [1.]], [[1.], [1.]]])
     lp, st = hmm3.decode(np.asarray([[0, 0, 0], [1, 0, 0], [2, 0, 0]]))
-    assert math.exp(lp) == pytest.approx(0.01344, rel=1e-9)
+    assert math.exp(lp) == pytest.approx(0.01344, rel=rel)
     assert_array_equal(st, [1, 0, 0])
     hmm4, _ = make_hmm([3, 1, 1, 10], [EMISSIONPROB, [[1.], [1.]], [[1.], [1.]], [[.1] * 10, [.1] * 10]])
     obs4 = np.asarray([[0, 0, 0, 0], [1, 0, 0, 5], [2, 0, 0, 7]])
     lp, st = hmm4.decode(obs4)
-    assert math.exp(lp) == pytest.approx(0.01344 * 1e-3, rel=1e-9)
+    assert math.exp(lp) == pytest.approx(0.01344 * 1e-3, rel=rel)
     assert_array_equal(st, [1, 0, 0])
     table4 = IntegerTrackTable(4, "scaffold_1", 10, 13)
     for row in range(4):
         table4.writeRow(row, [obs4[0][row], obs4[1][row], obs4[2][row]])
     lp, st = hmm4.decode(table4)
-    assert math.exp(lp) == pytest.approx(0.01344 * 1e-3, rel=1e-9)
+    assert math.exp(lp) == pytest.approx(0.01344 * 1e-3, rel=rel)
     assert_array_equal(st, [1, 0, 0])
     # posteriors (hmmTest.py:147-151 values hold for the eps-renormalised score_samples)
     sc, post = hmm.score_samples(obs)

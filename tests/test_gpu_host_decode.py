@@ -112,7 +112,8 @@ def test_time_sharded_single_sequence_virtual_ranks(nranks):
         if kind == "viterbi":
             path = np.concatenate([r["result"][1] for r in res])
             assert_array_equal(path, st_full[0])
-            assert sum(r["result"][0] for r in res) == pytest.approx(lp_full[0], rel=1e-12)
+            # the shards return float64 path scores, the single-GPU decode the fp32 DP's own value
+            assert sum(r["result"][0] for r in res) == pytest.approx(lp_full[0], rel=1e-8)
         elif kind == "map":
             assert_array_equal(np.concatenate([r["result"] for r in res]), out["map_states"][0])
         else:
