@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-em", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="skip the strong-scaling runs of configs 3 and 4")
     return ap.parse_args()
 
 
@@ -216,13 +217,98 @@ def run_reference_arm(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args.T, args.gpus),
+            "data": "synthetic",
+            "config": dict(workload_config(args.T, args.gpus),
+                           ran="bounded sample of that workload: %d processes x %d observations per step "
+                               "(same model, one sequence each); the reference is O(T), cells/s does not depend on T" % (cores, per),
+                           obs_per_step=cores * per),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": "%d processes x %d observations per step (one sequence each, "
                                        "teHmmEval --chroms --proc style), N=30, K=10" % (cores, per)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ strong scaling of configs 3 and 4
+def run_split(world, rank):
+    """BASELINE.json configs[3] and [2] split over the ranks the way north_star says: the 24
+    chromosomes of the hg19-scale decode and the 350 training sequences are dealt to the ranks by
+    longest-processing-time bin packing (parallel.shard_indices); decoding needs no collective, an
+    EM iteration ends in ONE all-reduce of the packed statistics.  Fixed total work (strong
+    scaling); host wall clock between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tehmm_b200 import parallel, synth
+    from tehmm_b200.emission import IndependentMultinomialEmissionModel
+    from tehmm_b200.hmm import MultitrackHmm
+
+    def reduce(x, op):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def make_hmm(m, **kw):
+        em = IndependentMultinomialEmissionModel(m["N"], list(m["syms"]), zeroAsMissingData=True)
+        em.logProbs = m["table"].copy()
+        return MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy(), **kw), em
+
+    def sample_long(m, T, seed, piece=4_000_000):
+        out = np.empty((T, m["K"]), dtype=np.uint8)
+        for i, a in enumerate(range(0, T, piece)):
+            n = min(piece, T - a)
+            out[a:a + n] = synth.sample_obs(m, n, seed=seed + i)[0]
+        return out
+
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
+    out = {}
+    m = synth.make_model(N=N_STATES, seed=0)
+    # ---- config 4: hg19-scale decode, chromosomes sharded
+    lens = synth.bench_lengths("c4")
+    idx = parallel.shard_indices(lens)
+    mine = [sample_long(m, lens[i], seed=200 + 7 * i) for i in idx]
+    hv, _ = make_hmm(m)
+    hm, _ = make_hmm(m, algorithm="map")
+    for _ in range(2):
+        hv.decode_batch(mine); hm.decode_batch(mine)
+    best = None
+    for _ in range(3):
+        barrier(); t0 = time.perf_counter()
+        hv.decode_batch(mine)
+        hm.decode_batch(mine)
+        torch.cuda.synchronize()
+        dt = reduce(time.perf_counter() - t0, MAX)
+        best = dt if best is None else min(best, dt)
+    out["c4_decode"] = {"what": "hg19-scale decode (24 sequences, %d bins), Viterbi + MAP through decode_batch with host "
+                                "buffers, sequences dealt to %d rank(s); no collective" % (sum(lens), world),
+                        "seconds": best, "cells_per_s": sum(lens) * N_STATES / best,
+                        "largest_shard_steps": int(reduce(sum(lens[i] for i in idx), MAX))}
+    del mine
+    # ---- config 3: Baum-Welch iterations, sequences sharded, one all-reduce per iteration
+    lens = synth.bench_lengths("c3")
+    own = set(parallel.shard_indices(lens))
+    seqs = [synth.sample_obs(m, n, seed=100 + i)[0] if i in own else np.zeros((n, m["K"]), dtype=np.uint8)
+            for i, n in enumerate(lens)]
+    m0 = synth.make_model(N=N_STATES, seed=7, zero_frac=0.0)
+    hmm, _ = make_hmm(m0, n_iter=2, thresh=0.0)
+    hmm.fit(seqs)                       # warm-up (allocator, kernels, NCCL)
+    n_iter = 10
+    hmm, _ = make_hmm(m0, n_iter=n_iter, thresh=0.0)
+    barrier(); t0 = time.perf_counter()
+    hmm.fit(seqs)
+    torch.cuda.synchronize()
+    dt = reduce(time.perf_counter() - t0, MAX)
+    out["c3_em"] = {"what": "Baum-Welch on 350 sequences (%d steps) through MultitrackHmm.fit, %d iterations, sequences "
+                            "dealt to %d rank(s), one all-reduce + host M-step per iteration" % (sum(lens), n_iter, world),
+                    "seconds_per_em_iteration": dt / n_iter, "cells_per_s_per_iteration": sum(lens) * N_STATES / (dt / n_iter)}
+    return out
 
 
 # ------------------------------------------------------------------ our arm
@@ -302,7 +388,6 @@ def run_ours(args):
         out = sweep(evs[k])
     barrier()
     launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
     stage_ms = np.zeros(4)
     total_ms = 0.0
     for k in range(args.steps):
@@ -338,38 +423,41 @@ def run_ours(args):
     # algorithmic bytes per time step of each kernel: symbols in, compulsory fp32 lattice spill, states out
     alg_bytes = {"emission": K, "forward": K + 4 * N_STATES, "backward": K + 4 * N_STATES + 1,
                  "viterbi_dp": K + N_STATES, "traceback": 2, "rescore": 0}
-    # DRAM bytes per launch from the committed `ncu --set full` capture of this command
-    # (profiles/r01_ncu_full_v3.txt: dram__bytes_read.sum + dram__bytes_write.sum), 10 M x 30 x 10 only
-    ncu_traffic = {"emission": 2.68e9, "forward": 2.79e9, "backward": 2.73e9, "viterbi_dp": 2.55e9, "traceback": 1.46e9,
-                   "rescore": 0.12e9}
-    # the dominant kernel: the longest one; when another is within 5 % of it and moves more algorithmic
-    # bytes, that one (backward and the Viterbi DP tie at ~0.8 ms and would swap from run to run; the
-    # DP's bound is fp32 issue, not HBM -- DESIGN.md section 5 -- so its HBM fraction says little).
-    # kernel_frac below lists every kernel either way.
-    longest = max(kern_us.values())
-    dom = max((k for k in kern_us if kern_us[k] >= 0.95 * longest), key=lambda k: (alg_bytes[k], kern_us[k]))
+    # DRAM bytes per launch: `ncu --set full` capture of this command (dram__bytes_read.sum +
+    # dram__bytes_write.sum per kernel), 10 M x 30 x 10 only; the stamp says which capture
+    traffic_src = os.path.join(ROOT, "profiles", "r02_sweep_traffic.json")
+    ncu_traffic, traffic_stamp = None, None
+    if os.path.exists(traffic_src) and T == T_DEFAULT and args.precision == "f32":
+        tj = json.load(open(traffic_src))
+        ncu_traffic, traffic_stamp = tj["bytes_per_launch"], {"file": "profiles/r02_sweep_traffic.json", "commit": tj.get("commit"),
+                                                              "capture": tj.get("capture")}
+    # the dominant kernel is the longest one, whatever it moves; the headline fraction is the whole
+    # sweep's (its 303 algorithmic bytes per step over the time of ALL its kernels)
+    dom = max(kern_us, key=lambda k: kern_us[k])
     dom_s = kern_us[dom] * 1e-6
-    achieved = alg_bytes[dom] * T / dom_s / 1e9
-    sweep_achieved = (3 * K + 9 * N_STATES + 3) * T / (total_ms / args.steps * 1e-3) / 1e9
-    have_traffic = T == T_DEFAULT and args.precision == "f32"
-    traffic_total = float(sum(ncu_traffic.values())) if have_traffic else None
-    traffic_gbs = traffic_total / (total_ms / args.steps * 1e-3) / 1e9 if have_traffic else None
-    kernel_dram_frac = ({k: (ncu_traffic[k] / (v * 1e-6) / 1e9 / peak if v > 0 else None) for k, v in kern_us.items()}
-                        if have_traffic else None)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak,
-                "traffic": ncu_traffic.get(dom) if (T == T_DEFAULT and args.precision == "f32") else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_step": alg_bytes[dom],
-                "kernel_choice": "longest kernel; within 5 % of it, the one with more algorithmic bytes",
+    sweep_s = total_ms / args.steps * 1e-3
+    sweep_alg = 3 * K + 9 * N_STATES + 3
+    sweep_achieved = sweep_alg * T / sweep_s / 1e9
+    traffic_total = float(sum(ncu_traffic.get(k, 0.0) for k in kern_us)) if ncu_traffic else None
+    traffic_gbs = traffic_total / sweep_s / 1e9 if ncu_traffic else None
+    vit_stage_us = kern_us["viterbi_dp"] + kern_us["traceback"] + max(kern_us["rescore"], 0)
+    roofline = {"bound": "hbm", "scope": "whole sweep: every kernel of one step", "achieved": sweep_achieved, "peak": peak,
+                "unit": "GB/s", "frac": sweep_achieved / peak, "traffic": traffic_total, "traffic_source": traffic_stamp,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": sweep_alg,
+                "dram_gbs": traffic_gbs, "dram_frac": traffic_gbs / peak if traffic_gbs else None,
+                "kernel": dom, "kernel_choice": "longest kernel of the step by its own CUDA-event time, no tie-break",
+                "dominant_kernel": {"name": dom, "us": kern_us[dom], "algorithmic_bytes_per_step": alg_bytes[dom],
+                                    "achieved": alg_bytes[dom] * T / dom_s / 1e9, "frac": alg_bytes[dom] * T / dom_s / 1e9 / peak,
+                                    "traffic": ncu_traffic.get(dom) if ncu_traffic else None},
+                "dominant_stage": {"name": "viterbi (DP + traceback + score)", "us": vit_stage_us,
+                                   "algorithmic_bytes_per_step": K + N_STATES + 2,
+                                   "frac": (K + N_STATES + 2) * T / (vit_stage_us * 1e-6) / 1e9 / peak},
                 "kernel_us": kern_us,
                 "kernel_frac": {k: (alg_bytes[k] * T / (v * 1e-6) / 1e9 / peak if v > 0 else None) for k, v in kern_us.items()},
-                "sweep": {"achieved": sweep_achieved, "frac": sweep_achieved / peak,
-                          "algorithmic_bytes_per_step": 3 * K + 9 * N_STATES + 3,
-                          # what the sweep really moves (lattices are materialised): the ncu DRAM
-                          # bytes of its six kernels over the measured sweep time, against the same peak
-                          "dram_traffic": traffic_total, "dram_gbs": traffic_gbs,
-                          "dram_frac": traffic_gbs / peak if traffic_gbs else None,
-                          "kernel_dram_frac": kernel_dram_frac},
+                "kernel_dram_frac": ({k: (ncu_traffic.get(k, 0.0) / (v * 1e-6) / 1e9 / peak if v > 0 else None)
+                                      for k, v in kern_us.items()} if ncu_traffic else None),
+                "issue_bound_note": "the sweep is bound by fp32 instruction issue, not HBM (DESIGN.md section 5, "
+                                    "profiles/r02_notes_sidecar.md): exact fp32 (max,+) at 30 states alone needs 0.56 ms per 10 M steps",
                 "stage_ms_per_step": {n: float(v / args.steps) for n, v in zip(stage_names, stage_ms)}}
 
     # ---- end to end through the public API, host buffers in and out
@@ -402,6 +490,18 @@ def run_ours(args):
                       "tehmm_decode_host: NumPy uint8 in (pinned), int64 paths out (uint8 states over PCIe, "
                       "widened by %s host threads)" % os.environ["TEHMM_HOST_THREADS"]}
         assert rv[0][1].dtype == np.int64 and rv[0][1].shape[0] == T
+        # where an end-to-end call spends its time: one more pair of calls, traced (a stream synchronisation
+        # per phase, so the phases add up to more than a timed call, whose copies overlap the kernels)
+        os.environ["TEHMM_HOST_TRACE"] = "2"
+        try:
+            br = {}
+            for name, h in (("viterbi", hmm_v), ("map", hmm_m)):
+                h.decode_batch([host_obs])
+                br[name] = {k: float(ctx.lib.tehmm_decode_host_phase_ms(ctx.handle, i))
+                            for i, k in enumerate(("set_batch", "h2d_and_emission", "trellis", "d2h_and_widen"))}
+            e2e["breakdown_ms_traced"] = br
+        finally:
+            del os.environ["TEHMM_HOST_TRACE"]
 
     # ---- seconds per EM iteration (second half of the BASELINE metric)
     em_iter = None
@@ -420,6 +520,15 @@ def run_ours(args):
         barrier()
         em_iter = {"seconds": a.elapsed_time(b_) * 1e-3 / n_em, "obs_per_gpu": T,
                    "what": "emission+forward+backward(xi,posteriors)+histograms+allreduce, device resident"}
+
+    split = None
+    if not args.no_split:
+        split = run_split(world, rank)
+
+    # the sampler ran through the sweep, the end-to-end loop, the EM iterations and the split runs
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "all timed regions of this run (sweep, e2e, em_iter, split)"
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -442,7 +551,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(T, world), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "em_iter": em_iter, "sanity": sanity}
+                "em_iter": em_iter, "split": split, "sanity": sanity}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

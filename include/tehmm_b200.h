@@ -261,6 +261,11 @@ int tehmm_decode_host(tehmm_ctx *ctx, const void *const *h_obs_ptrs, int64_t npt
                       int64_t *h_states, double *h_logprob, double *h_score);
 /* bytes the last tehmm_decode_host moved over PCIe: which = 0 host->device, 1 device->host */
 int64_t tehmm_decode_host_bytes(tehmm_ctx *ctx, int which);
+/* wall-clock milliseconds of the phases of the last tehmm_decode_host call made with the
+ * environment variable TEHMM_HOST_TRACE set ("1": also printed on stderr, "2": recorded only;
+ * tracing adds a stream synchronisation per phase, so it is not for timed runs): which = 0 batch
+ * set-up, 1 host->device copy + emission, 2 trellis, 3 device->host copy + widening; -1 if not traced */
+double tehmm_decode_host_phase_ms(tehmm_ctx *ctx, int which);
 /* device index / model shape of a context */
 int tehmm_ctx_device(tehmm_ctx *ctx);
 int tehmm_model_dims(tehmm_ctx *ctx, int *N, int *K, int *S);

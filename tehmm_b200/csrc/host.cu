@@ -155,6 +155,7 @@ struct HostPipe {
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int64_t redone = 0;                     // calls whose deferred verification failed and ran twice
     int defer_skip = 0, defer_penalty = 0;  // back-off after a refusal
+    double phase_ms[4] = {-1, -1, -1, -1};  // last traced call: set_batch, h2d+emission, trellis, d2h+widen (TEHMM_HOST_TRACE)
 
     ~HostPipe()
     {
@@ -220,22 +221,33 @@ size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // TEHMM_HOST_TRACE=1: wall-clock phases of tehmm_decode_host on stderr (adds a stream sync per phase)
 struct Trace {
-    bool on;
+    bool on, print;
     cudaStream_t st;
     std::chrono::steady_clock::time_point t0;
     std::string line;
-    Trace(cudaStream_t s) : on(getenv("TEHMM_HOST_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+    double *slot;       // HostPipe::phase_ms
+    int n = 0;
+    Trace(cudaStream_t s, double *ph) : on(false), print(false), st(s), t0(std::chrono::steady_clock::now()), slot(ph)
+    {
+        const char *e = getenv("TEHMM_HOST_TRACE");
+        on = e != nullptr && e[0] != '0';
+        print = on && e[0] == '1';            // "1": also a line on stderr; "2": record only
+        if (on) for (int i = 0; i < 4; ++i) slot[i] = -1.0;
+    }
     void mark(const char *name, bool sync)
     {
         if (!on) return;
         if (sync) cudaStreamSynchronize(st);
         const auto t1 = std::chrono::steady_clock::now();
+        const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        if (n < 4) slot[n] = ms;              // a second attempt (failed deferred check) overwrites nothing: n runs on
+        n += 1;
         char buf[64];
-        snprintf(buf, sizeof buf, " %s %.2f", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        snprintf(buf, sizeof buf, " %s %.2f", name, ms);
         line += buf;
         t0 = t1;
     }
-    ~Trace() { if (on) fprintf(stderr, "[tehmm_decode_host ms]%s\n", line.c_str()); }
+    ~Trace() { if (print) fprintf(stderr, "[tehmm_decode_host ms]%s\n", line.c_str()); }
 };
 
 }   // namespace
@@ -274,7 +286,7 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     HCU(cudaSetDevice(device));
     const cudaStream_t st = (cudaStream_t)(uintptr_t)tehmm_ctx_stream(c);
     HostPipe *p = get_pipe(c, device);
-    Trace tr(st);
+    Trace tr(st, p->phase_ms);
     const int64_t total = h_offsets[nseq];
     if (total <= 0) return herr(TEHMM_EINVAL, "empty batch");
     const int LD = tehmm_lattice_stride(c);
@@ -469,6 +481,14 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     if (h_score) memcpy(h_score, pin_lp + nseq, (size_t)nseq * 8);
     p->d2h_bytes = (int64_t)total + nseq * 16;
     return TEHMM_OK;
+}
+
+double tehmm_decode_host_phase_ms(tehmm_ctx *c, int which)
+{
+    std::lock_guard<std::mutex> l(g_mu);
+    auto it = g_pipes.find(c);
+    if (it == g_pipes.end() || which < 0 || which > 3) return -1.0;
+    return it->second->phase_ms[which];
 }
 
 int64_t tehmm_decode_host_bytes(tehmm_ctx *c, int which)
