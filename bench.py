@@ -521,6 +521,30 @@ def run_ours(args):
         em_iter = {"seconds": a.elapsed_time(b_) * 1e-3 / n_em, "obs_per_gpu": T,
                    "what": "emission+forward+backward(xi,posteriors)+histograms+allreduce, device resident"}
 
+    # ---- what speculation costs where filters forget slowly: all-missing stretches of
+    # 2 000 - 20 000 steps under the bench model and under a near-reducible matrix (diagonal 0.9999)
+    if rank == 0 and not args.no_em:
+        hard = {}
+        Th = 2_000_000
+        for name, sticky in (("bench_model_with_gaps", 0.9), ("diag_0.9999_with_gaps", 0.9999)):
+            mh = synth.make_model(N=N_STATES, seed=0, sticky=sticky)
+            oh, _ = synth.sample_obs(mh, Th, seed=1)
+            oh, _ = synth.add_missing_stretches(oh)
+            eng.upload_model(mh["log_start"], mh["log_trans"], mh["table"], 1.0, mh["widths"])
+            eng.upload_batch([oh])
+            keys = ("repair_passes_forward", "repair_passes_backward", "repair_passes_viterbi", "repair_passes_traceback", "fallbacks")
+            for _ in range(2):
+                s0 = {k: ctx.stat(k) for k in keys}
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                eng.viterbi()
+                torch.cuda.synchronize(); t2 = time.perf_counter()
+            hard[name] = dict({k: ctx.stat(k) - v for k, v in s0.items()}, obs=Th, warmup=ctx.stat("warmup"),
+                              fwd_bwd_map_ms=1e3 * (t1 - t0), viterbi_ms=1e3 * (t2 - t1), mix_rho=ctx.stat("mix_rho_ppm") * 1e-6)
+        sanity["slow_mixing"] = hard
+        eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+
     split = None
     if not args.no_split:
         split = run_split(world, rank)

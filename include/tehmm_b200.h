@@ -101,7 +101,10 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
  * xi kernel), "timing" (1 = bracket the first
  * launch of each main kernel with CUDA events on the context's stream), "defer" (see
  * tehmm_ctx_check), "bwd_tmap" (1 = the regular tiles of a single-sequence batch take the
- * tensor-map block kernel in the backward pass; experimental: bit-identical results, not faster).
+ * tensor-map block kernel in the backward pass; experimental: bit-identical results, not faster),
+ * "fallback_after" (ordinary repair passes before the chunks still flagged are resolved exactly by
+ * transfer operators and a float64 chain, csrc/fallback.cu; default 2, -1 = never: the plain loop, one
+ * pass per link of a chain of failed boundaries; stats "fallbacks", "fallback_chunks", "mix_rho_ppm").
  * stats: "launches", "chunks", "fine_chunks", "repaired_chunks_<pass>",
  * "repair_passes_<pass>", "tile_passes", and with "timing" the mean duration in
  * microseconds (over the launches since "timing" was set, at most 32) of "us_emission", "us_forward", "us_backward",

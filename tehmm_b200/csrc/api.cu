@@ -43,6 +43,8 @@ cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const
 cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
 size_t tehmm_xi_tile_scratch_bytes(int sms);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
+cudaError_t tehmm_launch_transfer_ops(cudaStream_t, const TehmmModelDev &, const TehmmChunk *, const int64_t *, int64_t, int, int, const void *, void *, double *, int);
+cudaError_t tehmm_launch_chain(cudaStream_t, const TehmmModelDev &, int, int, int, const int64_t *, const int64_t *, int64_t, const void *, const double *, const void *, void *);
 
 // ---------------------------------------------------------------- errors
 static thread_local std::string g_err;
@@ -96,6 +98,11 @@ struct tehmm_ctx {
     int64_t opt_rescore = 0;          // 1: the Viterbi log-probability is always the float64 re-score of the returned path (default: the fp32 DP's own normaliser sum where the lean kernel runs)
     int64_t opt_bwd_tmap = 0;         // 1: backward pass of the regular tiles by bwd_tile_tmap_kernel (tensor-map blocks) -- correct, not faster (profiles/r01_notes_v4.md)
     int64_t opt_xi_tile = 1;          // expected transition counts by xi_tile_kernel (0: one-chunk-per-warp backward)
+    // ordinary repair passes before the chunks still flagged are resolved exactly by transfer operators
+    // (fallback.cu; -1 = never: the plain loop, one pass per link of a chain of bad chunks)
+    int64_t opt_fallback_after = 2;
+    int64_t stat_fallbacks = 0, stat_fallback_chunks = 0, stat_noise_accepted = 0;
+    double mix_rho = 0.0;             // modulus of the second eigenvalue of the transition matrix (set_model)
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
     int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
@@ -217,6 +224,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "defer")) c->opt_defer = v;
     else if (!strcmp(name, "bwd_tmap")) c->opt_bwd_tmap = v;
     else if (!strcmp(name, "rescore")) c->opt_rescore = v;
+    else if (!strcmp(name, "fallback_after")) c->opt_fallback_after = v;
     else return fail(TEHMM_EINVAL, "unknown option %s", name);
     return TEHMM_OK;
 }
@@ -240,6 +248,10 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "fine_chunks")) return c->has_batch ? c->bf.nchunks : 0;
     if (!strcmp(name, "tile_passes")) return c->stat_tile_passes;
     if (!strcmp(name, "umma_passes")) return c->stat_umma_passes;
+    if (!strcmp(name, "fallbacks")) return c->stat_fallbacks;
+    if (!strcmp(name, "fallback_chunks")) return c->stat_fallback_chunks;
+    if (!strcmp(name, "noise_accepted")) return c->stat_noise_accepted;
+    if (!strcmp(name, "mix_rho_ppm")) return (int64_t)(c->mix_rho * 1e6);
     for (int i = 0; i < TEHMM_NTIMED; ++i)
         if (!strcmp(name, tk_names[i])) {
             // average over the launches recorded since "timing" was set (at most the last TEHMM_TRING)
@@ -578,6 +590,37 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
             cutt[(size_t)i * NP + j] = okt ? log_trans[(size_t)i * N + j] : NEG;
         }
     }
+    {   // How fast the chain forgets with NO help from the data (all-missing stretches): rho = |lambda_2(A)|,
+        // estimated as ||B^256||_F^(1/256), B = A - 1 pi^T (pi = stationary distribution by power iteration).
+        // Rounding noise of a filter is amplified by 1 / (1 - rho); see tolerance_after_fallback.
+        std::vector<double> A((size_t)N * N), pi(N, 1.0 / N), tmp(N), B((size_t)N * N), B2((size_t)N * N);
+        for (int i = 0; i < N; ++i) {
+            double rs = 0.0;
+            for (int j = 0; j < N; ++j) { A[(size_t)i * N + j] = lint[(size_t)i * NP + j]; rs += A[(size_t)i * N + j]; }
+            for (int j = 0; j < N; ++j) A[(size_t)i * N + j] = rs > 0.0 ? A[(size_t)i * N + j] / rs : (i == j ? 1.0 : 0.0);
+        }
+        for (int it = 0; it < 2000; ++it) {
+            double sum = 0.0;
+            for (int j = 0; j < N; ++j) { double a = 0.0; for (int i = 0; i < N; ++i) a += pi[i] * A[(size_t)i * N + j]; tmp[j] = a; sum += a; }
+            for (int j = 0; j < N; ++j) pi[j] = sum > 0.0 ? tmp[j] / sum : 1.0 / N;
+        }
+        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) B[(size_t)i * N + j] = A[(size_t)i * N + j] - pi[j];
+        double lognorm = 0.0;                 // log ||B^(2^k)||_F accumulated with renormalisation
+        for (int sq = 0; sq < 8; ++sq) {
+            double f = 0.0;
+            for (double v : B) f += v * v;
+            f = sqrt(f);
+            if (!(f > 0.0)) { lognorm = -INFINITY; break; }
+            for (double &v : B) v /= f;
+            lognorm = 2.0 * (lognorm + log(f));
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) { double a = 0.0; for (int k = 0; k < N; ++k) a += B[(size_t)i * N + k] * B[(size_t)k * N + j]; B2[(size_t)i * N + j] = a; }
+            B.swap(B2);
+        }
+        if (lognorm > -INFINITY) { double f = 0.0; for (double v : B) f += v * v; lognorm += f > 0.0 ? 0.5 * log(f) : -INFINITY; }
+        double rho = lognorm > -INFINITY ? exp(lognorm / 256.0) : 0.0;
+        c->mix_rho = std::min(1.0, std::max(0.0, rho));
+    }
     CU(cudaStreamSynchronize(c->stream));
     if (total > c->model_blob_bytes) {
         if (c->model_blob) { cudaFree(c->model_blob); c->model_blob = nullptr; c->model_blob_bytes = 0; }
@@ -891,11 +934,182 @@ static double tolerance(int prec, bool log_space)
 static void adapt_warmup(tehmm_ctx *c, int first_pass_bad, int64_t nchunks)
 {
     if (c->opt_warmup > 0) return;
-    if ((int64_t)first_pass_bad * 50 > nchunks && c->b.warmup < 4096) {
+    // (capped: beyond a few hundred steps a longer warm-up costs more than resolving the flagged chunks
+    //  exactly, resolve_flagged below)
+    if ((int64_t)first_pass_bad * 50 > nchunks && c->b.warmup < 256) {
         c->b.warmup *= 2;
         c->bf.warmup = c->b.warmup;
     }
 }
+
+// ---------------------------------------------------------------- exact resolution of flagged chunks
+// (fallback.cu)  The chunks flagged in `bad` get the boundary vector the serial recursion would hand
+// them: transfer operators of the flagged chunks on the device, the chain over each run of flagged
+// chunks on the host in float64, the vectors written into start_vec.  The caller re-runs the flagged
+// chunks (mode 1).  kind 0 forward / 1 backward (linear space, lat = blin), 2 Viterbi (log space,
+// lat = elog).  Blocks the stream; this is the slow path.
+static int resolve_flagged(tehmm_ctx *c, cudaStream_t st, const TehmmBatchDev &PB, int prec, int kind,
+                           const void *lat, void *sv, const void *ev, int *bad, int64_t reach)
+{
+    // A chunk that is NOT flagged agrees with what its neighbour handed it -- which proves it right only
+    // if everything further up the recursion is right.  Downstream of a flagged chunk the standing chunks
+    // are usually consistent with the WRONG vector (inside an uninformative stretch they all converged to
+    // the same stable guess), so the chain also runs through `reach` chunks beyond every flagged one and
+    // those are re-run as well; the verification after the re-run flags the next chunk if the truth has
+    // not met the guess yet, and the caller comes back with four times the reach.
+    const int N = c->m.N, NP = c->m.NP;
+    const int dir = kind == 1 ? -1 : +1;
+    const size_t ts = prec == TEHMM_F32 ? 4 : 8;
+    const int64_t nch = PB.nchunks;
+    std::vector<int> hb(nch);
+    std::vector<TehmmChunk> hch(nch);
+    CU(cudaMemcpyAsync(hb.data(), bad, sizeof(int) * (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hch.data(), PB.chunks, sizeof(TehmmChunk) * (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<char> want(nch, 0);
+    int64_t nflag = 0;
+    for (int64_t i = 0; i < nch; ++i) {
+        if (!hb[i]) continue;
+        nflag += 1;
+        want[i] = 1;
+        int64_t j = i;
+        for (int64_t g = 1; g <= reach; ++g) {
+            if (dir > 0 ? hch[j].t1 >= hch[j].s1 : hch[j].t0 <= hch[j].s0) break;    // end of the sequence
+            j += dir;
+            want[j] = 1;
+        }
+    }
+    if (nflag == 0) return TEHMM_OK;
+    // chain order, run after run (a run = consecutive wanted chunks of one sequence; its first chunk is
+    // flagged, so it has a neighbour on the side the recursion comes from)
+    std::vector<int64_t> list, run_off;
+    for (int64_t q = 0; q < nch; ++q) {
+        const int64_t i = dir > 0 ? q : nch - 1 - q;
+        if (!want[i]) continue;
+        const int64_t p = i - dir;
+        const bool linked = p >= 0 && p < nch && want[p] && hch[p].seq == hch[i].seq;
+        if (!linked) run_off.push_back((int64_t)list.size());
+        list.push_back(i);
+        hb[i] = 1;
+    }
+    const int64_t B = (int64_t)list.size(), nruns = (int64_t)run_off.size();
+    run_off.push_back(B);
+    DevBuf d_list, d_run, d_end, d_scale;
+    CU(d_list.alloc((size_t)B * 8)); CU(d_run.alloc((size_t)(nruns + 1) * 8));
+    CU(d_end.alloc((size_t)B * N * NP * ts)); CU(d_scale.alloc((size_t)B * N * 8));
+    CU(cudaMemcpyAsync(d_list.p, list.data(), (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_run.p, run_off.data(), (size_t)(nruns + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(bad, hb.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice, st));
+    CU(tehmm_launch_transfer_ops(st, c->m, PB.chunks, d_list.as<int64_t>(), B, prec, kind, lat, d_end.p, d_scale.as<double>(), c->sms));
+    CU(tehmm_launch_chain(st, c->m, prec, kind, dir, d_list.as<int64_t>(), d_run.as<int64_t>(), nruns, d_end.p, d_scale.as<double>(), ev, sv));
+    c->launches += 2;
+    CU(cudaStreamSynchronize(st));     // the temporaries go out of scope
+    c->stat_fallbacks += 1;
+    c->stat_fallback_chunks += B;
+    return TEHMM_OK;
+}
+
+// The same for the traceback: a flagged chunk assumed the wrong end state.  Its walk is a MAP from end
+// state to the state it implies for the left neighbour; N walks per chunk (the ordinary kernel on a list
+// of virtual chunks, forced end = each state), the maps composed right to left on the host.  Unlike the
+// vector recursions the standing chunks to the LEFT of a flagged one are usually wrong too, consistently
+// (inside an uninformative stretch every walk stays in the state it entered with), so the maps are also
+// computed for `reach` chunks to the left of every flagged chunk and the chain runs on for as long as it
+// contradicts what those chunks assumed; `reach` grows fourfold per round.  Integer work: the result is
+// exactly the serial traceback's.
+static int resolve_flagged_tb(tehmm_ctx *c, cudaStream_t st, const TehmmBatchDev &TBP, int prec,
+                              const void *d_lattice, uint8_t *states, uint8_t *spec_end, const uint8_t *pred,
+                              uint8_t *forced, int *bad, int tb_grid, int64_t reach)
+{
+    const int N = c->m.N;
+    const int64_t nch = TBP.nchunks;
+    std::vector<int> hb(nch);
+    std::vector<TehmmChunk> hch(nch);
+    std::vector<uint8_t> hpred(nch), hspec(nch), hforced(nch);
+    CU(cudaMemcpyAsync(hb.data(), bad, sizeof(int) * (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hch.data(), TBP.chunks, sizeof(TehmmChunk) * (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hpred.data(), pred, (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hspec.data(), spec_end, (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hforced.data(), forced, (size_t)nch, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // chunks whose maps are needed: the flagged ones and up to `reach` chunks to the left of each, inside
+    // the same sequence (a chunk without a left neighbour ends the chain: nobody consumes its pred)
+    std::vector<char> want(nch, 0);
+    int64_t nflag = 0;
+    for (int64_t i = nch - 1; i >= 0; --i) {
+        if (!hb[i]) continue;
+        nflag += 1;
+        want[i] = 1;
+        for (int64_t g = 1, j = i; g <= reach && hch[j].t0 > hch[j].s0; ++g) { j -= 1; want[j] = 1; }
+    }
+    if (nflag == 0) return TEHMM_OK;
+    std::vector<int64_t> list;                     // ascending
+    std::vector<int64_t> slot(nch, -1);
+    for (int64_t i = 0; i < nch; ++i) if (want[i]) { slot[i] = (int64_t)list.size(); list.push_back(i); }
+    const int64_t B = (int64_t)list.size(), nv = B * N;
+    std::vector<TehmmChunk> v((size_t)nv);
+    std::vector<uint8_t> vf((size_t)nv);
+    std::vector<int> vb((size_t)nv, 1);
+    for (int64_t k = 0; k < B; ++k)
+        for (int i = 0; i < N; ++i) { v[(size_t)(k * N + i)] = hch[list[k]]; vf[(size_t)(k * N + i)] = (uint8_t)i; }
+    DevBuf d_v, d_vf, d_vb, d_vs, d_vp;
+    CU(d_v.alloc(v.size() * sizeof(TehmmChunk))); CU(d_vf.alloc((size_t)nv)); CU(d_vb.alloc((size_t)nv * 4));
+    CU(d_vs.alloc((size_t)nv)); CU(d_vp.alloc((size_t)nv));
+    CU(cudaMemcpyAsync(d_v.p, v.data(), v.size() * sizeof(TehmmChunk), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_vf.p, vf.data(), (size_t)nv, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_vb.p, vb.data(), (size_t)nv * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(d_vp.p, 0, (size_t)nv, st));
+    TehmmBatchDev VB = TBP;
+    VB.nchunks = nv;
+    VB.chunks = d_v.as<TehmmChunk>();
+    const int vgrid = (int)std::max<int64_t>(1, std::min<int64_t>((nv + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA, (int64_t)tb_grid));
+    // (the walks scribble over these chunks' rows of `states`; every chunk whose map was computed is re-run below)
+    CU(tehmm_launch_traceback(st, c->m, VB, prec, d_lattice, nullptr, states, nullptr, d_vs.as<uint8_t>(), d_vp.as<uint8_t>(),
+                              d_vf.as<uint8_t>(), d_vb.as<int>(), 1, vgrid));
+    c->launches += 1;
+    std::vector<uint8_t> vp((size_t)nv);
+    CU(cudaMemcpyAsync(vp.data(), d_vp.p, (size_t)nv, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // right to left: `have` = the chain holds the true state at t0 - 1 of chunk i + 1 in `cur`
+    bool have = false;
+    int cur = 0;
+    for (int64_t i = nch - 1; i >= 0; --i) {
+        if (!want[i]) { have = false; continue; }
+        const bool seq_end = hch[i].t1 == hch[i].s1;
+        int end;
+        if (seq_end) { have = false; end = (int)hspec[i]; }                   // exact by construction (never flagged)
+        else if (have) end = cur;
+        else end = hb[i] ? (int)hpred[i + 1] : (int)hspec[i];                  // the right neighbour stands
+        // every chunk whose rows were scribbled over is re-run from the end state the chain gives it
+        // (the one it had, where the chain agrees with it)
+        hb[i] = 1;
+        hforced[i] = hspec[i] = (uint8_t)end;
+        cur = end < N ? (int)vp[(size_t)(slot[i] * N + end)] : 0;
+        have = true;
+    }
+    CU(cudaMemcpyAsync(forced, hforced.data(), (size_t)nch, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(spec_end, hspec.data(), (size_t)nch, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(bad, hb.data(), sizeof(int) * (size_t)nch, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    c->stat_fallbacks += 1;
+    c->stat_fallback_chunks += B;
+    return TEHMM_OK;
+}
+
+// Tolerance of the verifications that follow an exact resolution.  The chained vector and the vector the
+// re-run neighbour ends on are two roundings of the same quantity, and a filter's rounding noise (eps per
+// step: 2^-21 for the 3 x TF32 products, 2^-52 in float64) is amplified by 1 / (1 - rho) where the data
+// do not help (rho = |lambda_2| of the transition matrix): what is left after a resolution is compared
+// against that floor, not against the band a speculated boundary has to meet.
+static double tolerance_after_fallback(const tehmm_ctx *c, int prec, bool log_space)
+{
+    const double base = 100.0 * tolerance(prec, log_space);
+    if (log_space) return base;
+    const double eps = prec == TEHMM_F32 ? 4.8e-7 : 2.3e-16;
+    const double floor_ = 8.0 * eps / std::max(1e-9, 1.0 - c->mix_rho);
+    return std::min(0.1, std::max(base, floor_));
+}
+#define TEHMM_MAX_FALLBACK_ROUNDS 10    // reach 8 * 4^round chunks: far beyond any partition; then the plain loop
 
 // The tensor-core tile kernels (tile.cu) take the fp32, N <= 32, no
 // segment-ratio case; everything else runs one chunk per warp.
@@ -936,8 +1150,9 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     CU(launch(0));
     tk_end(c, TK_FORWARD);
     c->launches += 1;
-    const double tol = tolerance(prec, false);
+    double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
+    int fb_rounds = 0;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, +1, 1, bad, nbad, lkap));
         c->launches += 1;
@@ -951,6 +1166,12 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
         if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "forward repair did not converge (%d chunks left)", nb);
+        if (c->opt_fallback_after >= 0 && pass >= c->opt_fallback_after && d_ratios == nullptr && fb_rounds < TEHMM_MAX_FALLBACK_ROUNDS) {
+            // slow mixing: resolve the flagged chunks exactly (transfer operators + chain) instead of one link per pass
+            if (resolve_flagged(c, st, PB, prec, 0, d_blin, sv, ev, bad, (int64_t)8 << (2 * fb_rounds))) return TEHMM_ECUDA;
+            tol = tolerance_after_fallback(c, prec, false);
+            fb_rounds += 1;
+        }
         c->stat_repair_fwd += 1; c->stat_bad_fwd += nb;
         CU(launch(1));
         c->launches += 1;
@@ -994,8 +1215,9 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
     CU(launch(0));
     tk_end(c, TK_BACKWARD);
     c->launches += 1;
-    const double tol = tolerance(prec, false);
+    double tol = tolerance(prec, false);
     const int64_t max_pass = c->opt_max_repair > 0 ? c->opt_max_repair : PB.nchunks + 1;
+    int fb_rounds = 0;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, -1, 1, bad, nbad, nullptr));
         c->launches += 1;
@@ -1004,6 +1226,11 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
         if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "backward repair did not converge (%d chunks left)", nb);
+        if (c->opt_fallback_after >= 0 && pass >= c->opt_fallback_after && d_ratios == nullptr && fb_rounds < TEHMM_MAX_FALLBACK_ROUNDS) {
+            if (resolve_flagged(c, st, PB, prec, 1, d_blin, sv, ev, bad, (int64_t)8 << (2 * fb_rounds))) return TEHMM_ECUDA;
+            tol = tolerance_after_fallback(c, prec, false);
+            fb_rounds += 1;
+        }
         c->stat_repair_bwd += 1; c->stat_bad_bwd += nb;
         CU(launch(1));
         c->launches += 1;
@@ -1063,7 +1290,8 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 0, grid, d_rowmax, dsp));
     tk_end(c, TK_VITERBI_DP);
     c->launches += 1;
-    const double tol = tolerance(prec, true);
+    double tol = tolerance(prec, true);
+    int fb_rounds = 0;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_verify(st, c->b, prec, c->m.NP, sv, ev, tol, +1, 0, bad, nbad, nullptr));
         c->launches += 1;
@@ -1072,6 +1300,11 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "viterbi repair did not converge (%d chunks left)", nb);
+        if (c->opt_fallback_after >= 0 && pass >= c->opt_fallback_after && d_ratios_dp == nullptr && fb_rounds < TEHMM_MAX_FALLBACK_ROUNDS) {
+            if (resolve_flagged(c, st, PB, prec, 2, d_elog, sv, ev, bad, (int64_t)8 << (2 * fb_rounds))) return TEHMM_ECUDA;
+            tol = tolerance_after_fallback(c, prec, true);
+            fb_rounds += 1;
+        }
         c->stat_repair_vit += 1; c->stat_bad_vit += nb;
         CU(tehmm_launch_viterbi(st, c->m, c->b, prec, d_elog, d_ratios_dp, d_lattice, sv, ev, bad, 1, grid, d_rowmax, dsp));
         c->launches += 1;
@@ -1082,6 +1315,7 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
     CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 0, tb_grid));
     tk_end(c, TK_TRACEBACK);
     c->launches += 1;
+    int64_t tb_reach = 8;
     for (int64_t pass = 0;; ++pass) {
         CU(tehmm_launch_tb_verify(st, TBP, spec_end, pred, forced, bad, nbad));
         c->launches += 1;
@@ -1090,6 +1324,10 @@ int tehmm_run_viterbi(tehmm_ctx *c, int prec, const void *d_elog, const double *
         if (pass == 0) adapt_warmup(c, nb, TBP.nchunks);
         if (nb == 0) break;
         if (pass >= TBP.nchunks + 1 && pass >= max_pass) return fail(TEHMM_ESTATE, "traceback repair did not converge (%d chunks left)", nb);
+        if (c->opt_fallback_after >= 0 && pass >= c->opt_fallback_after && d_ratios_dp == nullptr && tb_reach < ((int64_t)1 << 40)) {
+            if (resolve_flagged_tb(c, st, TBP, prec, d_lattice, d_states, spec_end, pred, forced, bad, tb_grid, tb_reach)) return TEHMM_ECUDA;
+            tb_reach *= 4;
+        }
         c->stat_repair_tb += 1; c->stat_bad_tb += nb;
         CU(tehmm_launch_traceback(st, c->m, TBP, prec, d_lattice, d_ratios_dp, d_states, d_states64, spec_end, pred, forced, bad, 1, tb_grid));
         c->launches += 1;

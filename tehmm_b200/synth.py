@@ -95,3 +95,20 @@ def bench_lengths(config, rng=None):
                 155270560, 59373566]
         return [-(-x // 250) for x in hg19]
     raise ValueError(config)
+
+
+def add_missing_stretches(obs, n_stretches=8, lo=2_000, hi=20_000, seed=5):
+    """Overwrite `n_stretches` runs of lo..hi consecutive rows with the missing symbol in EVERY track
+    (assembly gaps, unmappable repeats): there the emission is uniform and a filter forgets its start
+    only as fast as the transition matrix mixes.  Returns (obs copy, [(start, end)])."""
+    rng = np.random.RandomState(seed)
+    out = obs.copy()
+    T = obs.shape[0]
+    spans = []
+    for _ in range(n_stretches):
+        n = int(rng.randint(lo, hi + 1))
+        n = min(n, max(1, T // (2 * n_stretches)))
+        a = int(rng.randint(0, max(1, T - n)))
+        out[a:a + n] = 0
+        spans.append((a, a + n))
+    return out, spans
