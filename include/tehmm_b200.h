@@ -282,6 +282,61 @@ int tehmm_path_score(tehmm_ctx *ctx, const uint8_t *d_states, const double *d_ra
                      const double *d_ratios_dp, int64_t lo, int64_t hi, double *d_logprob,
                      void *d_scratch);
 
+/* ------------------------------------------------- data formats either side of the trellis
+ * (csrc/tracks.cu).  The (T, K) symbol table the HMM reads is
+ * built in HBM: d_table is a DEVICE pointer to a row-major (T, K) matrix of elem_bytes-wide
+ * integers (1 = uint8, the reference's INTEGER_ARRAY_TYPE; 2, 4), exactly the layout of
+ * IntegerTrackTable.data (/root/reference/track.py:552-558) and of tehmm_set_batch's d_obs.
+ *
+ * tehmm_track_fill: column k := value (IntegerTrackTable.initRow, track.py:590-591).
+ * tehmm_rasterize_intervals: the per-base fill of readBedData (/root/reference/trackIO.py:175-203)
+ *   for n HOST intervals [h_start, h_end) in genome coordinates, in file order -- where intervals
+ *   overlap the later one wins, as in the reference's loop; the first base of an interval (after
+ *   clipping to [region_start, region_end)) gets h_val0 (the useDelta value), the others h_val.
+ *   Values are already mapped through the track's value map (strings -> categories: host work).
+ * tehmm_segment_table: bin/segmentTracks.py:200-277 (segmentTracks / isNewSegment) over nregions
+ *   regions (h_region_off: nregions + 1 row offsets into the table, one region per TrackTable):
+ *   d_cut[T] := 1 where a segment starts, d_seg_off (capacity T) := those rows, *h_nseg their
+ *   number.  h_ignore / h_cut: K flags (args.ignoreList / args.cutList), thresh, maxLen, fixLen as
+ *   the script's options, prev_mode = (--comp prev).  *h_passes (optional): scan passes used.
+ * tehmm_compress_segments: TrackTable.segment with interpolate (track.py:476-481,515-533,603-620)
+ *   followed by compressSegments (track.py:594-601): row s of d_out (nseg x K) := per-track mode of
+ *   rows [d_seg_off[s], d_seg_off[s+1]) (last segment: to T) for the tracks flagged in h_use_mode
+ *   (smallest among the most frequent values, as scipy.stats.mode), the segment's first row for
+ *   the others.  Gaussian tracks (mean of mapped-back values, re-mapped) are host work and not
+ *   covered.  uint8 tables.
+ * tehmm_run_sum: _track.runSum (/root/reference/_track.pyx:13-25): d_out[i] = number of zeros
+ *   in d_mask[0 .. i).                                                                          */
+int tehmm_track_fill(tehmm_ctx *ctx, void *d_table, int64_t T, int K, int elem_bytes, int k, int32_t value);
+int tehmm_rasterize_intervals(tehmm_ctx *ctx, const int64_t *h_start, const int64_t *h_end,
+                              const int32_t *h_val, const int32_t *h_val0, int64_t n,
+                              int64_t region_start, int64_t region_end, void *d_table, int K,
+                              int elem_bytes, int k);
+int tehmm_segment_table(tehmm_ctx *ctx, const void *d_table, int64_t T, int K, int elem_bytes,
+                        int64_t nregions, const int64_t *h_region_off, const uint8_t *h_ignore,
+                        const uint8_t *h_cut, int thresh, int64_t maxLen, int64_t fixLen, int prev_mode,
+                        uint8_t *d_cut, int64_t *d_seg_off, int64_t *h_nseg, int *h_passes);
+int tehmm_compress_segments(tehmm_ctx *ctx, const void *d_table, int64_t T, int K, int elem_bytes,
+                            const int64_t *d_seg_off, int64_t nseg, const uint8_t *h_use_mode,
+                            void *d_out);
+int tehmm_run_sum(tehmm_ctx *ctx, const uint8_t *d_mask, int32_t *d_out, int64_t n);
+/* BED reading on the host, natively: bedRead (/root/reference/trackIO.py:389-404) and, with
+ * need_intersect, what `intersectBed -a file -b interval | sortBed` leaves of it
+ * (trackIO.py:138-143: the parts of chrom's intervals inside [start, end), by start; stable).
+ * sort (without need_intersect): by (chrom, start) like sortBed (trackIO.py:147-151).
+ * valcol: 3 or 4 = the column whose string is the interval's value, 0 = none.  Values come back
+ * as indices into the distinct value strings IN ORDER OF FIRST APPEARANCE, the order in which
+ * the reference's loop shows them to the track's value map (which numbers categories in that
+ * order when it is allowed to grow).                                                          */
+typedef struct tehmm_bed tehmm_bed;
+int tehmm_bed_open(const char *path, const char *chrom, int64_t start, int64_t end, int need_intersect,
+                   int sort, int valcol, tehmm_bed **out);
+int64_t tehmm_bed_count(tehmm_bed *bed);
+int64_t tehmm_bed_nunique(tehmm_bed *bed);
+const char *tehmm_bed_unique(tehmm_bed *bed, int64_t i);
+int tehmm_bed_fetch(tehmm_bed *bed, int64_t *starts, int64_t *ends, int32_t *value_index);
+void tehmm_bed_close(tehmm_bed *bed);
+
 /* Decode output path: the per-observation BED writer of teHmmEval.py:238-262
  * (statesToBed, bedFile part): for observation i one line
  *   chrom \t curStart \t curStart + len_i \t name(states[i]) \n

@@ -61,6 +61,17 @@ SIGNATURES = {
     "tehmm_run_emission_stats": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_int, _c_void]),
     "tehmm_viterbi_workspace_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_track_fill": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_int, _c_int, ctypes.c_int32]),
+    "tehmm_rasterize_intervals": (_c_int, [_c_void, _c_void, _c_void, _c_void, _c_void, _c_i64, _c_i64, _c_i64, _c_void, _c_int, _c_int, _c_int]),
+    "tehmm_segment_table": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_int, _c_i64, _c_void, _c_void, _c_void, _c_int, _c_i64, _c_i64, _c_int, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_compress_segments": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_int, _c_void, _c_i64, _c_void, _c_void]),
+    "tehmm_run_sum": (_c_int, [_c_void, _c_void, _c_void, _c_i64]),
+    "tehmm_bed_open": (_c_int, [ctypes.c_char_p, ctypes.c_char_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, ctypes.POINTER(_c_void)]),
+    "tehmm_bed_count": (_c_i64, [_c_void]),
+    "tehmm_bed_nunique": (_c_i64, [_c_void]),
+    "tehmm_bed_unique": (ctypes.c_char_p, [_c_void, _c_i64]),
+    "tehmm_bed_fetch": (_c_int, [_c_void, _c_void, _c_void, _c_void]),
+    "tehmm_bed_close": (None, [_c_void]),
     "tehmm_decode_host": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_i64, _c_void, _c_int, _c_int, _c_void, _c_void, _c_void]),
     "tehmm_decode_host_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_decode_host_phase_ms": (ctypes.c_double, [_c_void, _c_int]),

@@ -1,8 +1,8 @@
 """Minimal host-side track containers for the hot path.
 
-The reference's data model (track.py) is out of scope;
-the hot path only needs the observation matrix and, for segmented tables, the
-per-observation segment lengths.  Anything that quacks like the reference's
+The hot path needs the observation matrix and, for segmented tables, the
+per-observation segment lengths; IntegerTrackTable.segment
+compresses a table to one row per segment on the GPU.  Anything that quacks like the reference's
 TrackTable (getNumPyArray / getSegmentOffsets / getSegmentLengthsAsRatio) is
 accepted, so the reference's own TrackData objects work unchanged.
 """
@@ -109,6 +109,40 @@ class IntegerTrackTable(TrackTable):
 
     def getNumPyArray(self):
         return self.data
+
+    def segment(self, segIntervals, trackList, interpolate=True):
+        """Transform the table to one row per segment interval (track.py:449-495): the offsets of the
+        segment intervals that fall into this table, the per-track mode of every segment written to
+        its first row (interpolateSegments / setAverages, track.py:515-533,603-620), then
+        compressSegments -- the last two on the GPU (tehmm_compress_segments).  segIntervals: sorted
+        (chrom, start, end, ...) tuples covering the table; trackList: iterable of tracks with
+        getNumber() / getDist(), or None (every track takes the mode).  Masked tables and gaussian
+        tracks (mean of mapped-back values) are not covered."""
+        import torch
+        from . import tracks_device
+        assert self.maskArray is None, "segment() on a masked table is not implemented"
+        offs = [int(iv[1]) - self.start for iv in segIntervals
+                if iv[0] == self.chrom and int(iv[1]) >= self.start and int(iv[1]) < self.origEnd]
+        assert len(offs) > 0 and offs[0] == 0, "segment intervals must start where the table starts"
+        self.segOffsets = np.asarray(offs, dtype=np.int64)
+        K = self.numTracks
+        use_mode = np.zeros(K, dtype=np.uint8)
+        if interpolate:
+            use_mode[:] = 1
+            if trackList is not None:
+                for track in trackList:
+                    if track.getDist() == "gaussian":
+                        raise NotImplementedError("gaussian tracks are averaged on the host in the reference (track.py:607-617)")
+        dev = torch.device("cuda", tracks_device._ctx().device)
+        d = torch.from_numpy(np.ascontiguousarray(self.data)).to(dev)
+        d_off = torch.from_numpy(self.segOffsets).to(dev)
+        self.data = tracks_device.compress(d, d_off, use_mode).cpu().numpy()
+        self.shape = (len(self), self.numTracks)
+
+    def compressSegments(self):
+        """one row per segment offset (track.py:594-601)"""
+        assert self.segOffsets is not None and len(self.segOffsets) > 0
+        self.data = self.data[self.segOffsets]
 
     def setSegments(self, segOffsets):
         """Keep one observation per segment (track.py:594-601 compressSegments)."""
