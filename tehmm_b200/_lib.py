@@ -206,9 +206,16 @@ class Context(object):
 _ctx_local = threading.local()
 
 
+def set_thread_device(device):
+    """the device the calling thread's contexts default to (None: back to TEHMM_B200_DEVICE / LOCAL_RANK)"""
+    _ctx_local.device = None if device is None else int(device)
+
+
 def get_context(device=None):
     """Process-global, per-thread, per-device context cache.  Never stored on model
     objects: they are pickled / deep-copied (modelIO.py:26-32, hmm.py:694)."""
+    if device is None:
+        device = getattr(_ctx_local, "device", None)          # set_thread_device: replicate training
     if device is None:
         device = int(os.environ.get("TEHMM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         n = load().tehmm_device_count()
