@@ -255,8 +255,8 @@ def run_split(world, rank):
         if world > 1:
             dist.barrier()
 
-    def make_hmm(m, **kw):
-        em = IndependentMultinomialEmissionModel(m["N"], list(m["syms"]), zeroAsMissingData=True)
+    def make_hmm(m, seg_len=None, **kw):
+        em = IndependentMultinomialEmissionModel(m["N"], list(m["syms"]), zeroAsMissingData=True, effectiveSegmentLength=seg_len)
         em.logProbs = m["table"].copy()
         return MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy(), **kw), em
 
@@ -308,6 +308,28 @@ def run_split(world, rank):
     out["c3_em"] = {"what": "Baum-Welch on 350 sequences (%d steps) through MultitrackHmm.fit, %d iterations, sequences "
                             "dealt to %d rank(s), one all-reduce + host M-step per iteration" % (sum(lens), n_iter, world),
                     "seconds_per_em_iteration": dt / n_iter, "cells_per_s_per_iteration": sum(lens) * N_STATES / (dt / n_iter)}
+    # the same with SEGMENT RATIOS (segmentTracks-style tables: one observation per variable-length segment,
+    # ratio = length / 100; _hmm.pyx:140-149,187-188): the ratios are folded into the emission lattice once
+    # (tehmm_fold_ratios) and the passes run on the tile kernels
+    from tehmm_b200.track import IntegerTrackTable
+    rng = np.random.RandomState(3)
+    tables = []
+    for o in seqs:
+        seg = np.minimum(rng.geometric(1.0 / 60.0, size=o.shape[0]), 100).astype(np.int64)
+        t = IntegerTrackTable(o.shape[1], "chrG", 0, int(seg.sum()))
+        t.segOffsets = np.concatenate([[0], np.cumsum(seg)[:-1]]).astype(np.int64)
+        t.data = o
+        t.shape = (len(t), o.shape[1])
+        tables.append(t)
+    hmm, _ = make_hmm(m0, seg_len=100, n_iter=2, thresh=0.0)
+    hmm.fit(tables)
+    hmm, _ = make_hmm(m0, seg_len=100, n_iter=n_iter, thresh=0.0)
+    barrier(); t0 = time.perf_counter()
+    hmm.fit(tables)
+    torch.cuda.synchronize()
+    dt_r = reduce(time.perf_counter() - t0, MAX)
+    out["c3_em_with_segment_ratios"] = {"seconds_per_em_iteration": dt_r / n_iter,
+                                        "relative_to_without_ratios": dt_r / dt}
     return out
 
 

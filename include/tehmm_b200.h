@@ -282,6 +282,19 @@ int tehmm_path_score(tehmm_ctx *ctx, const uint8_t *d_states, const double *d_ra
                      const double *d_ratios_dp, int64_t lo, int64_t hi, double *d_logprob,
                      void *d_scratch);
 
+/* Segment ratios on the fast path (csrc/ratios.cu).  In the forward / backward recursions a
+ * segment ratio r_t > 1 is a per-row diagonal factor A_jj^(r_t - 1) on the emission
+ * (/root/reference/_hmm.pyx:140-149,187-188), so tehmm_fold_ratios rewrites the linear emission
+ * lattice ONCE (d_blin and d_rowmax of tehmm_run_emission, in place) and tehmm_run_forward /
+ * tehmm_run_backward are then called WITHOUT ratios -- on the tensor-core tile kernels where those
+ * apply.  Do not hand the folded lattice to a pass that is also given the ratios.  What the
+ * E-step still owes the ratios is the diagonal term of _log_sum_lneta (_hmm.pyx:91-96,107-110):
+ * tehmm_ratio_diag_counts adds (1/N) sum_{t > s0, r_t > 1} (r_t - 1) gamma_t[j] to trans[j][j] of
+ * d_start_trans (layout of tehmm_run_backward's TRANS output), from the posterior lattice.      */
+int tehmm_fold_ratios(tehmm_ctx *ctx, int prec, const double *d_ratios, void *d_blin, double *d_rowmax);
+int tehmm_ratio_diag_counts(tehmm_ctx *ctx, int prec, const void *d_post, const double *d_ratios,
+                            double *d_start_trans, void *d_scratch);
+
 /* ------------------------------------------------- data formats either side of the trellis
  * (csrc/tracks.cu).  The (T, K) symbol table the HMM reads is
  * built in HBM: d_table is a DEVICE pointer to a row-major (T, K) matrix of elem_bytes-wide

@@ -61,6 +61,8 @@ SIGNATURES = {
     "tehmm_run_emission_stats": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_int, _c_void]),
     "tehmm_viterbi_workspace_bytes": (_c_i64, [_c_void, _c_int]),
     "tehmm_run_viterbi": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void, _c_void]),
+    "tehmm_fold_ratios": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void]),
+    "tehmm_ratio_diag_counts": (_c_int, [_c_void, _c_int, _c_void, _c_void, _c_void, _c_void]),
     "tehmm_track_fill": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_int, _c_int, ctypes.c_int32]),
     "tehmm_rasterize_intervals": (_c_int, [_c_void, _c_void, _c_void, _c_void, _c_void, _c_i64, _c_i64, _c_i64, _c_void, _c_int, _c_int, _c_int]),
     "tehmm_segment_table": (_c_int, [_c_void, _c_void, _c_i64, _c_int, _c_int, _c_i64, _c_void, _c_void, _c_void, _c_int, _c_i64, _c_i64, _c_int, _c_void, _c_void, _c_void, _c_void]),

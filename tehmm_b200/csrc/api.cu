@@ -44,6 +44,8 @@ cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const Tehm
 size_t tehmm_xi_tile_scratch_bytes(int sms);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
 cudaError_t tehmm_launch_transfer_ops(cudaStream_t, const TehmmModelDev &, const TehmmChunk *, const int64_t *, int64_t, int, int, const void *, void *, double *, int);
+cudaError_t tehmm_launch_ratio_fold(cudaStream_t, const TehmmModelDev &, int64_t, int, const double *, void *, double *, int);
+cudaError_t tehmm_launch_ratio_diag(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const double *, const void *, double *, double *, int);
 cudaError_t tehmm_launch_chain(cudaStream_t, const TehmmModelDev &, int, int, int, const int64_t *, const int64_t *, int64_t, const void *, const double *, const void *, void *);
 
 // ---------------------------------------------------------------- errors
@@ -800,7 +802,7 @@ static Scratch carve(const tehmm_ctx *c, int prec)
         int64_t cap = (c->b.total + 255) / 256;     // at least 256 steps per CTA
         s.nparts = (int)std::max<int64_t>(1, std::min(want, cap));
     }
-    s.hist = o; o = align_up(o + (size_t)s.nparts * std::max(c->m.tab_rows, c->m.srows) * c->m.N * 8);
+    s.hist = o; o = align_up(o + (size_t)s.nparts * std::max(c->m.tab_rows, c->m.srows) * c->m.N * 8 + 16);   // + the ratio cap (stats.cu)
     s.total = o;
     return s;
 }
@@ -1243,6 +1245,30 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
         tk_end(c, TK_XI);
         c->launches += 2;
     }
+    return TEHMM_OK;
+}
+
+int tehmm_fold_ratios(tehmm_ctx *c, int prec, const double *d_ratios, void *d_blin, double *d_rowmax)
+{
+    RUN_PROLOGUE();
+    if (!d_ratios || !d_blin || !d_rowmax) return fail(TEHMM_EINVAL, "NULL argument");
+    CU(tehmm_launch_ratio_fold(st, c->m, c->b.total, prec, d_ratios, d_blin, d_rowmax, c->sms));
+    c->launches += 1;
+    return TEHMM_OK;
+}
+
+int tehmm_ratio_diag_counts(tehmm_ctx *c, int prec, const void *d_post, const double *d_ratios,
+                            double *d_start_trans, void *d_scratch)
+{
+    RUN_PROLOGUE();
+    if (!d_post || !d_ratios || !d_start_trans || !d_scratch) return fail(TEHMM_EINVAL, "NULL argument");
+    const Scratch s = carve(c, prec);
+    double *part = (double *)((char *)d_scratch + s.xi);       // >= nchunks * NP * NP * ts bytes: room for nchunks * 64 doubles
+    // one warp per chunk walks its rows one after the other: the fine partition (5x as many, 5x shorter) where it fits
+    const size_t room = (size_t)c->b.nchunks * c->m.NP * c->m.NP * (prec == TEHMM_F32 ? 4 : 8);
+    const TehmmBatchDev &PB = (size_t)c->bf.nchunks * 64 * 8 <= room ? c->bf : c->b;
+    CU(tehmm_launch_ratio_diag(st, c->m, PB, prec, d_ratios, d_post, part, d_start_trans, c->sms));
+    c->launches += 2;
     return TEHMM_OK;
 }
 

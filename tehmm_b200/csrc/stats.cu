@@ -13,6 +13,7 @@
 //
 // Algorithmic HBM bytes per step: 4N (posteriors) + K (symbols).
 #include "scan.cuh"
+#include <algorithm>
 
 #define ST_TILE 32   // time steps staged per CTA iteration
 
@@ -171,6 +172,23 @@ emission_stats_atomic_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64
     }
 }
 
+// *max_bits = bit pattern of max_t (float)ratios[t] (ratios are positive: patterns order like values);
+// zeroed by the launcher.  The consumer rounds it up to a power of two (ratio_cap_of).
+__global__ void ratio_max_kernel(const double *__restrict__ ratios, int64_t total, unsigned *__restrict__ max_bits)
+{
+    float mx = 0.f;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        mx = fmaxf(mx, (float)ratios[t]);
+    unsigned b = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(mx, 0.f)));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits, b);
+}
+__device__ __forceinline__ float ratio_cap_of(const float *cap_dev)
+{
+    // (float)ratio rounds to nearest, so a ratio just below a power of two may round up to it: one binade of slack
+    const unsigned b = __float_as_uint(fmaxf(*cap_dev, 1.f));
+    return __uint_as_float(((b >> 23) + 1u) << 23);
+}
+
 // Same, over MERGED tracks (TehmmModelDev::sgdesc): a group of up to four tracks has one
 // histogram row per combination of its tracks' symbols, so a time step costs two reductions
 // per GROUP instead of two per track (10 tracks -> 5 groups at the bench shape: the kernel is
@@ -181,8 +199,14 @@ template <typename OBS, int SGT>
 __global__ void __launch_bounds__(SA_WARPS * 32, 1)
 emission_stats_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                              const float *__restrict__ post, double *__restrict__ part,
-                             double *__restrict__ dense_stats, int64_t steps_per_cta, int statS)
+                             double *__restrict__ dense_stats, int64_t steps_per_cta, int statS,
+                             const double *__restrict__ ratios, const float *__restrict__ cap_dev)
 {
+    // ratios != nullptr (fastAccumulateStats with segRatios, _emission.pyx:146-234): a row's posteriors are
+    // weighted by its segment ratio.  The fixed-point bins hold weight / cap with cap = the power of two at or
+    // above the largest ratio of the batch (ratio_cap_kernel), so they keep their 41-bit headroom; the flush
+    // multiplies it back (a power of two: exact).
+    const float cap = ratios ? ratio_cap_of(cap_dev) : 1.f, inv_cap = 1.f / cap;
     extern __shared__ __align__(16) unsigned char st_smem[];
     const int N = m.N, K = m.K;
     unsigned *hist = reinterpret_cast<unsigned *>(st_smem);                        // [srows][2 limbs][32]
@@ -210,6 +234,11 @@ emission_stats_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64
         float p[SA_ROWS];
 #pragma unroll
         for (int r = 0; r < SA_ROWS; ++r) p[r] = r < rows ? post[(tb + r) * 32 + lane] : 0.f;
+        if (ratios) {
+#pragma unroll
+            for (int r = 0; r < SA_ROWS; ++r)
+                if (r < rows) p[r] *= (float)ratios[tb + r] * inv_cap;
+        }
         // byte offset of the merged histogram row of every (row, group); -1: a symbol outside its table
         for (int e = lane; e < rows * SGT; e += 32) {
             const int r = e / SGT, gq = e - r * SGT;
@@ -240,7 +269,7 @@ emission_stats_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64
                         const int32_t *d = gd_s + gq * TEHMM_GDESC;
                         for (int i = 0; i < d[0]; ++i) {
                             const int k = d[2 + i];
-                            atomicAdd(&dense_stats[((int64_t)k * N + lane) * statS + (int)obs[(tb + r) * K + k]], (double)p[r]);
+                            atomicAdd(&dense_stats[((int64_t)k * N + lane) * statS + (int)obs[(tb + r) * K + k]], (double)p[r] * (double)cap);
                         }
                     }
                 }
@@ -252,7 +281,7 @@ emission_stats_merged_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64
             for (int row = warp; row < m.srows; row += SA_WARPS) {
                 const unsigned lo = hist[row * 64 + lane], hi = hist[row * 64 + 32 + lane];
                 if ((lo | hi) && lane < N) {
-                    dst[(int64_t)row * N + lane] += ((double)hi * 1048576.0 + (double)lo) * 9.094947017729282e-13;    // 2^20, 2^-40
+                    dst[(int64_t)row * N + lane] += ((double)hi * 1048576.0 + (double)lo) * 9.094947017729282e-13 * (double)cap;    // 2^20, 2^-40
                     hist[row * 64 + lane] = 0u;
                     hist[row * 64 + 32 + lane] = 0u;
                 }
@@ -348,14 +377,21 @@ static cudaError_t launch_stats(cudaStream_t st, const TehmmModelDev &m, const T
         emission_stats_global_kernel<T, OBS><<<148 * 8, 256, 0, st>>>(m, (const OBS *)b.obs, b.total, post, ratios, obs_stats, statS);
         return cudaGetLastError();
     }
-    if (sizeof(T) == 4 && m.LD == 32 && m.SG >= 1 && m.SG <= 8 && m.SG < m.K && !ratios) {
+    if (sizeof(T) == 4 && m.LD == 32 && m.SG >= 1 && m.SG <= 8 && m.SG < m.K) {
         const size_t sm3 = (size_t)m.srows * 256 + (size_t)(8 * TEHMM_GDESC + ((m.K + 3) & ~3)) * 4 + (size_t)SA_WARPS * SA_ROWS * 8 * 4 + 16;
         if (sm3 <= 220 * 1024) {
             const int64_t per = ((b.total + nparts - 1) / nparts + SA_TILE - 1) / SA_TILE * SA_TILE;
+            // the ratio cap lives behind the CTA partials (part has room for max(tab_rows, srows) * N doubles per CTA)
+            float *cap_dev = reinterpret_cast<float *>(part + (int64_t)nparts * std::max(m.tab_rows, m.srows) * m.N);
+            if (ratios) {
+                cudaError_t ec = cudaMemsetAsync(cap_dev, 0, sizeof(float), st);
+                if (ec != cudaSuccess) return ec;
+                ratio_max_kernel<<<148 * 4, 256, 0, st>>>(ratios, b.total, reinterpret_cast<unsigned *>(cap_dev));
+            }
 #define ST_MERGED(G_) do { auto k3 = emission_stats_merged_kernel<OBS, G_>; \
                            cudaError_t e3 = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3); \
                            if (e3 != cudaSuccess) return e3; \
-                           k3<<<nparts, SA_WARPS * 32, sm3, st>>>(m, (const OBS *)b.obs, b.total, (const float *)post, part, obs_stats, per, statS); } while (0)
+                           k3<<<nparts, SA_WARPS * 32, sm3, st>>>(m, (const OBS *)b.obs, b.total, (const float *)post, part, obs_stats, per, statS, ratios, cap_dev); } while (0)
             switch (m.SG) {
             case 1: ST_MERGED(1); break;
             case 2: ST_MERGED(2); break;

@@ -319,6 +319,13 @@ class Engine(object):
                                                self._p(blin), self._p(rowmax)))
         return elog, blin, rowmax
 
+    def fold_ratios(self, prec, d_ratios, blin, rowmax):
+        """segment ratios of the forward / backward recursions folded into the linear emission lattice
+        (tehmm_fold_ratios): the passes that follow run without ratios, on the tile kernels"""
+        if d_ratios is not None:
+            _lib.check(self.lib.tehmm_fold_ratios(self.ctx.handle, prec, self._p(d_ratios), self._p(blin), self._p(rowmax)))
+        return None
+
     def run_forward(self, prec, tdt, blin, rowmax, d_ratios, want_alpha=True):
         alpha = self.empty(self.total * self.LD, tdt) if want_alpha else None
         logprob = self.empty(self.nseq, self.torch.float64)
@@ -388,6 +395,7 @@ class Engine(object):
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
         _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
+        d_rd = self.fold_ratios(prec, d_rd, blin, rowmax)
         # deferred verification (tehmm_ctx_check): one wait per call instead of one per stage
         _, logprob = self.ctx.optimistic(lambda: self.run_forward(prec, tdt, blin, rowmax, d_rd, want_alpha=False))
         return logprob.cpu().numpy()
@@ -398,6 +406,7 @@ class Engine(object):
         prec, tdt = self._prec(precision)
         d_re, d_rd = self.upload_ratios(ratios_em), self.upload_ratios(ratios_dp)
         _, blin, rowmax = self.run_emission(prec, tdt, d_re, False, True)
+        d_rd = self.fold_ratios(prec, d_rd, blin, rowmax)
         flags = (_lib.BWD_POSTERIORS if want_post else 0) | (_lib.BWD_MAP if want_map else 0) | \
                 (_lib.BWD_RENORM_EPS if renorm_eps else 0)
 
@@ -511,19 +520,23 @@ class Engine(object):
         n_total, slots = seq_slots if seq_slots is not None else (self.nseq, list(range(self.nseq)))
         d_r = ratios if (ratios is None or torch.is_tensor(ratios)) else self.upload_ratios(ratios)
         _, blin, rowmax = self.run_emission(prec, tdt, d_r, False, True)
+        self.fold_ratios(prec, d_r, blin, rowmax)          # forward / backward below run without ratios
         base = 2 + N + N * N + K * N * S
         flags = 0
         if want_trans or want_start:
             flags |= _lib.BWD_TRANS
-        if want_obs:
-            flags |= _lib.BWD_POSTERIORS
+        if want_obs or (d_r is not None and flags):
+            flags |= _lib.BWD_POSTERIORS                    # the ratios' diagonal counts come from the posteriors
 
         def stages():
-            alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, d_r)
+            alpha, logprob = self.run_forward(prec, tdt, blin, rowmax, None)
             packed = torch.zeros(base + n_total, dtype=torch.float64, device=self.device)
             if flags:
-                post, _, _ = self.run_backward(prec, tdt, flags, blin, alpha, d_r,
+                post, _, _ = self.run_backward(prec, tdt, flags, blin, alpha, None,
                                                start_trans=packed[2:2 + N + N * N])
+                if d_r is not None and (flags & _lib.BWD_TRANS):
+                    _lib.check(self.lib.tehmm_ratio_diag_counts(self.ctx.handle, prec, self._p(post), self._p(d_r),
+                                                                self._p(packed[2:2 + N + N * N]), self._p(self.scratch(prec))))
                 if want_obs:
                     self.run_emission_stats(prec, post, d_r, packed[2 + N + N * N:base], S)
             return packed, logprob
