@@ -302,6 +302,22 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     const size_t o_rowmax = o; o = up256(o + (size_t)total * 8);
     const size_t o_la = o; o = up256(o + lat);
     const size_t o_lb = o; o = up256(o + lat);
+    // Where the widening to int64 happens.  Host (default): one byte per step over PCIe, the pool's threads
+    // widen behind the copy.  Device (TEHMM_WIDEN=gpu, and only when the caller's result array is page-locked:
+    // the Python layer registers its result pool under TEHMM_PIN_RESULTS=1): a kernel widens and the DMA engine
+    // writes the int64 path straight into the result.  Measured, not the default: 9.6 vs 8.7 ms per
+    // Viterbi + MAP pair on one GPU and 22.4 vs 18.2 ms with eight ranks on one host
+    // (profiles/r02_notes_e2e.md) -- eight times the bytes over PCIe and into host memory cost more than the
+    // host threads they save; the 1 -> 8 GPU end-to-end curve is bound by the host's memory system either way.
+    bool gpu_widen = false;
+    {
+        cudaPointerAttributes attr;
+        const bool pinned_out = cudaPointerGetAttributes(&attr, h_states) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const char *w = getenv("TEHMM_WIDEN");
+        if (pinned_out) gpu_widen = w != nullptr && !strcmp(w, "gpu");
+    }
+    const size_t o_s64 = o; if (gpu_widen) o = up256(o + (size_t)total * 8);
     const size_t o_scratch = o;
     // the scratch size depends on the partition: describe the batch first, with the obs pointer
     // the arena will have (the arena may have to grow before anything is enqueued)
@@ -436,6 +452,24 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         }
         pin_lp = (double *)(p->pin_out + up256((size_t)total));
         HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 16, cudaMemcpyDeviceToHost, st));
+        if (gpu_widen) {
+            int64_t *d_s64 = (int64_t *)(A + o_s64);
+            HOK(tehmm_widen_states(c, d_states, d_s64, total));
+            HCU(cudaMemcpyAsync(h_states, d_s64, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+            HCU(cudaStreamSynchronize(st));
+            tr.mark("d2h(int64)", false);
+            rc = TEHMM_OK;
+            if (attempt == 0) {
+                int64_t unverified = 0;
+                HOK(tehmm_ctx_set_option(c, "defer", 0));
+                HOK(tehmm_ctx_check(c, &unverified));
+                if (unverified == 0) { p->defer_penalty /= 2; break; }
+                p->redone += 1;
+                p->defer_penalty = std::min(256, std::max(4, 2 * p->defer_penalty));
+                p->defer_skip = p->defer_penalty;
+            }
+            continue;
+        }
         // slices, so that the widening of slice i overlaps the transfer of slice i+1
         const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
         const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
@@ -479,7 +513,7 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     }
     memcpy(h_logprob, pin_lp, (size_t)nseq * 8);
     if (h_score) memcpy(h_score, pin_lp + nseq, (size_t)nseq * 8);
-    p->d2h_bytes = (int64_t)total + nseq * 16;
+    p->d2h_bytes = (gpu_widen ? (int64_t)total * 8 : (int64_t)total) + nseq * 16;
     return TEHMM_OK;
 }
 

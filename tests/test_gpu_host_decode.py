@@ -76,6 +76,30 @@ def test_decode_host_equals_device_path_large():
     assert eng.h2d_bytes == (T + 200_003) * 10 and eng.d2h_bytes == T + 200_003 + 32
 
 
+def test_device_side_widening_into_the_registered_result(monkeypatch):
+    """TEHMM_WIDEN=gpu: the int64 path is written by the DMA engine straight into the (page-locked) result
+    array of the Python layer's pool -- no host thread touches it; same states as the host-widening route."""
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=30, seed=0)
+    obs, _ = synth.sample_obs(m, 700_001, seed=5)
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    monkeypatch.setenv("TEHMM_WIDEN", "host")
+    lp_h, _, st_h = eng.decode_host([obs], _lib.DECODE_VITERBI)
+    assert eng.d2h_bytes == 700_001 + 16
+    monkeypatch.setenv("TEHMM_WIDEN", "gpu")
+    lp_g, _, st_g = eng.decode_host([obs], _lib.DECODE_VITERBI)
+    assert eng.d2h_bytes == 8 * 700_001 + 16, "the result pool's blocks must be page-locked for the device-side route"
+    assert_array_equal(lp_g, lp_h)
+    assert_array_equal(st_g[0], st_h[0])
+    assert st_g[0].dtype == np.int64
+    _, sc_g, ms_g = eng.decode_host([obs], _lib.DECODE_MAP)
+    monkeypatch.setenv("TEHMM_WIDEN", "host")
+    _, sc_h, ms_h = eng.decode_host([obs], _lib.DECODE_MAP)
+    assert_array_equal(ms_g[0], ms_h[0])
+    assert_array_equal(sc_g, sc_h)
+
+
 def test_decode_api_uses_host_path_and_keeps_reference_answers():
     """hmmTest.py:48-135 known answer through MultitrackHmm.decode (now tehmm_decode_host)."""
     from tehmm_b200.emission import IndependentMultinomialEmissionModel
