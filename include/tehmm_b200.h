@@ -259,9 +259,20 @@ int tehmm_run_viterbi(tehmm_ctx *ctx, int prec, const void *d_elog, const double
  * states that crossed PCIe.  Blocks until the outputs are complete.          */
 #define TEHMM_DECODE_VITERBI 0
 #define TEHMM_DECODE_MAP 1
+#define TEHMM_DECODE_BOTH 2
 int tehmm_decode_host(tehmm_ctx *ctx, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes,
                       int64_t nseq, const int64_t *h_offsets, int algorithm, int prec,
                       int64_t *h_states, double *h_logprob, double *h_score);
+/* Both decodings of the same observations in ONE call -- what teHmmEval.py does when asked for the
+ * Viterbi path and the posterior decoding of the same tracks (teHmmEval.py:127-160), and what the
+ * fwd-bwd + Viterbi sweep of BASELINE.json is: the observations cross PCIe once, one emission pass
+ * feeds both stages, and the MAP path travels and is widened while the Viterbi kernels run.
+ * Outputs as two tehmm_decode_host calls would give them (bit-identical), plus the forward
+ * log-likelihood.                                                                              */
+int tehmm_decode_host_both(tehmm_ctx *ctx, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes,
+                           int64_t nseq, const int64_t *h_offsets, int prec,
+                           int64_t *h_viterbi_states, double *h_viterbi_logprob,
+                           int64_t *h_map_states, double *h_map_score, double *h_forward_logprob);
 /* bytes the last tehmm_decode_host moved over PCIe: which = 0 host->device, 1 device->host */
 int64_t tehmm_decode_host_bytes(tehmm_ctx *ctx, int which);
 /* wall-clock milliseconds of the phases of the last tehmm_decode_host call made with the

@@ -148,6 +148,7 @@ struct HostPipe {
     cudaEvent_t ring_ev[NRING] = {};
     bool ring_used[NRING] = {};
     cudaStream_t copy_stream = nullptr;     // host -> device copies, ahead of the compute stream
+    cudaEvent_t both_ev = nullptr;          // TEHMM_DECODE_BOTH: the backward pass is done (the MAP path may leave)
     std::vector<cudaEvent_t> slice_ev;      // one per slice of a call, reused
     unsigned char *pin_out = nullptr;       // states + the per-sequence scalars
     size_t pin_out_bytes = 0;
@@ -168,6 +169,7 @@ struct HostPipe {
         if (pin_out) cudaFreeHost(pin_out);
         for (cudaEvent_t e : slice_ev) cudaEventDestroy(e);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (both_ev) cudaEventDestroy(both_ev);
         delete pool;
     }
 };
@@ -268,16 +270,20 @@ void tehmm_hostpipe_release(tehmm_ctx *c)
 
 extern "C" {
 
-int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes, int64_t nseq,
-                      const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
-                      double *h_logprob, double *h_score)
+// algorithm TEHMM_DECODE_BOTH: h_states = the Viterbi path, h_logprob = its log-probability, h_states_map = the
+// MAP path, h_score = its score, h_fwd_logprob = the forward log-likelihood
+static int decode_host_impl(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes, int64_t nseq,
+                            const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
+                            double *h_logprob, double *h_score, int64_t *h_states_map, double *h_fwd_logprob)
 {
     if (!c || !h_obs_ptrs || !h_offsets || !h_states || !h_logprob) return herr(TEHMM_EINVAL, "NULL argument");
     if (nptr != 1 && nptr != nseq) return herr(TEHMM_EINVAL, "nptr must be 1 (one contiguous matrix) or nseq (one matrix per sequence)");
     for (int64_t i = 0; i < nptr; ++i)
         if (!h_obs_ptrs[i] && (nptr == 1 || h_offsets[i + 1] > h_offsets[i])) return herr(TEHMM_EINVAL, "h_obs_ptrs[%lld] is NULL", (long long)i);
-    if (algorithm != TEHMM_DECODE_VITERBI && algorithm != TEHMM_DECODE_MAP) return herr(TEHMM_EINVAL, "bad algorithm");
-    if (algorithm == TEHMM_DECODE_MAP && !h_score) return herr(TEHMM_EINVAL, "h_score is required for MAP");
+    if (algorithm != TEHMM_DECODE_VITERBI && algorithm != TEHMM_DECODE_MAP && algorithm != TEHMM_DECODE_BOTH) return herr(TEHMM_EINVAL, "bad algorithm");
+    if (algorithm != TEHMM_DECODE_VITERBI && !h_score) return herr(TEHMM_EINVAL, "h_score is required for MAP");
+    if (algorithm == TEHMM_DECODE_BOTH && (!h_states_map || !h_fwd_logprob)) return herr(TEHMM_EINVAL, "BOTH needs h_states_map and h_fwd_logprob");
+    const bool both = algorithm == TEHMM_DECODE_BOTH;
     if (prec != TEHMM_F32 && prec != TEHMM_F64) return herr(TEHMM_EINVAL, "bad prec");
     if (nseq <= 0) return herr(TEHMM_EINVAL, "nseq must be positive");
     int N = 0, K = 0, S = 0;
@@ -298,10 +304,12 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     size_t o = 0;
     const size_t o_obs = o; o = up256(o + obs_bytes_total);
     const size_t o_states = o; o = up256(o + (size_t)total);
-    const size_t o_lp = o; o = up256(o + (size_t)nseq * 16);
+    const size_t o_states2 = o; if (both) o = up256(o + (size_t)total);
+    const size_t o_lp = o; o = up256(o + (size_t)nseq * 32);        // [first logprob | score | second logprob] x nseq
     const size_t o_rowmax = o; o = up256(o + (size_t)total * 8);
     const size_t o_la = o; o = up256(o + lat);
     const size_t o_lb = o; o = up256(o + lat);
+    const size_t o_lc = o; if (both) o = up256(o + lat);          // BOTH: A = log emission, C = linear emission, B = alpha, then delta
     // Where the widening to int64 happens.  Host (default): one byte per step over PCIe, the pool's threads
     // widen behind the copy.  Device (TEHMM_WIDEN=gpu, and only when the caller's result array is page-locked:
     // the Python layer registers its result pool under TEHMM_PIN_RESULTS=1): a kernel widens and the DMA engine
@@ -361,10 +369,12 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     // enqueued on the compute stream behind that slice's event, so it overlaps the transfer of the
     // next one (the emission is the only stage that can start before the whole batch has arrived).
     if (!p->copy_stream) HCU(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-    double *d_lp = (double *)(A + o_lp), *d_sc = d_lp + nseq;
-    uint8_t *d_states = (uint8_t *)(A + o_states);
+    if (!p->both_ev) HCU(cudaEventCreateWithFlags(&p->both_ev, cudaEventDisableTiming));
+    double *d_lp = (double *)(A + o_lp), *d_sc = d_lp + nseq, *d_lp2 = d_lp + 2 * nseq;
+    uint8_t *d_states = (uint8_t *)(A + o_states), *d_states2 = (uint8_t *)(A + o_states2);
     const bool viterbi = algorithm == TEHMM_DECODE_VITERBI;
-    void *em_log = viterbi ? (void *)(A + o_la) : nullptr, *em_lin = viterbi ? nullptr : (void *)(A + o_la);
+    void *em_log = (viterbi || both) ? (void *)(A + o_la) : nullptr;
+    void *em_lin = both ? (void *)(A + o_lc) : (viterbi ? nullptr : (void *)(A + o_la));
     const bool piecewise = tehmm_emission_rows_supported(c, prec) == 1;
     const size_t row_bytes = (size_t)K * obs_bytes;
     int64_t slice_rows = (int64_t)(SLICE / row_bytes) & ~(int64_t)31;
@@ -432,7 +442,12 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         HOK(tehmm_ctx_set_option(c, "defer", attempt == 0 ? 1 : 0));
         // ---- the trellis
         if (!piecewise) HOK(tehmm_run_emission(c, prec, nullptr, em_log, em_lin, (double *)(A + o_rowmax)));
-        if (viterbi) {
+        if (both) {
+            // forward + backward(MAP) first: their states travel and are widened while the Viterbi kernels run
+            HOK(tehmm_run_forward(c, prec, A + o_lc, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp2, A + o_scratch));
+            HOK(tehmm_run_backward(c, prec, TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS, A + o_lc, A + o_lb, nullptr, nullptr,
+                                   d_states2, d_sc, nullptr, A + o_scratch));
+        } else if (viterbi) {
             HOK(tehmm_run_viterbi(c, prec, A + o_la, (const double *)(A + o_rowmax), nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
         } else {
             HOK(tehmm_run_forward(c, prec, A + o_la, (double *)(A + o_rowmax), nullptr, A + o_lb, d_lp, A + o_scratch));
@@ -442,7 +457,7 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
 
         tr.mark("trellis", true);
         // ---- device -> host: one byte per step over PCIe, widened by the host's cores
-        const size_t out_bytes = up256((size_t)total) + (size_t)nseq * 16;
+        const size_t out_bytes = (both ? 2 : 1) * up256((size_t)total) + (size_t)nseq * 32;
         if (p->pin_out_bytes < out_bytes) {
             HCU(cudaStreamSynchronize(st));
             if (p->pin_out) cudaFreeHost(p->pin_out);
@@ -450,9 +465,9 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
             HCU(cudaMallocHost((void **)&p->pin_out, out_bytes + out_bytes / 8));
             p->pin_out_bytes = out_bytes + out_bytes / 8;
         }
-        pin_lp = (double *)(p->pin_out + up256((size_t)total));
-        HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 16, cudaMemcpyDeviceToHost, st));
-        if (gpu_widen) {
+        pin_lp = (double *)(p->pin_out + (both ? 2 : 1) * up256((size_t)total));
+        if (!both) HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 32, cudaMemcpyDeviceToHost, st));
+        if (gpu_widen && !both) {
             int64_t *d_s64 = (int64_t *)(A + o_s64);
             HOK(tehmm_widen_states(c, d_states, d_s64, total));
             HCU(cudaMemcpyAsync(h_states, d_s64, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
@@ -473,30 +488,51 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
         // slices, so that the widening of slice i overlaps the transfer of slice i+1
         const int nsl = (int)std::min<int64_t>(8, (total + (1 << 20) - 1) >> 20);
         const int64_t per_sl = ((total + nsl - 1) / nsl + 63) & ~(int64_t)63;
-        while ((int)p->slice_ev.size() < nsl) {            // the upload's events are long complete: reuse them
+        while ((int)p->slice_ev.size() < 2 * nsl) {        // the upload's events are long complete: reuse them
             cudaEvent_t ev;
             HCU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             p->slice_ev.push_back(ev);
         }
         const std::vector<cudaEvent_t> &evs = p->slice_ev;
-        for (int i = 0; i < nsl; ++i) {
-            const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
-            if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + a, d_states + a, (size_t)n, cudaMemcpyDeviceToHost, st));
-            HCU(cudaEventRecord(evs[i], st));
-        }
+        // queue the copies of one path (`which` picks the half of the pinned buffer and of the events)
+        auto queue_copies = [&](const uint8_t *d_src, int which, cudaStream_t cs) -> int {
+            for (int i = 0; i < nsl; ++i) {
+                const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+                if (n > 0) HCU(cudaMemcpyAsync(p->pin_out + which * up256((size_t)total) + a, d_src + a, (size_t)n, cudaMemcpyDeviceToHost, cs));
+                HCU(cudaEventRecord(evs[which * nsl + i], cs));
+            }
+            return TEHMM_OK;
+        };
+        auto widen_slices = [&](int64_t *h_dst, int which) {
+            for (int i = 0; i < nsl; ++i) {
+                const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
+                cudaError_t e = cudaEventSynchronize(evs[which * nsl + i]);
+                if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
+                if (n <= 0 || rc != TEHMM_OK) continue;
+                const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
+                const uint8_t *src = p->pin_out + which * up256((size_t)total) + a;
+                int64_t *dst = h_dst + a;
+                p->pool->parallel_for(nth, [&](int t) {
+                    const int64_t b0 = (int64_t)t * per;
+                    if (b0 < n) widen_u8_i64(src + b0, dst + b0, std::min(per, n - b0));
+                });
+            }
+        };
         rc = TEHMM_OK;
-        for (int i = 0; i < nsl; ++i) {
-            const int64_t a = (int64_t)i * per_sl, n = std::min(per_sl, total - a);
-            cudaError_t e = cudaEventSynchronize(evs[i]);
-            if (e != cudaSuccess) { rc = herr(TEHMM_ECUDA, "decode failed: %s", cudaGetErrorString(e)); continue; }
-            if (n <= 0 || rc != TEHMM_OK) continue;
-            const int64_t per = ((n + nth - 1) / nth + 63) & ~(int64_t)63;
-            const uint8_t *src = p->pin_out + a;
-            int64_t *dst = h_states + a;
-            p->pool->parallel_for(nth, [&](int t) {
-                const int64_t b0 = (int64_t)t * per;
-                if (b0 < n) widen_u8_i64(src + b0, dst + b0, std::min(per, n - b0));
-            });
+        if (both) {
+            // the MAP path leaves on the copy stream behind the backward pass; the Viterbi stage is queued on
+            // the compute stream meanwhile, and the host widens the MAP path while those kernels run
+            HCU(cudaEventRecord(p->both_ev, st));
+            HCU(cudaStreamWaitEvent(p->copy_stream, p->both_ev, 0));
+            HOK(queue_copies(d_states2, 1, p->copy_stream));
+            HOK(tehmm_run_viterbi(c, prec, A + o_la, (const double *)(A + o_rowmax), nullptr, nullptr, A + o_lb, d_states, nullptr, d_lp, A + o_scratch));
+            HCU(cudaMemcpyAsync(pin_lp, d_lp, (size_t)nseq * 32, cudaMemcpyDeviceToHost, st));
+            HOK(queue_copies(d_states, 0, st));
+            widen_slices(h_states_map, 1);
+            widen_slices(h_states, 0);
+        } else {
+            HOK(queue_copies(d_states, 0, st));
+            widen_slices(h_states, 0);
         }
         if (rc != TEHMM_OK) return rc;
         HCU(cudaStreamSynchronize(st));
@@ -513,9 +549,27 @@ int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr,
     }
     memcpy(h_logprob, pin_lp, (size_t)nseq * 8);
     if (h_score) memcpy(h_score, pin_lp + nseq, (size_t)nseq * 8);
-    p->d2h_bytes = (gpu_widen ? (int64_t)total * 8 : (int64_t)total) + nseq * 16;
+    if (both) memcpy(h_fwd_logprob, pin_lp + 2 * nseq, (size_t)nseq * 8);
+    p->d2h_bytes = (gpu_widen && !both ? (int64_t)total * 8 : (both ? 2 : 1) * (int64_t)total) + nseq * (both ? 32 : 16);
     return TEHMM_OK;
 }
+
+int tehmm_decode_host(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes, int64_t nseq,
+                      const int64_t *h_offsets, int algorithm, int prec, int64_t *h_states,
+                      double *h_logprob, double *h_score)
+{
+    if (algorithm == TEHMM_DECODE_BOTH) return herr(TEHMM_EINVAL, "TEHMM_DECODE_BOTH goes through tehmm_decode_host_both");
+    return decode_host_impl(c, h_obs_ptrs, nptr, obs_bytes, nseq, h_offsets, algorithm, prec, h_states, h_logprob, h_score, nullptr, nullptr);
+}
+
+int tehmm_decode_host_both(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t nptr, int obs_bytes, int64_t nseq,
+                           const int64_t *h_offsets, int prec, int64_t *h_viterbi_states, double *h_viterbi_logprob,
+                           int64_t *h_map_states, double *h_map_score, double *h_forward_logprob)
+{
+    return decode_host_impl(c, h_obs_ptrs, nptr, obs_bytes, nseq, h_offsets, TEHMM_DECODE_BOTH, prec, h_viterbi_states,
+                            h_viterbi_logprob, h_map_score, h_map_states, h_forward_logprob);
+}
+
 
 double tehmm_decode_host_phase_ms(tehmm_ctx *c, int which)
 {

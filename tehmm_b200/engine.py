@@ -251,6 +251,39 @@ class Engine(object):
         self.d2h_bytes = int(self.lib.tehmm_decode_host_bytes(self.ctx.handle, 1))
         return logprob, score, [states[offsets[i]:offsets[i + 1]] for i in range(len(arrays))]
 
+    def decode_host_both(self, obs_list, precision=None):
+        """Viterbi AND posterior (MAP) decoding of the same observations in one call
+        (tehmm_decode_host_both): one upload, one emission pass.  Returns
+        (viterbi logprob[nseq], [viterbi states], map score[nseq], [map states], forward logprob[nseq])."""
+        self._bind_stream()
+        self.batch_token = None
+        prec, _ = self._prec(precision)
+        arrays = [as_obs_array(o) for o in obs_list]
+        assert len(arrays) > 0
+        K = arrays[0].shape[1]
+        for a in arrays:
+            assert a.shape[1] == K, "all sequences must have the same number of tracks"
+        dt = arrays[0].dtype
+        if any(a.dtype != dt for a in arrays):
+            dt = np.dtype(np.int32)
+            arrays = [a.astype(np.int32) for a in arrays]
+        n = len(arrays)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([a.shape[0] for a in arrays], out=offsets[1:])
+        ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        total = int(offsets[-1])
+        vst, mst = _result_pool.empty_int64(total), _result_pool.empty_int64(total)
+        vlp, msc, flp = (np.empty(n, dtype=np.float64) for _ in range(3))
+        _lib.check(self.lib.tehmm_decode_host_both(self.ctx.handle, ptrs, n, dt.itemsize, n, _lib.ptr(offsets), prec,
+                                                   _lib.ptr(vst), _lib.ptr(vlp), _lib.ptr(mst), _lib.ptr(msc), _lib.ptr(flp)))
+        self._keep.pop("obs", None)
+        self._keep["offsets"] = offsets
+        self.total, self.nseq = total, n
+        self.h2d_bytes = int(self.lib.tehmm_decode_host_bytes(self.ctx.handle, 0))
+        self.d2h_bytes = int(self.lib.tehmm_decode_host_bytes(self.ctx.handle, 1))
+        cut = lambda st: [st[offsets[i]:offsets[i + 1]] for i in range(n)]
+        return vlp, cut(vst), msc, cut(mst), flp
+
     def use_device_batch(self, d_obs, obs_bytes, offsets):
         """Batch already resident on the device (bench / multi-call reuse)."""
         self._bind_stream()

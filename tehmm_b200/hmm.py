@@ -343,6 +343,34 @@ class MultitrackHmm(BaseHMM):
             res.append((float(sc), st))
         return res
 
+    def decode_both_batch(self, obs_list):
+        """Viterbi path AND posterior (MAP) decoding of every sequence in ONE pass over the data: what
+        decode_batch(obs, "viterbi") followed by decode_batch(obs, "map") return (bit-identical), as
+        [(viterbi logprob, viterbi states, map score, map states)], for the price of one upload and one
+        emission pass (teHmmEval.py asks for both of the same tracks, teHmmEval.py:127-160; the
+        reference computes its frame once per call).  Sequences with segment ratios, and models of
+        more than 64 states, take the two calls."""
+        wide = self._wide()
+        ratios = None if wide else [self._seg_ratios(o) for o in obs_list]
+        if wide or any(r is not None for r in ratios):
+            v = self.decode_batch(obs_list, "viterbi") if self._algorithm not in decoder_algorithms else None
+            saved = self._algorithm
+            try:
+                self._algorithm = "viterbi"
+                v = self.decode_batch(obs_list, "viterbi")
+                self._algorithm = "map"
+                m = self.decode_batch(obs_list, "map")
+            finally:
+                self._algorithm = saved
+            return [(a[0], a[1], b[0], b[1]) for a, b in zip(v, m)]
+        vlp, vst, msc, mst, flp = self._engine().decode_host_both(obs_list)
+        for lp in flp:
+            self._note_forward_logprob(float(lp))
+        return [(float(a), s, float(b), t) for a, s, b, t in zip(vlp, vst, msc, mst)]
+
+    def decode_both(self, obs):
+        return self.decode_both_batch([obs])[0]
+
     # ------------------------------------------------------------ one long sequence over all ranks
     def decode_sharded(self, obs, algorithm="viterbi", halo=4096, gather=True):
         """decode() of ONE long sequence with its time axis split over the ranks of the

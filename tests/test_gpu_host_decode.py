@@ -88,16 +88,43 @@ def test_device_side_widening_into_the_registered_result(monkeypatch):
     lp_h, _, st_h = eng.decode_host([obs], _lib.DECODE_VITERBI)
     assert eng.d2h_bytes == 700_001 + 16
     monkeypatch.setenv("TEHMM_WIDEN", "gpu")
+    from tehmm_b200 import engine as engine_mod
+    del st_h
+    engine_mod._result_pool._free[:] = []           # blocks are page-locked when they are created
     lp_g, _, st_g = eng.decode_host([obs], _lib.DECODE_VITERBI)
     assert eng.d2h_bytes == 8 * 700_001 + 16, "the result pool's blocks must be page-locked for the device-side route"
     assert_array_equal(lp_g, lp_h)
-    assert_array_equal(st_g[0], st_h[0])
+    st_g_copy = st_g[0].copy()
     assert st_g[0].dtype == np.int64
     _, sc_g, ms_g = eng.decode_host([obs], _lib.DECODE_MAP)
     monkeypatch.setenv("TEHMM_WIDEN", "host")
     _, sc_h, ms_h = eng.decode_host([obs], _lib.DECODE_MAP)
     assert_array_equal(ms_g[0], ms_h[0])
     assert_array_equal(sc_g, sc_h)
+    _, _, st_h2 = eng.decode_host([obs], _lib.DECODE_VITERBI)
+    assert_array_equal(st_g_copy, st_h2[0])
+
+
+def test_decode_both_equals_the_two_calls():
+    """one upload, one emission pass, both decodings: bit-identical to decode(viterbi) and decode(map)"""
+    from tehmm_b200 import synth
+    from tehmm_b200.emission import IndependentMultinomialEmissionModel
+    from tehmm_b200.hmm import MultitrackHmm
+    m = synth.make_model(N=30, seed=0)
+    obs = [synth.sample_obs(m, T, seed=20 + i)[0] for i, T in enumerate([1_200_003, 17, 300_000, 1])]
+    em = IndependentMultinomialEmissionModel(30, list(m["syms"]), zeroAsMissingData=True)
+    em.logProbs = m["table"].copy()
+    hv = MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy())
+    hm = MultitrackHmm(em, startprob=m["pi"].copy(), transmat=m["A"].copy(), algorithm="map")
+    v, mp = hv.decode_batch(obs), hm.decode_batch(obs)
+    both = hv.decode_both_batch(obs)
+    assert len(both) == len(obs)
+    for (vlp, vst, msc, mst), (lp, st), (sc, ms) in zip(both, v, mp):
+        assert vlp == lp and msc == sc
+        assert_array_equal(vst, st)
+        assert_array_equal(mst, ms)
+        assert vst.dtype == np.int64 and mst.dtype == np.int64
+    assert hv.getLastLogProb() is not None
 
 
 def test_decode_api_uses_host_path_and_keeps_reference_answers():
