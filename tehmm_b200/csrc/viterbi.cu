@@ -221,11 +221,17 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
 // halves: lane l keeps the maximum of to-state 2a+h = l, so e rows, delta rows
 // and the normalisation stay one-lane-per-state.  max is exact and the adds see
 // the same operands as before, so the lattice is bit-identical to viterbi_kernel's.
+// RATIO: segment ratios (_hmm.pyx:222-225,232-247).  Every candidate of to-state j gets
+// common_j = [r_t > 1] logA_jj (r_t - 1), folded into e; the from-state-0 candidate gets logA_jj r_t
+// instead (minus logA_00 when j = 0) -- the reference's asymmetry -- i.e. a per-step correction
+// x0_j = (r_t > 1 ? logA_jj : logA_jj r_t) - [j = 0] logA_00 on ONE of a lane's 32 candidates.
+template <bool RATIO>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 3)
 viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ elog,
                     float *__restrict__ lattice, float *__restrict__ start_vec,
                     float *__restrict__ end_vec, const int *__restrict__ bad, int mode,
-                    const double *__restrict__ rowmax, double *__restrict__ score_part)
+                    const double *__restrict__ rowmax, double *__restrict__ score_part,
+                    const double *__restrict__ ratios)
 {
     // score_part != nullptr: the chunk also returns its share of the Viterbi log-probability,
     //     sum over its rows of (the maximum M_t taken out of the delta row + rowmax[t]),
@@ -248,6 +254,11 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
     const float ls = (float)m.cut_start[lane];
     const uint32_t ds_base = (uint32_t)__cvta_generic_to_shared(&ds_all[warp][0][0]);
     const uint32_t ds_rd = ds_base + 64u * (uint32_t)h, ds_wr = ds_base + 4u * (uint32_t)lane;
+    // RATIO: diagonal of log A for this lane's state (common term) and for its two to-states (from-0 correction)
+    const float dgl = RATIO ? (float)m.cut_trans[(int64_t)lane * 32 + lane] : 0.f;
+    const float dg0 = RATIO ? (float)m.cut_trans[(int64_t)a2 * 32 + a2] : 0.f;
+    const float dg1 = RATIO ? (float)m.cut_trans[(int64_t)(a2 + 1) * 32 + a2 + 1] : 0.f;
+    const float a00 = RATIO ? (float)m.cut_trans[0] : 0.f;
 
     for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
          ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
@@ -261,6 +272,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         }
         const float *ep = elog + tw * 32 + lane;
         float *lp = lattice + tw * 32 + lane;
+        const double *rp = RATIO ? ratios + tw : nullptr;
         unsigned row = 0;
         const unsigned row0 = (unsigned)(ch.t0 - tw), row1 = (unsigned)(ch.t1 - tw);
         float dd, msum = 0.f;
@@ -270,7 +282,7 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         // addresses of this lane's slot and of its half of the vector in the buffer used by
         // this step (the two buffers alternate, so a lane may run one step ahead of the others).
         // Lanes >= N need no masking: their columns of log A are -inf and elog padding is 0.
-        auto lean_step = [&](float et, uint32_t wr, uint32_t rd) {
+        auto lean_step = [&](float et, uint32_t wr, uint32_t rd, float r = 1.f) {
             asm volatile("st.shared.f32 [%0], %1;" :: "r"(wr), "f"(dd) : "memory");
             __syncwarp();
             u64 x[8];
@@ -280,8 +292,18 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             float p0, p1;
             {
                 const u64 c0 = fadd2(x[0], A2[0][0]), c1 = fadd2(x[0], A2[1][0]);
-                p0 = fmaxf(lo2(c0), hi2(c0));
-                p1 = fmaxf(lo2(c1), hi2(c1));
+                float f0 = lo2(c0), f1 = lo2(c1);          // candidates of from-state 16h
+                if (RATIO) {
+                    // (a zero-probability self transition would give inf - inf in the reference's terms; guarded to 0
+                    //  like viterbi_kernel)
+                    float x0 = dg0 > -INFINITY ? (r > 1.f ? dg0 : dg0 * r) : 0.f;
+                    float x1 = dg1 > -INFINITY ? (r > 1.f ? dg1 : dg1 * r) : 0.f;
+                    if (a2 == 0 && a00 > -INFINITY) x0 -= a00;
+                    if (h == 0) { f0 += x0; f1 += x1; }
+                    if (r > 1.f) et += dgl * (r - 1.f);      // -inf for a state without self transition: it cannot hold a long segment
+                }
+                p0 = fmaxf(f0, hi2(c0));
+                p1 = fmaxf(f1, hi2(c1));
             }
 #pragma unroll
             for (int q = 1; q < 8; ++q) {
@@ -300,8 +322,8 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             msum += M;
         };
         uint32_t wrA = ds_wr, wrB = ds_wr + 128u, rdA = ds_rd, rdB = ds_rd + 128u;
-        auto step1 = [&](float et) {       // single step, then swap the buffers
-            lean_step(et, wrA, rdA);
+        auto step1 = [&](float et, float r = 1.f) {       // single step, then swap the buffers
+            lean_step(et, wrA, rdA, r);
             uint32_t t = wrA; wrA = wrB; wrB = t;
             t = rdA; rdA = rdB; rdB = t;
         };
@@ -309,37 +331,44 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         if (mode == 1) {
             dd = start_vec[ci * 32 + lane];
         } else if (from_start) {
-            const float v = ls + (own ? *ep : -INFINITY);
+            float v = ls + (own ? *ep : -INFINITY);
+            if (RATIO) {                   // _hmm.pyx:222-225
+                const float r0 = (float)rp[0];
+                if (r0 > 1.f && dgl > -INFINITY) v += dgl * (r0 - 1.f);
+                else if (r0 > 1.f) v = -INFINITY;
+            }
             const float M = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));
             dd = v - (M > -INFINITY ? M : 0.f);
             if (row0 == 0) { *lp = dd; macc = (double)M; }
             ep += 32; lp += 32;
+            if (RATIO) rp += 1;
             row = 1;
         } else {
             dd = own ? 0.f : -INFINITY;
         }
         if (mode == 0 && row0 > 0) {
-            for (; row < row0; ++row) { step1(*ep); ep += 32; lp += 32; }
+            for (; row < row0; ++row) { step1(*ep, RATIO ? (float)*rp : 1.f); ep += 32; lp += 32; if (RATIO) rp += 1; }
             start_vec[ci * 32 + lane] = dd;
             msum = 0.f;                   // warm-up rows belong to the chunk on the left
         }
         // steady state: the next VIT_U rows of e in flight; VIT_U is even, so the buffer
         // parity is the same at the top of every iteration
-        float en[VIT_U];
+        float en[VIT_U], rn[VIT_U];
         if (row + VIT_U <= row1) {
 #pragma unroll
-            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 32];
+            for (int u = 0; u < VIT_U; ++u) { en[u] = ep[u * 32]; rn[u] = RATIO ? (float)rp[u] : 1.f; }
         }
         while (row + 2 * VIT_U <= row1) {
-            float ec[VIT_U];
+            float ec[VIT_U], rc[VIT_U];
 #pragma unroll
-            for (int u = 0; u < VIT_U; ++u) ec[u] = en[u];
+            for (int u = 0; u < VIT_U; ++u) { ec[u] = en[u]; rc[u] = rn[u]; }
             ep += VIT_U * 32;
+            if (RATIO) rp += VIT_U;
 #pragma unroll
-            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 32];
+            for (int u = 0; u < VIT_U; ++u) { en[u] = ep[u * 32]; rn[u] = RATIO ? (float)rp[u] : 1.f; }
 #pragma unroll
             for (int u = 0; u < VIT_U; ++u) {
-                if (u & 1) lean_step(ec[u], wrB, rdB); else lean_step(ec[u], wrA, rdA);
+                if (u & 1) lean_step(ec[u], wrB, rdB, rc[u]); else lean_step(ec[u], wrA, rdA, rc[u]);
                 lp[u * 32] = dd;
             }
             lp += VIT_U * 32;
@@ -349,13 +378,14 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
         if (row + VIT_U <= row1) {
 #pragma unroll
             for (int u = 0; u < VIT_U; ++u) {
-                if (u & 1) lean_step(en[u], wrB, rdB); else lean_step(en[u], wrA, rdA);
+                if (u & 1) lean_step(en[u], wrB, rdB, rn[u]); else lean_step(en[u], wrA, rdA, rn[u]);
                 lp[u * 32] = dd;
             }
             ep += VIT_U * 32; lp += VIT_U * 32;
+            if (RATIO) rp += VIT_U;
             row += VIT_U;
         }
-        for (; row < row1; ++row) { step1(*ep); *lp = dd; ep += 32; lp += 32; }
+        for (; row < row1; ++row) { step1(*ep, RATIO ? (float)*rp : 1.f); *lp = dd; ep += 32; lp += 32; if (RATIO) rp += 1; }
         end_vec[ci * 32 + lane] = dd;
         if (score_part != nullptr) {
             double rs = 0.0;
@@ -574,11 +604,15 @@ __device__ __forceinline__ int tb4_argmax(float c0, float c1, float c2, float c3
     return __shfl_sync(TEHMM_FULL, 4 * u + il, lane0 + ulo);
 }
 
+// RATIO: the from-state-0 candidate carries the reference's extra term (see viterbi_lean_kernel); the term
+// common to all from-states does not move the arg-max.
+template <bool RATIO>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 4)
 vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ lattice,
                       uint8_t *__restrict__ states, int64_t *__restrict__ states64,
                       uint8_t *__restrict__ spec_end, uint8_t *__restrict__ pred,
-                      const uint8_t *__restrict__ forced_end, const int *__restrict__ bad, int mode)
+                      const uint8_t *__restrict__ forced_end, const int *__restrict__ bad, int mode,
+                      const double *__restrict__ ratios)
 {
     __shared__ __align__(16) float AT[32 * 32];            // AT[s*32 + i] = min(logA[i][s], 0)
     for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
@@ -591,6 +625,7 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
     const unsigned segshift = 8u * (unsigned)c;
     const int lane0 = 8 * c;
     const uint32_t at_lane = (uint32_t)__cvta_generic_to_shared(AT) + (uint32_t)u * 16u;
+    const float a00 = (float)m.cut_trans[0];
 
     for (int64_t wg = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; wg * 4 < b.nchunks;
          wg += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
@@ -618,8 +653,13 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
         }
         int spec = st;
         float4 ring[TB4_PF];
+        float rring[TB4_PF];                           // RATIO: the ratio of the row the walk stands on
+        const double *__restrict__ rr = RATIO ? ratios + tbase : nullptr;
 #pragma unroll
-        for (int p = 0; p < TB4_PF; ++p) ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - p, 0) * 32);
+        for (int p = 0; p < TB4_PF; ++p) {
+            ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - p, 0) * 32);
+            rring[p] = RATIO ? (float)rr[max(row - p, 0)] : 1.f;
+        }
         while (__any_sync(TEHMM_FULL, row >= 1)) {
 #pragma unroll
             for (int p = 0; p < TB4_PF; ++p) {
@@ -630,10 +670,19 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
                     if (states64) states64[tbase + row] = st;
                 }
                 const float4 dv = ring[p];
+                const float r = rring[p];
                 ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - TB4_PF, 0) * 32);
+                if (RATIO) rring[p] = (float)rr[max(row - TB4_PF, 0)];
                 float4 a;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(at_lane + (uint32_t)st * 128u));
+                if (RATIO) {
+                    // candidate of from-state 0 (lane u = 0, first element): + logA_ss r - [r > 1] logA_ss (r - 1), - logA_00 for s = 0
+                    const float dgs = AT[st * 32 + st];
+                    float extra0 = dgs > -INFINITY ? (r > 1.f ? dgs : dgs * r) : 0.f;
+                    if (st == 0 && a00 > -INFINITY) extra0 -= a00;
+                    if (u == 0) a.x += extra0;
+                }
                 const int sn = tb4_argmax(dv.x + a.x, dv.y + a.y, dv.z + a.z, dv.w + a.w, u, segshift, lane0);
                 if (act) { st = sn; row -= 1; }
             }
@@ -753,8 +802,11 @@ cudaError_t tehmm_launch_viterbi(cudaStream_t st, const TehmmModelDev &m, const 
                                  const double *rowmax, double *score_part)
 {
     if (prec == TEHMM_F32) {
-        if (m.NS == 1 && m.LD == 32 && !ratios) {
-            viterbi_lean_kernel<<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, rowmax, rowmax ? score_part : nullptr);
+        if (m.NS == 1 && m.LD == 32) {
+            if (ratios)
+                viterbi_lean_kernel<true><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, nullptr, nullptr, ratios);
+            else
+                viterbi_lean_kernel<false><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, rowmax, rowmax ? score_part : nullptr, nullptr);
             return cudaGetLastError();
         }
         if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
@@ -790,10 +842,13 @@ cudaError_t tehmm_launch_traceback(cudaStream_t st, const TehmmModelDev &m, cons
                                    int mode, int grid)
 {
     if (prec == TEHMM_F32) {
-        if (m.NS == 1 && m.LD == 32 && !ratios) {
+        if (m.NS == 1 && m.LD == 32) {
             const int64_t need = ((b.nchunks + 3) / 4 + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
             const int g4 = (int)(need < grid ? (need < 1 ? 1 : need) : grid);
-            vit_traceback4_kernel<<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode);
+            if (ratios)
+                vit_traceback4_kernel<true><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, ratios);
+            else
+                vit_traceback4_kernel<false><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, nullptr);
             return cudaGetLastError();
         }
         if (m.NS == 1) return launch_tb<float, 1>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);

@@ -164,3 +164,39 @@ def test_c5_shaped_single_long_sequence_50_states(oracle):
     assert stt["obs"].sum() == pytest.approx(T * m["K"], rel=1e-6)
     assert stt["trans"].sum() * N == pytest.approx(T - 1, rel=1e-6)
     assert np.all(stt["trans"][m["A"] == 0] == 0)
+
+
+def test_viterbi_with_segment_ratios_on_the_lean_kernels(oracle):
+    """decode of segmented tables (hmm.py:674: the DP sees the segment ratios, basehmm.py:327: the emission does
+    not): the fp32 lean DP and the four-chunks-per-warp traceback take the ratios, including the from-state-0
+    rule of _hmm.pyx:234-237; paths equal the oracle's except at near-ties, float64 (generic kernels) exactly"""
+    import time
+    import torch
+    from parity import assert_near_ties_only, oracle_frame
+    from tehmm_b200 import synth
+    from tehmm_b200.engine import get_engine
+    m = synth.make_model(N=30, seed=5)
+    lens = [150_000, 1, 2, 40_001]
+    rng = np.random.RandomState(4)
+    obs = [synth.sample_obs(m, n, seed=60 + i)[0] for i, n in enumerate(lens)]
+    ratios = [np.minimum(rng.geometric(1.0 / 60.0, size=n), 300) / 100.0 for n in lens]      # some > 1, most < 1
+    assert max(r.max() for r in ratios) > 1.5
+    eng = get_engine(0)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    out = {}
+    for prec in ("f64", "f32"):
+        out[prec] = eng.viterbi(ratios_em=None, ratios_dp=ratios, precision=prec)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng.viterbi(ratios_em=None, ratios_dp=ratios, precision="f32")
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    eng.viterbi(precision="f32")
+    torch.cuda.synchronize(); t2 = time.perf_counter()
+    print("viterbi fp32 with ratios %.2f ms, without %.2f ms" % (1e3 * (t1 - t0), 1e3 * (t2 - t1)))
+    for i, (o, r) in enumerate(zip(obs, ratios)):
+        frame = oracle_frame(oracle, o, m["table"], 1.0, None)
+        want, wlp = oracle._viterbi(o.shape[0], 30, m["log_start"], m["log_trans"], r, frame)
+        assert_array_equal(out["f64"][1][i], want)
+        assert out["f64"][0][i] == pytest.approx(wlp, rel=1e-10)
+        assert_near_ties_only(out["f32"][1][i], want, frame, m["log_start"], m["log_trans"], r, label="ratios seq %d" % i)
+        assert out["f32"][0][i] == pytest.approx(wlp, rel=1e-6)
