@@ -280,6 +280,9 @@ int64_t tehmm_decode_host_bytes(tehmm_ctx *ctx, int which);
  * tracing adds a stream synchronisation per phase, so it is not for timed runs): which = 0 batch
  * set-up, 1 host->device copy + emission, 2 trellis, 3 device->host copy + widening; -1 if not traced */
 double tehmm_decode_host_phase_ms(tehmm_ctx *ctx, int which);
+/* self-test of the library's host thread pool (no GPU needed): `rounds` back-to-back parallel loops of
+ * `threads` tiny tasks; returns the number of rounds in which an index did not run exactly once */
+int64_t tehmm_host_pool_selftest(int threads, int64_t rounds);
 /* device index / model shape of a context */
 int tehmm_ctx_device(tehmm_ctx *ctx);
 int tehmm_model_dims(tehmm_ctx *ctx, int *N, int *K, int *S);

@@ -70,14 +70,19 @@ public:
     }
 private:
     // A job is (generation, task count, function), snapshotted under the lock by whoever runs it.
-    // The task counter carries the generation in its high 32 bits, so a worker left over from
-    // generation g that fetches after parallel_for g+1 has reset the counter sees a foreign
-    // generation and leaves without running (or double counting) a task of the new job.
+    // The task counter carries the generation in its high 32 bits and is advanced by compare-and-swap
+    // ONLY while it still belongs to the caller's generation: a worker left over from generation g that
+    // comes back for more after parallel_for g+1 has reset the counter must neither run a task of the new
+    // job nor consume one of its indices (a plain fetch_add did the latter: task 0 of the new job was
+    // never run and parallel_for waited for ever -- seen once in ~25 bench runs).
     void work(uint64_t gen, int ntasks, const std::function<void(int)> *fn)
     {
         for (;;) {
-            const uint64_t v = next_.fetch_add(1);
-            if ((v >> 32) != (gen & 0xffffffffu) || (int)(v & 0xffffffffu) >= ntasks) return;
+            uint64_t v = next_.load();
+            for (;;) {
+                if ((v >> 32) != (gen & 0xffffffffu) || (int)(v & 0xffffffffu) >= ntasks) return;
+                if (next_.compare_exchange_weak(v, v + 1)) break;
+            }
             (*fn)((int)(v & 0xffffffffu));
             std::lock_guard<std::mutex> l(mu_);
             if (--pending_ == 0) done_.notify_all();
@@ -570,6 +575,23 @@ int tehmm_decode_host_both(tehmm_ctx *c, const void *const *h_obs_ptrs, int64_t 
                             h_viterbi_logprob, h_map_score, h_map_states, h_forward_logprob);
 }
 
+
+// Self-test of the host thread pool (no GPU): `rounds` back-to-back parallel_for calls of `threads` tiny tasks;
+// returns the number of rounds in which some index did not run exactly once (0 = pass).  A round that loses
+// a task would never return; the caller runs this under a timeout.
+int64_t tehmm_host_pool_selftest(int threads, int64_t rounds)
+{
+    if (threads < 1 || rounds < 0) return -1;
+    Pool pool(threads - 1);
+    std::vector<std::atomic<int>> hits((size_t)threads);
+    int64_t bad = 0;
+    for (int64_t r = 0; r < rounds; ++r) {
+        for (auto &h : hits) h.store(0);
+        pool.parallel_for(threads, [&](int i) { hits[(size_t)i].fetch_add(1); });
+        for (auto &h : hits) if (h.load() != 1) { ++bad; break; }
+    }
+    return bad;
+}
 
 double tehmm_decode_host_phase_ms(tehmm_ctx *c, int which)
 {

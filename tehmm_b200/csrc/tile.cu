@@ -627,7 +627,7 @@ bwd_tile_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__rest
     // per stage: b rows then alpha rows
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(tile_smem) +
                            (uint32_t)(warp * BWD_STAGES * 2 * TILE_STAGE_BYTES + lane * 16);
-    const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
+    constexpr bool renorm = (OUT & TEHMM_BWD_RENORM_EPS) != 0;      // compile time: no branch in the posterior epilogue
     const float eps32 = 1.1920928955078125e-07f;
     const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
     const float renorm_invf = (float)renorm_inv;
@@ -1332,6 +1332,7 @@ cudaError_t tehmm_launch_backward_tile(cudaStream_t st, const TehmmModelDev &m, 
     const int th = TILE_WARPS * 32;
     const int smem = TILE_WARPS * BWD_STAGES * 2 * TILE_STAGE_BYTES;
     const int out = flags & (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP);
+    const int outr = flags & (TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS);
     // ---- the regular tiles of a single-sequence batch, first pass: tensor-map blocks
     int64_t group0 = 0;
     if (TEHMM_TILE_TENSOR && use_tmap && b.nseq == 1 && mode == 0 && fine_len > b.warmup && fine_len % BT_TB == 0 &&
@@ -1370,11 +1371,15 @@ cudaError_t tehmm_launch_backward_tile(cudaStream_t st, const TehmmModelDev &m, 
 #define BWD_TILE(O) do { cudaError_t e = cudaFuncSetAttribute(bwd_tile_kernel<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
                          if (e != cudaSuccess) return e; \
                          bwd_tile_kernel<O><<<grid, th, smem, st>>>(m, b, flags, blin, alpha, post, map_states, map_part, start_vec, end_vec, bad, mode, group0); } while (0)
-    switch (out) {
+    switch (outr) {
     case 0: BWD_TILE(0); break;
     case TEHMM_BWD_POSTERIORS: BWD_TILE(TEHMM_BWD_POSTERIORS); break;
     case TEHMM_BWD_MAP: BWD_TILE(TEHMM_BWD_MAP); break;
-    default: BWD_TILE(TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP); break;
+    case TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP: BWD_TILE(TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP); break;
+    case TEHMM_BWD_RENORM_EPS: BWD_TILE(0); break;                 // nothing to renormalise without an output
+    case TEHMM_BWD_POSTERIORS | TEHMM_BWD_RENORM_EPS: BWD_TILE(TEHMM_BWD_POSTERIORS | TEHMM_BWD_RENORM_EPS); break;
+    case TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS: BWD_TILE(TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS); break;
+    default: BWD_TILE(TEHMM_BWD_POSTERIORS | TEHMM_BWD_MAP | TEHMM_BWD_RENORM_EPS); break;
     }
 #undef BWD_TILE
     return cudaGetLastError();

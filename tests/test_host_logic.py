@@ -153,3 +153,13 @@ def test_result_pool_recycles_only_unreachable_blocks():
     d[:] = 5
     assert b[0] == 9 and c[0] == 1
     assert d.dtype == np.int64 and d.flags.writeable and d.shape == (900,)
+
+
+@pytest.mark.timeout(120)
+def test_host_thread_pool_back_to_back_jobs():
+    """the decode path's thread pool under back-to-back parallel loops (a worker of the previous loop
+    coming back for more must not consume an index of the next one: that lost a task and hung the call)"""
+    from tehmm_b200 import _lib
+    lib = _lib.load()
+    for threads in (2, 4, 16):
+        assert lib.tehmm_host_pool_selftest(threads, 200_000) == 0
