@@ -94,7 +94,8 @@ struct tehmm_ctx {
     // option "timing": CUDA events around the first (speculative) launch of each main kernel, on the
     // launching stream; read back in microseconds with tehmm_ctx_get_stat("us_<kernel>")
     int64_t opt_timing = 0;
-    int64_t opt_umma = 0;             // 1: forward pass on tcgen05 / TMEM (umma.cu) where it applies -- correct, not yet faster
+    int64_t opt_umma = 0;             // 1: forward pass on tcgen05 / TMEM (umma.cu) for <= 32 states too -- correct, not faster there
+    int64_t opt_umma64 = 1;           // 33..64 states, one sequence: forward pass on tcgen05 / TMEM (default; 0 = one chunk per warp)
     int *d_fault = nullptr;           // raised by a kernel whose barrier protocol timed out
     int64_t stat_umma_passes = 0;
     int64_t opt_rescore = 0;          // 1: the Viterbi log-probability is always the float64 re-score of the returned path (default: the fp32 DP's own normaliser sum where the lean kernel runs)
@@ -222,6 +223,7 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     else if (!strcmp(name, "timing")) { c->opt_timing = v; for (int i = 0; i < TEHMM_NTIMED; ++i) c->ev_n[i] = 0; }
     else if (!strcmp(name, "fine_len")) c->opt_fine_len = v;
     else if (!strcmp(name, "umma")) c->opt_umma = v;
+    else if (!strcmp(name, "umma64")) c->opt_umma64 = v;
     else if (!strcmp(name, "xi_tile")) c->opt_xi_tile = v;
     else if (!strcmp(name, "defer")) c->opt_defer = v;
     else if (!strcmp(name, "bwd_tmap")) c->opt_bwd_tmap = v;
@@ -633,7 +635,7 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
     unsigned char *d = (unsigned char *)c->model_blob;
     TehmmModelDev &m = c->m;
     m.N = N; m.K = K; m.S = S; m.NS = NS; m.NP = NP; m.tab_rows = rows; m.normalize = normalize;
-    m.LD = NS == 1 ? 32 : N;
+    m.LD = NP;                      // rows of 32 or 64 elements: 16-byte vector / bulk / tensor-map accesses (N..LD-1 are padding)
     m.table_in_smem = (size_t)rows * N * 8 <= tehmm_emission_table_budget(K) ? 1 : 0;
     m.log_start = (const double *)(d + o_ls); m.log_trans = (const double *)(d + o_lt);
     m.table = (const double *)(d + o_tab); m.table_t = (const double *)(d + o_tt);
@@ -1132,10 +1134,15 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     int *bad = (int *)(w + s.bad), *nbad = (int *)(w + s.nbad);
     const int grid = scan_grid(c);
     const bool tile = use_tile(c, prec, d_ratios);
-    const TehmmBatchDev &PB = tile ? c->bf : c->b;       // the partition this pass runs on
+    // 33..64 states: the tcgen05 kernel (csrc/umma.cu, M128 N64 K8 tf32, state and accumulator in tensor memory,
+    // transition matrix in shared memory) takes the first pass over a single-sequence batch on the fine
+    // partition; repairs and everything else stay with the one-chunk-per-warp kernel
+    const bool wide_umma = c->opt_umma64 != 0 && c->opt_tile != 0 && prec == TEHMM_F32 && c->m.NS == 2 && c->m.LD == 64 &&
+                           d_ratios == nullptr && c->b.nseq == 1;
+    const TehmmBatchDev &PB = (tile || wide_umma) ? c->bf : c->b;       // the partition this pass runs on
     bool umma_used = false;
     auto launch = [&](int mode) -> cudaError_t {
-        if (tile && c->opt_umma && tehmm_forward_umma_ok(c->m, PB, mode, c->fine_len)) {
+        if (((tile && c->opt_umma) || wide_umma) && tehmm_forward_umma_ok(c->m, PB, mode, c->fine_len)) {
             cudaError_t eu = tehmm_launch_forward_umma(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha,
                                                        (float *)sv, (float *)ev, cs, c->sms, c->fine_len, c->d_fault);
             if (eu == cudaSuccess) { c->stat_umma_passes += 1; umma_used = true; return eu; }

@@ -43,15 +43,25 @@
 #define UM_CTAS 1                     // resident CTAs per SM
 #endif
 #define UM_ROWS 128
-#define UM_BOX (UM_ROWS * UM_TB * 128)            // bytes of one box: 32 KB
 #define UM_NLD 2                      // load buffers
 #define UM_NST 2                      // store buffers
+// NH = number of 32-column halves of a lattice row: 1 for <= 32 states (row stride 32), 2 for 33..64 states
+// (row stride 64; round 2).  A box is always {32 floats, TB steps, 128 chunks} with the 128-byte swizzle, so a
+// block of a 64-state lattice is two boxes side by side; TB = 1 there (shared memory).
+template <int NH> struct UmCfg {
+    static constexpr int TB = NH == 1 ? UM_TB : 1;
+    static constexpr int BOX = UM_ROWS * TB * 128;           // bytes of one box
+    static constexpr int BLK = NH * BOX;                     // bytes of one block buffer
+    static constexpr int NP = 32 * NH;
+    static constexpr int BMAT = NP * NP * 4;                 // one part (hi or lo) of the transition matrix
+    static constexpr int SMEM = 1024 + (UM_NLD + UM_NST) * BLK + 2 * BMAT + 256 + 2048;
+    static constexpr unsigned TMEM_COLS = NH == 1 ? 128u : 256u;
+};
 #ifdef UM_PROFILE
 #define UM_T(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
 #else
 #define UM_T(i) do { } while (0)
 #endif
-#define UM_SMEM (1024 + (UM_NLD + UM_NST) * UM_BOX + 2 * 4096 + 256)
 
 __device__ __forceinline__ void um_mbar_init(uint32_t bar, int count)
 {
@@ -131,35 +141,47 @@ __device__ __forceinline__ uint64_t um_smem_desc(uint32_t addr, uint32_t lbo, ui
            ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
 
-__global__ void __launch_bounds__(UM_ROWS, UM_CTAS)
+// NH == 2 runs TWO threads per chunk (256 per CTA): warps 0-3 take columns 0-31 of the rows, warps 4-7 columns
+// 32-63 (a warp reaches the 32 tensor-memory lanes of its index modulo 4), which halves the serial epilogue
+// between two tensor-core steps; the halves of a row exchange their maxima through shared memory.
+template <int NH>
+__global__ void __launch_bounds__(UM_ROWS * NH, UM_CTAS)
 fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
                 const double *__restrict__ rowmax, float *__restrict__ alpha,
                 float *__restrict__ start_vec, float *__restrict__ end_vec, double *__restrict__ cscale,
                 const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
                 int lf, int nfull, int *__restrict__ fault)
 {
+    typedef UmCfg<NH> C;
+    constexpr int UMTB = C::TB, NP = C::NP, LDS_ = 32 * NH;       // LDS_: lattice row stride in floats
+    constexpr uint32_t UMBOX = C::BOX, UMBLK = C::BLK, BMAT = C::BMAT;
     extern __shared__ unsigned char um_raw[];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(um_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B boxes: 1024-byte aligned
     unsigned char *gbase = um_raw + (base - raw);
-    const uint32_t ldbuf = base, stbuf = base + UM_NLD * UM_BOX, bhi = stbuf + UM_NST * UM_BOX, blo = bhi + 4096;
-    const uint32_t bars = blo + 4096;                             // ld[UM_NLD], mma
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + 2 * 4096 + 64);
+    const uint32_t ldbuf = base, stbuf = base + UM_NLD * UMBLK, bhi = stbuf + UM_NST * UMBLK, blo = bhi + BMAT;
+    const uint32_t bars = blo + BMAT;                             // ld[UM_NLD], mma
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UMBLK + 2 * BMAT + 64);
     int *esum_s = reinterpret_cast<int *>(gbase);                 // reused after the main loop (load buffer 0)
+    float *mxs = reinterpret_cast<float *>(gbase + (UM_NLD + UM_NST) * UMBLK + 2 * BMAT + 256);   // [parity][half][row]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tid % UM_ROWS, hh = tid / UM_ROWS;           // this thread's chunk of the tile and its column half
+    constexpr int NTHR = UM_ROWS * NH;
     const int N = m.N, W = b.warmup;
 
     // ---- transition matrix, hi / lo TF32 parts, canonical K-major layout: B[n = j][k = i] = A[i][j]
-    for (int e = tid; e < 32 * 32; e += UM_ROWS) {
-        const int n = e >> 5, k = e & 31;
-        const double v = m.lin_trans[(int64_t)k * 32 + n];
+    // (per 16-byte K-chunk: NP rows of 16 bytes; LBO = NP * 16 between the two chunks of one K = 8 instruction,
+    //  SBO = 128 between 8-row groups)
+    for (int e = tid; e < NP * NP; e += NTHR) {
+        const int n = e / NP, k = e % NP;
+        const double v = m.lin_trans[(int64_t)k * NP + n];
         uint32_t h;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"((float)v));
         uint32_t l;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"((float)(v - (double)__uint_as_float(h))));
-        const uint32_t off = (uint32_t)((k >> 2) * 512 + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
-        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + off) = h;
-        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UM_BOX + 4096 + off) = l;
+        const uint32_t off = (uint32_t)((k >> 2) * (NP * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
+        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UMBLK + off) = h;
+        *reinterpret_cast<uint32_t *>(gbase + (UM_NLD + UM_NST) * UMBLK + BMAT + off) = l;
     }
     if (tid == 0) {
         for (int i = 0; i < UM_NLD + 1; ++i) um_mbar_init(bars + 8 * i, 1);
@@ -167,7 +189,7 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(128u) : "memory");
+                     :: "r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // B parts (generic writes) -> tensor core (async proxy)
@@ -175,17 +197,17 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_d = tmem, t_hi = tmem + 32, t_lo = tmem + 64;              // column offsets
-    const uint32_t my_lane = (uint32_t)(warp * 32) << 16;                        // this warp's TMEM lanes
+    const uint32_t t_d = tmem, t_hi = tmem + NP, t_lo = tmem + 2 * NP;          // column offsets
+    const uint32_t my_lane = (uint32_t)((warp & 3) * 32) << 16;                  // this warp's TMEM lanes
     const uint32_t bar_mma = bars + 8 * UM_NLD;
-    // kind::tf32, F32 accumulate, A and B K-major, N = 32, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+    // kind::tf32, F32 accumulate, A and B K-major, N = NP, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)NP >> 3) << 17) | ((128u >> 4) << 24);
 
     uint32_t mma_phase = 0, ld_phase = 0;                         // bit i of ld_phase: parity of load barrier i
     volatile int *vfault = fault;
     for (int64_t tile = blockIdx.x; tile * UM_ROWS < b.nchunks; tile += gridDim.x) {
         // ---- this thread's chunk
-        const int64_t c = tile * UM_ROWS + tid;
+        const int64_t c = tile * UM_ROWS + row;
         const bool valid = c < b.nchunks;
         TehmmChunk ch = b.chunks[valid ? c : b.nchunks - 1];
         const int64_t dist = ch.t0 - ch.s0;
@@ -194,46 +216,51 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         const int ks = first ? W : 0, ke = W + len;
         const bool boxed = valid && len == lf && c < nfull;      // its rows travel in the boxes
         const int kmax = W + lf;
-        const int nblk = (kmax + UM_TB - 1) / UM_TB;
+        const int nblk = (kmax + UMTB - 1) / UMTB;
         const int c0 = (int)(tile * UM_ROWS);
-        const float *brow0 = blin + (ch.t0 - W) * 32;            // row of clock 0 (direct path only)
-        float *arow0 = alpha ? alpha + (ch.t0 - W) * 32 : nullptr;
+        const float *brow0 = blin + (ch.t0 - W) * LDS_;          // row of clock 0 (direct path only)
+        float *arow0 = alpha ? alpha + (ch.t0 - W) * LDS_ : nullptr;
 
         auto issue_load = [&](int j) {                           // thread 0
-            const int k0 = j * UM_TB;
+            const int k0 = j * UMTB;
             const bool warm = k0 < W;
             const uint32_t bar = bars + 8 * (j % UM_NLD);
-            um_mbar_expect_tx(bar, UM_BOX);
-            um_tensor_load3(ldbuf + (j % UM_NLD) * UM_BOX, &tmap_b, 0, warm ? lf - W + k0 : k0 - W, c0 - (warm ? 1 : 0), bar);
+            um_mbar_expect_tx(bar, UMBLK);
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh)
+                um_tensor_load3(ldbuf + (j % UM_NLD) * UMBLK + hh * UMBOX, &tmap_b, 32 * hh, warm ? lf - W + k0 : k0 - W, c0 - (warm ? 1 : 0), bar);
         };
         if (tid == 0)
             for (int j = 0; j < UM_NLD && j < nblk; ++j) issue_load(j);
 
         // ---- initial operand: a flat vector (a row that starts its sequence stays empty until clock W)
         uint32_t xh[32], xl[32];
+        {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            xh[i] = (valid && !first && i < N) ? __float_as_uint(1.f) : 0u;
-            xl[i] = 0u;
+            for (int i = 0; i < 32; ++i) {
+                xh[i] = (valid && !first && 32 * hh + i < N) ? __float_as_uint(1.f) : 0u;
+                xl[i] = 0u;
+            }
+            um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
+            um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
         }
-        um_tmem_st32(t_hi + my_lane, xh);
-        um_tmem_st32(t_lo + my_lane, xl);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         float scp = 1.f;
         int shp = 0, esum = 0;
 
         auto issue_mma = [&]() {                                 // thread 0, after the CTA barrier
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            constexpr uint32_t LBO = NP * 16, KSTEP = 2 * LBO;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                um_mma_tf32_ts(t_d, t_lo + kk * 8, um_smem_desc(bhi + kk * 1024, 512, 128), idesc, kk > 0);
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_lo + kk * 8, um_smem_desc(bhi + kk * KSTEP, LBO, 128), idesc, kk > 0);
 #ifndef UM_EXP_ONE_PRODUCT
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(blo + kk * 1024, 512, 128), idesc, 1);
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(blo + kk * KSTEP, LBO, 128), idesc, 1);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(bhi + kk * 1024, 512, 128), idesc, 1);
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(bhi + kk * KSTEP, LBO, 128), idesc, 1);
 #endif
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_mma) : "memory");
         };
@@ -245,126 +272,134 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #endif
         for (int j = 0; j < nblk; ++j) {
-            const uint32_t lb = ldbuf + (j % UM_NLD) * UM_BOX, sb = stbuf + (j % UM_NST) * UM_BOX;
+            const uint32_t lb = ldbuf + (j % UM_NLD) * UMBLK, sb = stbuf + (j % UM_NST) * UMBLK;
             um_mbar_wait(bars + 8 * (j % UM_NLD), (ld_phase >> (j % UM_NLD)) & 1u, vfault);
             ld_phase ^= 1u << (j % UM_NLD);
             UM_T(0);
-            const bool storing = alpha != nullptr && j * UM_TB + UM_TB > W;
+            const bool storing = alpha != nullptr && j * UMTB + UMTB > W;
             if (storing && j >= UM_NST) {                        // the store that last used this buffer has read it
                 if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(UM_NST - 1) : "memory");
                 __syncthreads();
             }
 #pragma unroll
-            for (int s = 0; s < UM_TB; ++s) {
-                const int k = j * UM_TB + s;
+            for (int s = 0; s < UMTB; ++s) {
+                const int k = j * UMTB + s;
                 if (k >= kmax) break;
-                // b row of this clock: from the box (128-byte line L = row * TB + s, 16-byte chunks XOR-swizzled) or direct
-                float bt[32];
-                const uint32_t line = (uint32_t)(tid * UM_TB + s);
-                if (boxed) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(bt[4 * q]), "=f"(bt[4 * q + 1]), "=f"(bt[4 * q + 2]), "=f"(bt[4 * q + 3])
-                                     : "r"(lb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
-                } else {
-                    const bool on = valid && k >= ks && k < ke;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 v = on ? *reinterpret_cast<const float4 *>(brow0 + (int64_t)k * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        bt[4 * q] = v.x; bt[4 * q + 1] = v.y; bt[4 * q + 2] = v.z; bt[4 * q + 3] = v.w;
-                    }
-                }
+                const uint32_t line = (uint32_t)(row * UMTB + s);      // 128-byte line of this thread's row in a box
+                const bool on = valid && k >= ks && k < ke;
+                const bool start_here = first && k == ks;
                 // D of this clock
                 UM_T(1);
                 um_mbar_wait(bar_mma, mma_phase, vfault);
                 mma_phase ^= 1u;
                 UM_T(2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t dv[32];
-                um_tmem_ld32(t_d + my_lane, dv);
-                UM_T(3);
-                // x' = D .* b * scale in packed fp32 (FMUL2), maximum as a 3-input tree
                 const u64 sc2 = pk2(scp, scp);
-                u64 a2[16];
-                float m0 = 0.f, m1 = 0.f;
+                const int sh_now = start_here ? 0 : shp;
+                float mx = 0.f;
+                {
+                    // b row half of this clock: from the box (16-byte chunks XOR-swizzled) or direct
+                    float bt[32];
+                    if (boxed) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const u64 d2 = ((u64)dv[2 * i + 1] << 32) | (u64)dv[2 * i];
-                    a2[i] = um_fmul2(d2, um_fmul2(pk2(bt[2 * i], bt[2 * i + 1]), sc2));
-                    if (i & 1) m1 = fmax3(m1, lo2(a2[i]), hi2(a2[i])); else m0 = fmax3(m0, lo2(a2[i]), hi2(a2[i]));
-                }
-                float mx = fmaxf(m0, m1);
-                int sh_now = shp;
-                if (first && k == ks) {                          // alpha_0 = pi .* b_0
-                    mx = 0.f;
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(bt[4 * q]), "=f"(bt[4 * q + 1]), "=f"(bt[4 * q + 2]), "=f"(bt[4 * q + 3])
+                                         : "r"(lb + hh * UMBOX + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 v = on ? *reinterpret_cast<const float4 *>(brow0 + (int64_t)k * LDS_ + 32 * hh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            bt[4 * q] = v.x; bt[4 * q + 1] = v.y; bt[4 * q + 2] = v.z; bt[4 * q + 3] = v.w;
+                        }
+                    }
+                    uint32_t dv[32];
+                    um_tmem_ld32(t_d + 32 * hh + my_lane, dv);
+                    UM_T(3);
+                    // x' = D .* b * scale in packed fp32 (FMUL2), maximum as a 3-input tree
+                    u64 a2[16];
+                    float m0 = 0.f, m1 = 0.f;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float p0 = (float)m.lin_start[2 * i] * bt[2 * i], p1 = (float)m.lin_start[2 * i + 1] * bt[2 * i + 1];
-                        a2[i] = pk2(p0, p1);
-                        mx = fmax3(mx, p0, p1);
+                        const u64 d2 = ((u64)dv[2 * i + 1] << 32) | (u64)dv[2 * i];
+                        a2[i] = um_fmul2(d2, um_fmul2(pk2(bt[2 * i], bt[2 * i + 1]), sc2));
+                        if (i & 1) m1 = fmax3(m1, lo2(a2[i]), hi2(a2[i])); else m0 = fmax3(m0, lo2(a2[i]), hi2(a2[i]));
                     }
-                    sh_now = 0;
-                }
-                if (!valid || k < ks) {
+                    float mh = fmaxf(m0, m1);
+                    if (start_here) {                            // alpha_0 = pi .* b_0
+                        mh = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) a2[i] = 0ull;
-                    mx = 0.f;
+                        for (int i = 0; i < 16; ++i) {
+                            const float p0 = (float)m.lin_start[32 * hh + 2 * i] * bt[2 * i], p1 = (float)m.lin_start[32 * hh + 2 * i + 1] * bt[2 * i + 1];
+                            a2[i] = pk2(p0, p1);
+                            mh = fmax3(mh, p0, p1);
+                        }
+                    }
+                    if (!valid || k < ks) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) a2[i] = 0ull;
+                        mh = 0.f;
+                    }
+                    mx = fmaxf(mx, mh);
+                    if (k >= W) {
+                        if (alpha) {
+                            if (boxed) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    asm volatile("st.shared.v2.u64 [%0], {%1,%2};"
+                                                 :: "r"(sb + hh * UMBOX + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)), "l"(a2[2 * q]), "l"(a2[2 * q + 1]) : "memory");
+                            } else if (valid && k < ke) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    *reinterpret_cast<ulonglong2 *>(arow0 + (int64_t)k * LDS_ + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                            }
+                        }
+                    } else if (k == W - 1 && pred) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<ulonglong2 *>(start_vec + c * NP + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                    }
+                    if (valid && k + 1 == ke) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<ulonglong2 *>(end_vec + c * NP + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                    }
+                    // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly (FFMA2: a - hi)
+                    const u64 neg1 = pk2(-1.f, -1.f);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const u64 h2 = a2[i] & 0xffffe000ffffe000ull;
+                        const u64 l2 = ffma2(h2, neg1, a2[i]);
+                        xh[2 * i] = (uint32_t)h2; xh[2 * i + 1] = (uint32_t)(h2 >> 32);
+                        xl[2 * i] = (uint32_t)l2; xl[2 * i + 1] = (uint32_t)(l2 >> 32);
+                    }
+                    UM_T(4);
+                    um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
+                    um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
                 }
+                if (NH == 2) mxs[((k & 1) * 2 + hh) * UM_ROWS + row] = mx;       // the other half of the row reads it behind the barrier
+                if (k >= W) esum += k < ke ? sh_now : 0;
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                UM_T(5);
+                if (s == UMTB - 1 || k + 1 >= kmax) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // alpha rows -> TMA store
+                __syncthreads();
+                if (NH == 2) mx = fmaxf(mx, mxs[((k & 1) * 2 + (hh ^ 1)) * UM_ROWS + row]);
                 {   // exact power-of-two scale for the NEXT step (scale_of in tile.cu)
                     const unsigned mb = __float_as_uint(mx);
                     scp = __uint_as_float(0x7f000000u - (mb & 0x7f800000u));
                     shp = (int)(mb >> 23) - 127;
                 }
-                if (k >= W) {
-                    esum += k < ke ? sh_now : 0;
-                    if (alpha) {
-                        if (boxed) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                asm volatile("st.shared.v2.u64 [%0], {%1,%2};"
-                                             :: "r"(sb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)), "l"(a2[2 * q]), "l"(a2[2 * q + 1]) : "memory");
-                        } else if (valid && k < ke) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<ulonglong2 *>(arow0 + (int64_t)k * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
-                        }
-                    }
-                } else if (k == W - 1 && pred) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<ulonglong2 *>(start_vec + c * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
-                }
-                if (valid && k + 1 == ke) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<ulonglong2 *>(end_vec + c * 32 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
-                }
-                // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly (FFMA2: a - hi)
-                const u64 neg1 = pk2(-1.f, -1.f);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const u64 h2 = a2[i] & 0xffffe000ffffe000ull;
-                    const u64 l2 = ffma2(h2, neg1, a2[i]);
-                    xh[2 * i] = (uint32_t)h2; xh[2 * i + 1] = (uint32_t)(h2 >> 32);
-                    xl[2 * i] = (uint32_t)l2; xl[2 * i + 1] = (uint32_t)(l2 >> 32);
-                }
-                UM_T(4);
-                um_tmem_st32(t_hi + my_lane, xh);
-                um_tmem_st32(t_lo + my_lane, xl);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                UM_T(5);
-                if (s == UM_TB - 1 || k + 1 >= kmax) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // alpha rows -> TMA store
-                __syncthreads();
                 UM_T(6);
                 if (tid == 0 && k + 1 < kmax) issue_mma();
                 UM_T(7);
             }
             if (tid == 0) {
                 if (storing) {
-                    const int k0 = j * UM_TB;
-                    um_tensor_store3(&tmap_a, 0, k0 - W, c0, sb);       // clocks before W are never in a storing block: W % TB == 0
+                    const int k0 = j * UMTB;
+#pragma unroll
+                    for (int hh = 0; hh < NH; ++hh)
+                        um_tensor_store3(&tmap_a, 32 * hh, k0 - W, c0, sb + hh * UMBOX);       // clocks before W are never in a storing block: W % TB == 0
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (j + UM_NLD < nblk) issue_load(j + UM_NLD);           // every thread has passed the barrier after reading lb
@@ -379,9 +414,9 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
         __syncthreads();
 
         // ---- log of everything taken out of each chunk: exponents and row maxima
-        esum_s[tid] = esum;
+        if (hh == 0) esum_s[row] = esum;
         __syncthreads();
-        for (int rr = warp; rr < UM_ROWS; rr += UM_ROWS / 32) {
+        for (int rr = warp; rr < UM_ROWS; rr += NTHR / 32) {
             const int64_t cc = tile * UM_ROWS + rr;
             if (cc >= b.nchunks) break;
             const TehmmChunk c2 = b.chunks[cc];
@@ -395,11 +430,11 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(C::TMEM_COLS) : "memory");
 }
 
-// [chunk][step][32 floats] view, boxes {32, UM_TB, 128}, 128-byte swizzle
-static bool um_make_tmap(CUtensorMap *tm, const float *base, int64_t lf, int64_t nfull)
+// [chunk][step][32 * NH floats] view, boxes {32, TB, 128}, 128-byte swizzle
+static bool um_make_tmap(CUtensorMap *tm, const float *base, int64_t lf, int64_t nfull, int nh, int tb)
 {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -416,20 +451,44 @@ static bool um_make_tmap(CUtensorMap *tm, const float *base, int64_t lf, int64_t
         else
             cudaGetLastError();
     }
-    if (!encode || nfull < 1 || lf < UM_TB) return false;
-    const cuuint64_t dims[3] = {32, (cuuint64_t)lf, (cuuint64_t)nfull};
-    const cuuint64_t strides[2] = {128, (cuuint64_t)lf * 128};
-    const cuuint32_t box[3] = {32, UM_TB, UM_ROWS}, estr[3] = {1, 1, 1};
+    if (!encode || nfull < 1 || lf < tb) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)(32 * nh), (cuuint64_t)lf, (cuuint64_t)nfull};
+    const cuuint64_t strides[2] = {(cuuint64_t)(128 * nh), (cuuint64_t)lf * 128 * nh};
+    const cuuint32_t box[3] = {32, (cuuint32_t)tb, UM_ROWS}, estr[3] = {1, 1, 1};
     return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// whether this batch / pass can take the tcgen05 kernel
+// whether this batch / pass can take the tcgen05 kernel: one sequence, first pass, lattice rows of 32 or 64 floats
 bool tehmm_forward_umma_ok(const TehmmModelDev &m, const TehmmBatchDev &b, int mode, int64_t fine_len)
 {
-    return m.NS == 1 && m.LD == 32 && b.nseq == 1 && mode == 0 && fine_len >= b.warmup && (b.warmup % UM_TB) == 0 &&
+    const int nh = m.NS;
+    const int tb = nh == 1 ? UM_TB : 1;
+    return m.LD == 32 * nh && b.nseq == 1 && mode == 0 && fine_len >= b.warmup && (b.warmup % tb) == 0 &&
            b.total / fine_len >= 1;
+}
+
+template <int NH>
+static cudaError_t launch_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
+                               const float *blin, const double *rowmax, float *alpha,
+                               float *start_vec, float *end_vec, double *cscale, int sms,
+                               int64_t fine_len, int *fault)
+{
+    typedef UmCfg<NH> C;
+    CUtensorMap tb, ta;
+    memset(&tb, 0, sizeof tb);
+    memset(&ta, 0, sizeof ta);
+    const int64_t nfull = b.total / fine_len;
+    if (!um_make_tmap(&tb, blin, fine_len, nfull, NH, C::TB) || (alpha && !um_make_tmap(&ta, alpha, fine_len, nfull, NH, C::TB)))
+        return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(fwd_umma_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (b.nchunks + UM_ROWS - 1) / UM_ROWS;
+    const int grid = (int)(tiles < (int64_t)sms * UM_CTAS ? tiles : (int64_t)sms * UM_CTAS);
+    fwd_umma_kernel<NH><<<grid, UM_ROWS * NH, C::SMEM, st>>>(m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, tb, ta,
+                                                        (int)fine_len, (int)nfull, fault);
+    return cudaGetLastError();
 }
 
 cudaError_t tehmm_launch_forward_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
@@ -437,17 +496,6 @@ cudaError_t tehmm_launch_forward_umma(cudaStream_t st, const TehmmModelDev &m, c
                                       float *start_vec, float *end_vec, double *cscale, int sms,
                                       int64_t fine_len, int *fault)
 {
-    CUtensorMap tb, ta;
-    memset(&tb, 0, sizeof tb);
-    memset(&ta, 0, sizeof ta);
-    const int64_t nfull = b.total / fine_len;
-    if (!um_make_tmap(&tb, blin, fine_len, nfull) || (alpha && !um_make_tmap(&ta, alpha, fine_len, nfull)))
-        return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(fwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM);
-    if (e != cudaSuccess) return e;
-    const int64_t tiles = (b.nchunks + UM_ROWS - 1) / UM_ROWS;
-    const int grid = (int)(tiles < (int64_t)sms * UM_CTAS ? tiles : (int64_t)sms * UM_CTAS);
-    fwd_umma_kernel<<<grid, UM_ROWS, UM_SMEM, st>>>(m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, tb, ta,
-                                                    (int)fine_len, (int)nfull, fault);
-    return cudaGetLastError();
+    if (m.NS == 1) return launch_umma<1>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
+    return launch_umma<2>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
 }

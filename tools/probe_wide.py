@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""33..64 states, one sequence: forward pass by the tcgen05 kernel (option umma64, default) against the
+one-chunk-per-warp kernel; log-likelihoods must agree."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tehmm_b200 import _lib, synth
+from tehmm_b200.engine import Engine
+
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+ctx = _lib.get_context(0); eng = Engine(ctx)
+for N in (50, 64, 33):
+    m = synth.make_model(N=N, seed=0)
+    obs, _ = synth.sample_obs(m, T, seed=1)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    prec, tdt = eng._prec("f32")
+    _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
+    res = {}
+    for opt in (1, 0):
+        ctx.set_option("umma64", opt)
+        for _ in range(2):
+            alpha, lp = ctx.optimistic(lambda: eng.run_forward(prec, tdt, blin, rowmax, None))
+        torch.cuda.synchronize()
+        ctx.set_option("timing", 1)
+        for _ in range(3):
+            alpha, lp = ctx.optimistic(lambda: eng.run_forward(prec, tdt, blin, rowmax, None))
+        torch.cuda.synchronize()
+        res[opt] = (ctx.stat("us_forward"), float(lp[0].item()), ctx.stat("umma_passes"), ctx.stat("repaired_chunks_forward"))
+        ctx.set_option("timing", 0)
+    ctx.set_option("umma64", 1)
+    print(json.dumps({"N": N, "T": T, "tcgen05_us": res[1][0], "warp_kernel_us": res[0][0], "logprob_tcgen05": res[1][1],
+                      "logprob_warp": res[0][1], "rel_diff": abs(res[1][1] - res[0][1]) / abs(res[0][1]),
+                      "umma_passes": res[1][2], "repaired": res[1][3]}), flush=True)
