@@ -20,6 +20,10 @@ import os
 import sys
 import time
 
+# config 5 holds two 60 GiB lattices at a time on a 178 GiB device: the caching allocator must not carve a
+# small tensor out of a cached lattice-sized block (a third block of that size does not fit)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -143,6 +147,7 @@ def run_c5(scale):
     states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False, rowmax=rm)
     ev[1].record()
     del elog
+    torch.cuda.empty_cache()
     _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
     alpha, logprob = eng.run_forward(prec, tdt, blin, rowmax, None)
     ev[2].record()
