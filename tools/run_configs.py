@@ -20,10 +20,6 @@ import os
 import sys
 import time
 
-# config 5 holds two 60 GiB lattices at a time on a 178 GiB device: the caching allocator must not carve a
-# small tensor out of a cached lattice-sized block (a third block of that size does not fit)
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -142,11 +138,15 @@ def run_c5(scale):
     eng.use_device_batch(d_obs, 1, np.array([0, T], dtype=np.int64))
     prec, tdt = eng._prec("f32")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    eng.ctx.set_option("timing", 1)        # kernel times by the library's own events (the stage times below include cudaMalloc)
     ev[0].record()
     elog, _, rm = eng.run_emission(prec, tdt, None, True, False)
     states, _, vlp = eng.run_viterbi(prec, elog, None, None, want64=False, rowmax=rm)
     ev[1].record()
     del elog
+    # config 5 holds two 60 GiB lattices at a time on a 178 GiB device: give the cached blocks back, or the
+    # allocator carves the 2 GB rowmax out of a cached lattice-sized block and a third block of that size does not fit
+    # (expandable segments avoid that too, but mapping 60 GiB in 2 MB granules takes seconds)
     torch.cuda.empty_cache()
     _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
     alpha, logprob = eng.run_forward(prec, tdt, blin, rowmax, None)
@@ -156,6 +156,8 @@ def run_c5(scale):
     ev[3].record()
     torch.cuda.synchronize()
     peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+    kernel_us = {k: eng.ctx.stat("us_" + k) for k in ("emission", "forward", "backward", "viterbi_dp", "traceback", "rescore")}
+    eng.ctx.set_option("timing", 0)
     vit_ms, fwd_ms, bwd_ms = (ev[i].elapsed_time(ev[i + 1]) for i in range(3))
     st_full = states[:2_000_000].cpu().numpy().astype(np.int64)
     ms_full = mstates[:2_000_000].cpu().numpy().astype(np.int64)
@@ -167,7 +169,8 @@ def run_c5(scale):
     _, st_pre = eng.viterbi()
     out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
     return {"config": "c5", "steps": T, "states": N, "tracks": 10, "host_generation_seconds": gen_s,
-            "viterbi_ms": vit_ms, "forward_ms": fwd_ms, "backward_map_ms": bwd_ms,
+            "viterbi_ms": vit_ms, "forward_ms": fwd_ms, "backward_map_ms": bwd_ms, "kernel_us": kernel_us,
+            "umma_passes": eng.ctx.stat("umma_passes"),
             "cells_per_s_sweep": T * N / ((vit_ms + fwd_ms + bwd_ms) * 1e-3),
             "peak_device_memory_gb": peak_gb, "logprob": lp, "viterbi_logprob": vlp,
             "viterbi_le_logprob": bool(vlp <= lp), "repaired_chunks": repairs,
