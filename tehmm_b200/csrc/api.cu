@@ -40,6 +40,8 @@ cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, cons
 int tehmm_tile_warps(void);
 bool tehmm_forward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int64_t);
 cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, int, int64_t, int *);
+bool tehmm_backward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int, int64_t);
+cudaError_t tehmm_launch_backward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, int, int64_t, int *);
 cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
 size_t tehmm_xi_tile_scratch_bytes(int sms);
 cudaError_t tehmm_launch_convert(cudaStream_t, int, const void *, double *, int64_t);
@@ -1212,8 +1214,20 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
                          !(flags & TEHMM_BWD_RENORM_EPS) && c->opt_xi_tile != 0;
     if (xi_tile) flags &= ~TEHMM_BWD_TRANS;
     const bool tile = use_tile(c, prec, d_ratios) && !(flags & TEHMM_BWD_TRANS);
-    const TehmmBatchDev &PB = tile ? c->bf : c->b;
+    // 33..64 states, one sequence, no transition counts: the tcgen05 twin of the forward kernel (csrc/umma.cu) takes the
+    // first pass on the fine partition; repairs stay with the one-chunk-per-warp kernel on the same partition
+    const bool wide_umma = c->opt_umma64 != 0 && c->opt_tile != 0 && prec == TEHMM_F32 && c->m.NS == 2 && c->m.LD == 64 &&
+                           d_ratios == nullptr && c->b.nseq == 1 && !(flags & TEHMM_BWD_TRANS);
+    const TehmmBatchDev &PB = (tile || wide_umma) ? c->bf : c->b;
+    bool umma_used = false;
     auto launch = [&](int mode) -> cudaError_t {
+        if (wide_umma && tehmm_backward_umma_ok(c->m, PB, flags, mode, c->fine_len)) {
+            cudaError_t eu = tehmm_launch_backward_umma(st, c->m, PB, flags, (const float *)d_blin, (const float *)d_alpha, (float *)d_post,
+                                                        d_map_states, mp, (float *)sv, (float *)ev, c->sms, c->fine_len, c->d_fault);
+            if (eu == cudaSuccess) { c->stat_umma_passes += 1; umma_used = true; return eu; }
+            if (eu != cudaErrorNotSupported) return eu;
+            cudaGetLastError();
+        }
         if (tile) {
             c->stat_tile_passes += 1;
             return tehmm_launch_backward_tile(st, c->m, PB, flags, (const float *)d_blin, (const float *)d_alpha, (float *)d_post, d_map_states, mp, (float *)sv, (float *)ev, bad, mode, c->sms, c->fine_len, (int)c->opt_bwd_tmap);
@@ -1231,7 +1245,12 @@ int tehmm_run_backward(tehmm_ctx *c, int prec, int flags, const void *d_blin, co
         CU(tehmm_launch_verify(st, PB, prec, c->m.NP, sv, ev, tol, -1, 1, bad, nbad, nullptr));
         c->launches += 1;
         int nb = 0;
-        if (read_nbad(c, nbad, &nb)) return TEHMM_ECUDA;
+        if (umma_used && pass == 0) CU(cudaMemcpyAsync(c->h_nbad + 1, c->d_fault, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (read_nbad(c, nbad, &nb, !umma_used)) return TEHMM_ECUDA;
+        if (umma_used && pass == 0 && c->h_nbad[1]) {
+            CU(cudaMemsetAsync(c->d_fault, 0, sizeof(int), st));
+            return fail(TEHMM_ECUDA, "bwd_umma_kernel: a barrier wait timed out (tensor-memory protocol fault)");
+        }
         if (pass == 0) adapt_warmup(c, nb, PB.nchunks);
         if (nb == 0) break;
         if (pass >= max_pass) return fail(TEHMM_ESTATE, "backward repair did not converge (%d chunks left)", nb);

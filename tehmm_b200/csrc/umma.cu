@@ -491,6 +491,404 @@ static cudaError_t launch_umma(cudaStream_t st, const TehmmModelDev &m, const Te
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ backward twin (33..64 states)
+// The backward recursion in the same shape, run right to left (hmm.py:715-729 -> _hmm.pyx:160-198, the
+// posterior glue basehmm.py:265-272,357).  With X the operand row (b_{t+1} .* beta'_{t+1}, scaled) the
+// accumulator of a clock IS beta'_t = X A^T (the transition matrix is staged transposed), so the epilogue of
+// clock k (time t = t1 - 1 + W - k) reads D, b_t and alpha_t of the SAME row:
+//     next X   = D .* b_t * 2^-shift                         (exactly fwd_umma_kernel's epilogue)
+//     p        = D .* alpha_t,  Z = sum p                    posterior = p / Z, MAP state = argmax p
+// Two threads per chunk (column halves) exchange their partial Z / best / arg-max through shared memory across
+// the step's one CTA barrier, next to the row maximum; the normalisation, the MAP byte and the posterior rows
+// are written BEHIND the barrier, while the tensor core runs the next clock.  The posterior rows overwrite the
+// alpha box they were computed from (same thread, same addresses) and leave as one tensor-map store per
+// clock; alpha buffers cycle load -> read -> overwrite -> store -> reload (three of them).  First pass of a
+// single-sequence batch only; repairs and transition counts stay with backward_kernel (backward.cu), whose
+// start_vec / end_vec / map_part conventions these are.
+#define UM_NA 3
+template <int NH> struct UmBwdCfg {
+    static constexpr int BOX = UM_ROWS * 128;
+    static constexpr int BLK = NH * BOX;
+    static constexpr int NP = 32 * NH;
+    static constexpr int BMAT = NP * NP * 4;
+    static constexpr int XCH = 4 * 2 * NH * UM_ROWS * 4;       // row maximum, Z, best, arg-max: [parity][half][row]
+    static constexpr int SMEM = 1024 + (UM_NLD + UM_NA) * BLK + 2 * BMAT + 256 + XCH;
+    static constexpr unsigned TMEM_COLS = NH == 1 ? 128u : 256u;
+};
+
+template <int NH>
+__global__ void __launch_bounds__(UM_ROWS * NH, 1)
+bwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, int flags, const float *__restrict__ blin,
+                const float *__restrict__ alpha, float *__restrict__ post, uint8_t *__restrict__ map_states,
+                double *__restrict__ map_part, float *__restrict__ start_vec, float *__restrict__ end_vec,
+                const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_a,
+                const __grid_constant__ CUtensorMap tmap_p, int lf, int nfull, int *fault)
+{
+    typedef UmBwdCfg<NH> C;
+    constexpr int NP = C::NP, LDS_ = 32 * NH;
+    constexpr uint32_t UMBOX = C::BOX, UMBLK = C::BLK, BMAT = C::BMAT;
+    constexpr int OFF_MAT = (UM_NLD + UM_NA) * C::BLK, OFF_BAR = OFF_MAT + 2 * C::BMAT;
+    extern __shared__ unsigned char um_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(um_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char *gbase = um_raw + (base - raw);
+    const uint32_t bbuf = base, abuf = base + UM_NLD * UMBLK, bhi = base + OFF_MAT, blo = bhi + BMAT;
+    const uint32_t bars = base + OFF_BAR;                         // b[UM_NLD], alpha[UM_NA], mma
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gbase + OFF_BAR + 64);
+    float *mxs = reinterpret_cast<float *>(gbase + OFF_BAR + 256);
+    float *zs = mxs + 2 * NH * UM_ROWS, *bests = zs + 2 * NH * UM_ROWS;
+    int *idxs = reinterpret_cast<int *>(bests + 2 * NH * UM_ROWS);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid % UM_ROWS, hh = tid / UM_ROWS;
+    constexpr int NTHR = UM_ROWS * NH;
+    const int N = m.N, W = b.warmup;
+    const bool want_post = (flags & TEHMM_BWD_POSTERIORS) != 0 && post != nullptr;
+    const bool want_map = (flags & TEHMM_BWD_MAP) != 0 && map_states != nullptr;
+    const bool renorm = (flags & TEHMM_BWD_RENORM_EPS) != 0;
+    const float eps32 = 1.1920928955078125e-07f;
+    const double renorm_inv = 1.0 / (1.0 + (double)N * 1.1920928955078125e-07);
+    const float renorm_invf = (float)renorm_inv;
+
+    // ---- transition matrix TRANSPOSED, hi / lo TF32 parts, canonical K-major layout: B[n = i][k = j] = A[i][j]
+    for (int e = tid; e < NP * NP; e += NTHR) {
+        const int n = e / NP, k = e % NP;
+        const double v = m.lin_trans[(int64_t)n * NP + k];
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"((float)v));
+        uint32_t l;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"((float)(v - (double)__uint_as_float(h))));
+        const uint32_t off = (uint32_t)((k >> 2) * (NP * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 3) * 4);
+        *reinterpret_cast<uint32_t *>(gbase + OFF_MAT + off) = h;
+        *reinterpret_cast<uint32_t *>(gbase + OFF_MAT + BMAT + off) = l;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < UM_NLD + UM_NA + 1; ++i) um_mbar_init(bars + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_d = tmem, t_hi = tmem + NP, t_lo = tmem + 2 * NP;
+    const uint32_t my_lane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t bar_a0 = bars + 8 * UM_NLD, bar_mma = bars + 8 * (UM_NLD + UM_NA);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((uint32_t)NP >> 3) << 17) | ((128u >> 4) << 24);
+
+    uint32_t mma_phase = 0, b_phase = 0, a_phase = 0;
+    volatile int *vfault = fault;
+    for (int64_t tile = blockIdx.x; tile * UM_ROWS < b.nchunks; tile += gridDim.x) {
+        const int64_t c = tile * UM_ROWS + row;
+        const bool valid = c < b.nchunks;
+        const TehmmChunk ch = b.chunks[valid ? c : b.nchunks - 1];
+        const int64_t rem = ch.s1 - ch.t1;                        // steps of the sequence to the right of the chunk
+        const bool succ = valid && rem > 0;
+        const bool exact = valid && rem <= (int64_t)W;            // beta_{T-1} = 1 is within reach (_hmm.pyx:179)
+        const int len = valid ? (int)(ch.t1 - ch.t0) : 0;
+        const int ks = exact ? W - (int)rem : 0, ke = W + len;
+        const bool own_boxed = valid && c < nfull;                // its own rows travel in the boxes
+        const bool warm_boxed = valid && c + 1 < nfull;           // and so do the warm-up rows (chunk c + 1)
+        const int kmax = W + lf;
+        const int c0 = (int)(tile * UM_ROWS);
+        const int64_t trow = ch.t1 - 1 + W;                       // time of clock 0
+        const float *bclk0 = blin + trow * LDS_ + 32 * hh;
+        const float *aclk0 = alpha + trow * LDS_ + 32 * hh;
+        float *pclk0 = want_post ? post + trow * LDS_ + 32 * hh : nullptr;
+        uint8_t *mclk0 = want_map ? map_states + trow : nullptr;
+        double mapsum = 0.0;
+
+        auto issue_b = [&](int j) {                               // thread 0: b rows of clock j
+            const uint32_t bar = bars + 8 * (j % UM_NLD);
+            um_mbar_expect_tx(bar, UMBLK);
+#pragma unroll
+            for (int h2 = 0; h2 < NH; ++h2)
+                um_tensor_load3(bbuf + (j % UM_NLD) * UMBLK + h2 * UMBOX, &tmap_b, 32 * h2, j < W ? W - 1 - j : lf - 1 - (j - W),
+                                j < W ? c0 + 1 : c0, bar);
+        };
+        auto issue_a = [&](int ja) {                              // thread 0: alpha rows of clock W + ja
+            const uint32_t bar = bar_a0 + 8 * (ja % UM_NA);
+            um_mbar_expect_tx(bar, UMBLK);
+#pragma unroll
+            for (int h2 = 0; h2 < NH; ++h2)
+                um_tensor_load3(abuf + (ja % UM_NA) * UMBLK + h2 * UMBOX, &tmap_a, 32 * h2, lf - 1 - ja, c0, bar);
+        };
+        if (tid == 0) {
+            for (int j = 0; j < UM_NLD && j < kmax; ++j) issue_b(j);
+            for (int ja = 0; ja < UM_NA && ja < lf; ++ja) issue_a(ja);
+        }
+
+        uint32_t xh[32], xl[32];
+        {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                xh[i] = (valid && !exact && 32 * hh + i < N) ? __float_as_uint(1.f) : 0u;     // speculate from a flat vector
+                xl[i] = 0u;
+            }
+            um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
+            um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        float scp = 1.f;
+
+        auto issue_mma = [&]() {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            constexpr uint32_t LBO = NP * 16, KSTEP = 2 * LBO;
+#pragma unroll
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_lo + kk * 8, um_smem_desc(bhi + kk * KSTEP, LBO, 128), idesc, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(blo + kk * KSTEP, LBO, 128), idesc, 1);
+#pragma unroll
+            for (int kk = 0; kk < NP / 8; ++kk)
+                um_mma_tf32_ts(t_d, t_hi + kk * 8, um_smem_desc(bhi + kk * KSTEP, LBO, 128), idesc, 1);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_mma) : "memory");
+        };
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) issue_mma();
+
+        for (int k = 0; k < kmax; ++k) {
+            const bool warm = k < W;
+            const int ja = k - W;
+            const uint32_t lb = bbuf + (k % UM_NLD) * UMBLK + hh * UMBOX;
+            const uint32_t ab = abuf + ((ja < 0 ? 0 : ja) % UM_NA) * UMBLK + hh * UMBOX;
+            um_mbar_wait(bars + 8 * (k % UM_NLD), (b_phase >> (k % UM_NLD)) & 1u, vfault);
+            b_phase ^= 1u << (k % UM_NLD);
+            if (!warm) {
+                um_mbar_wait(bar_a0 + 8 * (ja % UM_NA), (a_phase >> (ja % UM_NA)) & 1u, vfault);
+                a_phase ^= 1u << (ja % UM_NA);
+            }
+            const uint32_t line = (uint32_t)row;
+            const bool on = valid && k >= ks && k < ke;
+            const bool start_here = exact && k == ks;
+            const bool boxed = warm ? warm_boxed : own_boxed;
+            const int par = k & 1;
+            float bt[32];
+            if (boxed) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(bt[4 * q]), "=f"(bt[4 * q + 1]), "=f"(bt[4 * q + 2]), "=f"(bt[4 * q + 3])
+                                 : "r"(lb + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = on ? *reinterpret_cast<const float4 *>(bclk0 - (int64_t)k * LDS_ + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bt[4 * q] = v.x; bt[4 * q + 1] = v.y; bt[4 * q + 2] = v.z; bt[4 * q + 3] = v.w;
+                }
+            }
+            um_mbar_wait(bar_mma, mma_phase, vfault);
+            mma_phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t dv[32];
+            um_tmem_ld32(t_d + 32 * hh + my_lane, dv);            // beta'_t, this thread's half of the row
+            if (start_here) {                                     // the sequence's last step: beta = 1
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dv[i] = 32 * hh + i < N ? __float_as_uint(1.f) : 0u;
+            }
+            const float scn = start_here ? 1.f : scp;
+            const u64 sc2 = pk2(scn, scn);
+            u64 a2[16];
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const u64 d2 = ((u64)dv[2 * i + 1] << 32) | (u64)dv[2 * i];
+                a2[i] = um_fmul2(d2, um_fmul2(pk2(bt[2 * i], bt[2 * i + 1]), sc2));
+                if (i & 1) m1 = fmax3(m1, lo2(a2[i]), hi2(a2[i])); else m0 = fmax3(m0, lo2(a2[i]), hi2(a2[i]));
+            }
+            float mx = fmaxf(m0, m1);
+            if (!valid || k < ks) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a2[i] = 0ull;
+                mx = 0.f;
+            }
+            {
+                const u64 neg1 = pk2(-1.f, -1.f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const u64 h2 = a2[i] & 0xffffe000ffffe000ull;
+                    const u64 l2 = ffma2(h2, neg1, a2[i]);
+                    xh[2 * i] = (uint32_t)h2; xh[2 * i + 1] = (uint32_t)(h2 >> 32);
+                    xl[2 * i] = (uint32_t)l2; xl[2 * i + 1] = (uint32_t)(l2 >> 32);
+                }
+                um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
+                um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
+            }
+            if (NH == 2) mxs[(par * NH + hh) * UM_ROWS + row] = mx;
+            // chunk boundary vectors (beta' itself, any scale: the verification is ratio based)
+            if (k == W - 1 && succ && k >= ks) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4 *>(start_vec + c * NP + 32 * hh + 4 * q) = make_uint4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+            }
+            if (valid && k + 1 == ke) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<uint4 *>(end_vec + c * NP + 32 * hh + 4 * q) = make_uint4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+            }
+            // products with alpha_t: this half's share of Z, its best state
+            float p[32];
+            float zown = 0.f, bown = 0.f;
+            int iown = 99;
+            const bool outp = valid && !warm && k < ke;
+            if (!warm) {
+                float at[32];
+                if (own_boxed) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(at[4 * q]), "=f"(at[4 * q + 1]), "=f"(at[4 * q + 2]), "=f"(at[4 * q + 3])
+                                     : "r"(ab + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = outp ? *reinterpret_cast<const float4 *>(aclk0 - (int64_t)k * LDS_ + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        at[4 * q] = v.x; at[4 * q + 1] = v.y; at[4 * q + 2] = v.z; at[4 * q + 3] = v.w;
+                    }
+                }
+                float z0 = 0.f, z1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    p[i] = __uint_as_float(dv[i]) * at[i];
+                    p[i + 1] = __uint_as_float(dv[i + 1]) * at[i + 1];
+                    z0 += p[i]; z1 += p[i + 1];
+                    if (i & 2) b1 = fmax3(b1, p[i], p[i + 1]); else b0 = fmax3(b0, p[i], p[i + 1]);
+                }
+                const float best = fmaxf(b0, b1);
+                int idx = 99;
+                if (want_map) {
+#pragma unroll
+                    for (int i = 31; i >= 0; --i)
+                        if (p[i] == best) idx = 32 * hh + i;       // lowest state among the maxima (np.argmax, basehmm.py:357)
+                }
+                if (NH == 2) {
+                    zs[(par * NH + hh) * UM_ROWS + row] = z0 + z1;
+                    bests[(par * NH + hh) * UM_ROWS + row] = best;
+                    idxs[(par * NH + hh) * UM_ROWS + row] = idx;
+                }
+                zown = z0 + z1; bown = best; iown = idx;
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (NH == 2) mx = fmaxf(mx, mxs[(par * NH + (hh ^ 1)) * UM_ROWS + row]);
+            {
+                const unsigned mb = __float_as_uint(mx);
+                scp = __uint_as_float(0x7f000000u - (mb & 0x7f800000u));
+            }
+            if (tid == 0 && k + 1 < kmax) issue_mma();
+            if (!warm) {
+                int idx = iown;
+                float Z = zown, best = bown;
+                if (NH == 2) {
+                    const float zo = zs[(par * NH + (hh ^ 1)) * UM_ROWS + row];
+                    const float bo = bests[(par * NH + (hh ^ 1)) * UM_ROWS + row];
+                    const int io = idxs[(par * NH + (hh ^ 1)) * UM_ROWS + row];
+                    Z = hh == 0 ? Z + zo : zo + Z;                // the same sum in both halves
+                    if (bo > best || (bo == best && io < idx)) { best = bo; idx = io; }
+                }
+                const float invZ = __frcp_rn(Z);
+                if (want_map && hh == 0 && outp) {
+                    mclk0[-(int64_t)k] = (uint8_t)(idx < N ? idx : 0);
+                    const float bg = best * invZ;
+                    mapsum += renorm ? ((double)bg + (double)eps32) * renorm_inv : (double)bg;
+                }
+                if (want_post) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] *= invZ;
+                        if (renorm) p[i] = 32 * hh + i < N ? (p[i] + eps32) * renorm_invf : 0.f;      // padding stays zero
+                    }
+                    if (own_boxed) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};"
+                                         :: "r"(ab + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)),
+                                            "f"(p[4 * q]), "f"(p[4 * q + 1]), "f"(p[4 * q + 2]), "f"(p[4 * q + 3]) : "memory");
+                    } else if (outp) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4 *>(pclk0 - (int64_t)k * LDS_ + 4 * q) = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // posterior rows -> TMA store (behind the next barrier)
+                }
+            }
+            if (tid == 0) {
+                if (k + UM_NLD < kmax) issue_b(k + UM_NLD);      // every thread has read this clock's b rows before the barrier
+                if (!warm) {
+                    if (want_post) {
+                        if (ja >= 1) {
+                            if (ja >= 2) {
+                                // the store of clock ja - 2 (issued a whole clock ago) has read its buffer: reload it
+                                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                                if (ja + 1 < lf) issue_a(ja + 1);
+                            }
+#pragma unroll
+                            for (int h2 = 0; h2 < NH; ++h2)
+                                um_tensor_store3(&tmap_p, 32 * h2, lf - ja, c0, abuf + ((ja - 1) % UM_NA) * UMBLK + h2 * UMBOX);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    } else if (ja + UM_NA < lf) {
+                        issue_a(ja + UM_NA);                      // nothing overwrites the alpha rows: reload at once
+                    }
+                }
+            }
+        }
+        if (want_post) {
+            __syncthreads();                                       // the last clock's rows are in shared memory
+            if (tid == 0) {
+#pragma unroll
+                for (int h2 = 0; h2 < NH; ++h2)
+                    um_tensor_store3(&tmap_p, 32 * h2, 0, c0, abuf + ((lf - 1) % UM_NA) * UMBLK + h2 * UMBOX);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            }
+        }
+        if (want_map && hh == 0 && valid) map_part[c] = mapsum;
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(C::TMEM_COLS) : "memory");
+}
+
+bool tehmm_backward_umma_ok(const TehmmModelDev &m, const TehmmBatchDev &b, int flags, int mode, int64_t fine_len)
+{
+    return m.NS == 2 && m.LD == 64 && b.nseq == 1 && mode == 0 && !(flags & TEHMM_BWD_TRANS) && fine_len >= b.warmup &&
+           b.total / fine_len >= 1;
+}
+
+cudaError_t tehmm_launch_backward_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b, int flags,
+                                       const float *blin, const float *alpha, float *post, uint8_t *map_states,
+                                       double *map_part, float *start_vec, float *end_vec, int sms,
+                                       int64_t fine_len, int *fault)
+{
+    typedef UmBwdCfg<2> C;
+    CUtensorMap tb, ta, tp;
+    memset(&tb, 0, sizeof tb);
+    memset(&ta, 0, sizeof ta);
+    memset(&tp, 0, sizeof tp);
+    const int64_t nfull = b.total / fine_len;
+    const bool want_post = (flags & TEHMM_BWD_POSTERIORS) != 0 && post != nullptr;
+    if (!um_make_tmap(&tb, blin, fine_len, nfull, 2, 1) || !um_make_tmap(&ta, alpha, fine_len, nfull, 2, 1) ||
+        (want_post && !um_make_tmap(&tp, post, fine_len, nfull, 2, 1)))
+        return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(bwd_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (b.nchunks + UM_ROWS - 1) / UM_ROWS;
+    const int grid = (int)(tiles < (int64_t)sms ? tiles : (int64_t)sms);
+    bwd_umma_kernel<2><<<grid, UM_ROWS * 2, C::SMEM, st>>>(m, b, flags, blin, alpha, post, map_states, map_part, start_vec, end_vec,
+                                                        tb, ta, tp, (int)fine_len, (int)nfull, fault);
+    return cudaGetLastError();
+}
+
 cudaError_t tehmm_launch_forward_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                       const float *blin, const double *rowmax, float *alpha,
                                       float *start_vec, float *end_vec, double *cscale, int sms,

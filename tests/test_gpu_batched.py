@@ -490,15 +490,15 @@ def test_forward_tcgen05_kernel_matches(oracle):
     assert np.mean(out["map_states"][0] == base["map_states"][0]) > 0.9999
 
 
-@pytest.mark.parametrize("N", [33, 50, 64])
-def test_forward_tcgen05_kernel_is_the_default_for_33_to_64_states(oracle, N):
-    """fwd_umma_kernel<2> (csrc/umma.cu; option "umma64", default on): the forward pass of a single-sequence
-    batch of 33..64 states on tcgen05.mma M128 N64 K8 with two threads per chunk.  Same log-likelihood,
-    posteriors and MAP path as the oracle and as the one-chunk-per-warp kernel, with a ragged last chunk
-    outside the boxes; multi-sequence batches stay on the one-chunk-per-warp kernel."""
+@pytest.mark.parametrize("N,T", [(33, 60_011), (50, 60_000), (50, 60_100), (64, 45_020)])
+def test_tcgen05_kernels_are_the_default_for_33_to_64_states(oracle, N, T):
+    """fwd_umma_kernel<2> and its backward twin bwd_umma_kernel<2> (csrc/umma.cu; option "umma64", default on):
+    the forward pass and the backward / posterior / MAP pass of a single-sequence batch of 33..64 states on
+    tcgen05.mma M128 N64 K8 with two threads per chunk.  Same log-likelihood, posteriors and MAP path as the
+    oracle and as the one-chunk-per-warp kernels -- with no ragged last chunk (60 000 = 400 x 150), one shorter
+    than the warm-up (11, 20 steps) and one longer (100); multi-sequence batches stay on the generic kernels."""
     from tehmm_b200 import synth
     m = synth.make_model(N=N, seed=41)
-    T = 60_011
     obs, _ = synth.sample_obs(m, T, seed=42)
     ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
     eng = engine(fine_len=150)
@@ -506,18 +506,29 @@ def test_forward_tcgen05_kernel_is_the_default_for_33_to_64_states(oracle, N):
     eng.upload_batch([obs])
     before = eng.ctx.stat("umma_passes")
     out = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
-    assert eng.ctx.stat("umma_passes") == before + 1
+    assert eng.ctx.stat("umma_passes") == before + 2             # forward and backward
+    only_map = eng.posteriors(renorm_eps=False, want_post=False, want_map=True, precision="f32")
+    assert eng.ctx.stat("umma_passes") == before + 4
+    eps = eng.posteriors(renorm_eps=True, want_map=True, precision="f32")
     eng.ctx.set_option("umma64", 0)
     try:
         base = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
+        base_eps = eng.posteriors(renorm_eps=True, want_map=True, precision="f32")
     finally:
         eng.ctx.set_option("umma64", 1)
-    assert eng.ctx.stat("umma_passes") == before + 1
+    assert eng.ctx.stat("umma_passes") == before + 6
+    assert eng.ctx.stat("repair_passes_backward") == 0
     assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
     assert_allclose(out["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
     assert out["logprob"][0] == pytest.approx(base["logprob"][0], rel=1e-7)
     assert_map_near_ties_only(out["map_states"][0], ref["post"], label="tcgen05 N=%d" % N)
-    # two sequences: not a regular [chunk][step][64] array, the tcgen05 kernel does not apply
+    assert np.array_equal(only_map["map_states"][0], out["map_states"][0])
+    assert_allclose(eps["post"][0], base_eps["post"][0], rtol=TOL["f32"], atol=ATOL["f32"])
+    for key in ("map_score", "map_logprob"):
+        if key in out:
+            assert_allclose(np.asarray(out[key]), np.asarray(base[key]), rtol=1e-6)
+            assert_allclose(np.asarray(eps[key]), np.asarray(base_eps[key]), rtol=1e-6)
+    # two sequences: not a regular [chunk][step][64] array, the tcgen05 kernels do not apply
     eng.upload_batch([obs[:20_000], obs[20_000:]])
     eng.posteriors(renorm_eps=False, want_post=False, want_map=True, precision="f32")
-    assert eng.ctx.stat("umma_passes") == before + 1
+    assert eng.ctx.stat("umma_passes") == before + 6

@@ -17,6 +17,7 @@ for N in (50, 64, 33):
     prec, tdt = eng._prec("f32")
     _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
     res = {}
+    bres = {}
     for opt in (1, 0):
         ctx.set_option("umma64", opt)
         for _ in range(2):
@@ -27,8 +28,19 @@ for N in (50, 64, 33):
             alpha, lp = ctx.optimistic(lambda: eng.run_forward(prec, tdt, blin, rowmax, None))
         torch.cuda.synchronize()
         res[opt] = (ctx.stat("us_forward"), float(lp[0].item()), ctx.stat("umma_passes"), ctx.stat("repaired_chunks_forward"))
+        # backward twin: MAP only, and posteriors + MAP
+        for fl in (2, 3):
+            for _ in range(3):
+                outs = ctx.optimistic(lambda: eng.run_backward(prec, tdt, fl, blin, alpha, None))
+            torch.cuda.synchronize()
+            bres.setdefault(opt, {})[fl] = (ctx.stat("us_backward"), outs[1].cpu().numpy() if outs[1] is not None else None)
+            del outs
         ctx.set_option("timing", 0)
     ctx.set_option("umma64", 1)
     print(json.dumps({"N": N, "T": T, "tcgen05_us": res[1][0], "warp_kernel_us": res[0][0], "logprob_tcgen05": res[1][1],
                       "logprob_warp": res[0][1], "rel_diff": abs(res[1][1] - res[0][1]) / abs(res[0][1]),
-                      "umma_passes": res[1][2], "repaired": res[1][3]}), flush=True)
+                      "umma_passes": res[1][2], "repaired": res[1][3],
+                      "bwd_map_tcgen05_us": bres[1][2][0], "bwd_map_warp_us": bres[0][2][0],
+                      "bwd_post_map_tcgen05_us": bres[1][3][0], "bwd_post_map_warp_us": bres[0][3][0],
+                      "map_agreement": float(np.mean(bres[1][2][1] == bres[0][2][1])),
+                      "repaired_backward": ctx.stat("repaired_chunks_backward")}), flush=True)
