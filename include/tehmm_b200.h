@@ -96,9 +96,10 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
  * chunk of the fine partition, 0 = auto), "umma" (1 = forward pass of a
  * single-sequence batch of <= 32 states by the tcgen05 / tensor-memory kernel of
  * csrc/umma.cu; same results, not faster than the mma.sync kernel there),
- * "umma64" (default 1: the same kernel, 64 columns, IS the forward pass of
- * single-sequence batches of 33..64 states; 0 = one chunk per warp; stat
- * "umma_passes" counts the launches of either), "xi_tile" (0 = expected transition
+ * "umma64" (default 1: the same kernel, 64 columns, and its backward twin ARE the
+ * forward and the backward / posterior / MAP pass of single-sequence batches of
+ * 33..64 states; 0 = one chunk per warp; stat "umma_passes" counts the launches
+ * of any of them), "xi_tile" (0 = expected transition
  * counts by the one-chunk-per-warp backward kernel instead of the tensor-core
  * xi kernel), "timing" (1 = bracket the first
  * launch of each main kernel with CUDA events on the context's stream), "defer" (see
