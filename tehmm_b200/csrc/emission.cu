@@ -434,11 +434,12 @@ static cudaError_t launch_emg(cudaStream_t st, const TehmmModelDev &m, const Teh
 
 static size_t em4_smem_bytes(const TehmmModelDev &m)
 {
-    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
+    const size_t head = ((size_t)m.grows * (128 * m.NS + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + m.K) * 4 + 15) & ~(size_t)15;
     return head + (size_t)EM4_WARPS * EM4_ROWS * 8 * 4;
 }
 
-template <typename OBS, int GT, bool RATIO>
+// NS = 2 (33..64 states, lattice rows of 64 floats; round 2): a row belongs to SIXTEEN lanes, two rows per pass.
+template <typename OBS, int GT, bool RATIO, int NS>
 __global__ void __launch_bounds__(EM4_WARPS * 32, 1)
 emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t total,
                         const double *__restrict__ ratios, float *__restrict__ elog,
@@ -453,19 +454,21 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
     const int K = m.K, N = m.N;
     // layout: gtab | gc | gdesc | nsym | per warp offs[32][8]
     float *tab_s = reinterpret_cast<float *>(em_smem);
-    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * 32);
+    constexpr int NP = 32 * NS, LPR = 8 * NS, RPP = 32 / LPR;      // columns, lanes per row, rows per pass
+    constexpr int ROWB = 128 * NS;                                  // bytes of a merged table row
+    double *gc_s = reinterpret_cast<double *>(tab_s + (size_t)m.grows * NP);
     int32_t *gd_s = reinterpret_cast<int32_t *>(gc_s + m.grows);
     int32_t *nsym_s = gd_s + TEHMM_GMAX * TEHMM_GDESC;
-    const size_t head = ((size_t)m.grows * (128 + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
+    const size_t head = ((size_t)m.grows * (ROWB + 8) + (size_t)(TEHMM_GMAX * TEHMM_GDESC + K) * 4 + 15) & ~(size_t)15;
     int32_t *offs = reinterpret_cast<int32_t *>(em_smem + head) + (size_t)warp * EM4_ROWS * 8;
 
-    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * 32; e += blockDim.x) tab_s[e] = m.gtab[e];
+    for (int64_t e = threadIdx.x; e < (int64_t)m.grows * NP; e += blockDim.x) tab_s[e] = m.gtab[e];
     for (int e = threadIdx.x; e < m.grows; e += blockDim.x) gc_s[e] = m.gc[e];
     for (int e = threadIdx.x; e < GT * TEHMM_GDESC; e += blockDim.x) gd_s[e] = m.gdesc[e];
     for (int e = threadIdx.x; e < K; e += blockDim.x) nsym_s[e] = m.track_nsym[e];
     __syncthreads();
 
-    const int q = lane >> 3, c = lane & 7;
+    const int q = lane / LPR, c = lane % LPR;
     const uint32_t lane_tab = (uint32_t)__cvta_generic_to_shared(tab_s) + (uint32_t)c * 16u;
     const uint32_t offs_a = (uint32_t)__cvta_generic_to_shared(offs);
     // pm[i]: -inf for a real state (max(d, -inf) = d), 0 for a padding column (max(-inf, 0) = 0)
@@ -497,7 +500,7 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
                     idx += sym * d[6 + i];
                 }
                 if (bad) idx = 0;
-                offs[lane * 8 + gq] = idx * 128;
+                offs[lane * 8 + gq] = idx * ROWB;
                 csum += gc_s[idx];
             }
         }
@@ -506,8 +509,8 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
         float mf_keep = 0.f;                     // lane r keeps the state maximum of row r
         if (!any_slow) {
 #pragma unroll 2
-            for (int p = 0; p < EM4_ROWS / 4; ++p) {
-                const int r = 4 * p + q;
+            for (int p = 0; p < EM4_ROWS / RPP; ++p) {
+                const int r = RPP * p + q;
                 int o[8];
                 asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(o[0]), "=r"(o[1]), "=r"(o[2]), "=r"(o[3]) : "r"(offs_a + r * 32));
                 if (GT > 4)
@@ -523,6 +526,7 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
                 mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 1));
                 mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 2));
                 mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 4));
+                if (NS == 2) mx = fmaxf(mx, __shfl_xor_sync(TEHMM_FULL, mx, 8));
                 const float rf = RATIO ? (float)ratios[min(tb + r, total - 1)] : 1.f;
                 float d[4], bl[4];
                 if (__builtin_expect(__any_sync(TEHMM_FULL, !(mx > -INFINITY)), 0)) {
@@ -544,28 +548,36 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
                     }
                 }
                 if (r < rows) {
-                    const int64_t o4 = (tb + r) * 32 + 4 * c;
+                    const int64_t o4 = (tb + r) * NP + 4 * c;
                     if (elog) *reinterpret_cast<float4 *>(elog + o4) = make_float4(d[0], d[1], d[2], d[3]);
                     if (blin) *reinterpret_cast<float4 *>(blin + o4) = make_float4(bl[0], bl[1], bl[2], bl[3]);
                 }
-                const float mm = __shfl_sync(TEHMM_FULL, mx, (lane & 3) * 8);
-                if ((lane >> 2) == p) mf_keep = mm;
+                const float mm = __shfl_sync(TEHMM_FULL, mx, (lane % RPP) * LPR);      // lane r keeps row r
+                if (lane / RPP == p) mf_keep = mm;
             }
         } else {
             // a symbol outside its track's table: index the dense float64 table exactly as the
             // reference does (rare); lane = state
             for (int r = 0; r < rows; ++r) {
-                double v = 0.0;
-                if (lane < N)
-                    for (int k = 0; k < K; ++k) v += m.table[((int64_t)k * N + lane) * m.S + (int64_t)obs[(tb + r) * K + k]];
-                v *= m.normalize;
-                const double M = warp_max(lane < N ? v : -INFINITY);
-                float d = M > -INFINITY ? (float)(v - M) : 0.f;
-                if (RATIO) d *= (float)ratios[tb + r];
-                float bl = __expf(d);
-                if (lane >= N) { d = 0.f; bl = 0.f; }
-                if (elog) elog[(tb + r) * 32 + lane] = d;
-                if (blin) blin[(tb + r) * 32 + lane] = bl;
+                double v[NS], vm = -INFINITY;
+#pragma unroll
+                for (int s2 = 0; s2 < NS; ++s2) {
+                    v[s2] = 0.0;
+                    if (lane + 32 * s2 < N)
+                        for (int k = 0; k < K; ++k) v[s2] += m.table[((int64_t)k * N + lane + 32 * s2) * m.S + (int64_t)obs[(tb + r) * K + k]];
+                    v[s2] *= m.normalize;
+                    if (lane + 32 * s2 < N) vm = fmax(vm, v[s2]);
+                }
+                const double M = warp_max(vm);
+#pragma unroll
+                for (int s2 = 0; s2 < NS; ++s2) {
+                    float d = M > -INFINITY ? (float)(v[s2] - M) : 0.f;
+                    if (RATIO) d *= (float)ratios[tb + r];
+                    float bl = __expf(d);
+                    if (lane + 32 * s2 >= N) { d = 0.f; bl = 0.f; }
+                    if (elog) elog[(tb + r) * NP + lane + 32 * s2] = d;
+                    if (blin) blin[(tb + r) * NP + lane + 32 * s2] = bl;
+                }
                 if (lane == r) { mf_keep = 0.f; csum = M; }
             }
         }
@@ -579,18 +591,18 @@ emission_merged4_kernel(TehmmModelDev m, const OBS *__restrict__ obs, int64_t to
     }
 }
 
-template <typename OBS, int GT, bool RATIO>
+template <typename OBS, int GT, bool RATIO, int NS>
 static cudaError_t launch_em4_3(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                 const double *ratios, float *elog, float *blin, double *rowmax,
                                 int *seq_flag, int sms, int64_t row0, int64_t row1)
 {
     const size_t smem = em4_smem_bytes(m);
-    cudaError_t e = cudaFuncSetAttribute(emission_merged4_kernel<OBS, GT, RATIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(emission_merged4_kernel<OBS, GT, RATIO, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t need = ((row1 - row0 + EM4_ROWS - 1) / EM4_ROWS + EM4_WARPS - 1) / EM4_WARPS;
     if (need < 1) need = 1;
     const int grid = (int)(need < sms ? need : sms);
-    emission_merged4_kernel<OBS, GT, RATIO><<<grid, EM4_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, row1, ratios, elog, blin,
+    emission_merged4_kernel<OBS, GT, RATIO, NS><<<grid, EM4_WARPS * 32, smem, st>>>(m, (const OBS *)b.obs, row1, ratios, elog, blin,
                                                                                 rowmax, seq_flag, b.seq_off, b.nseq, row0);
     return cudaGetLastError();
 }
@@ -600,8 +612,9 @@ static cudaError_t launch_em4(cudaStream_t st, const TehmmModelDev &m, const Teh
                               const double *ratios, float *elog, float *blin, double *rowmax,
                               int *seq_flag, int sms, int64_t row0, int64_t row1)
 {
-#define EM4_GO(GT) (ratios ? launch_em4_3<OBS, GT, true>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1) \
-                           : launch_em4_3<OBS, GT, false>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1))
+#define EM4_GO1(GT, NS_) (ratios ? launch_em4_3<OBS, GT, true, NS_>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1) \
+                                 : launch_em4_3<OBS, GT, false, NS_>(st, m, b, ratios, elog, blin, rowmax, seq_flag, sms, row0, row1))
+#define EM4_GO(GT) (m.NS == 1 ? EM4_GO1(GT, 1) : EM4_GO1(GT, 2))
     switch (m.G) {
     case 1: return EM4_GO(1);
     case 2: return EM4_GO(2);
@@ -613,6 +626,7 @@ static cudaError_t launch_em4(cudaStream_t st, const TehmmModelDev &m, const Teh
     default: return EM4_GO(8);
     }
 #undef EM4_GO
+#undef EM4_GO1
 }
 
 // _emission.pyx:59,73-80: the running maximum is never reset, so rows are
@@ -702,7 +716,7 @@ static cudaError_t launch_em_obs(cudaStream_t st, const TehmmModelDev &m, const 
 bool tehmm_emission_rows_ok(const TehmmModelDev &m, int prec, const double *ratios)
 {
     (void)ratios;
-    return prec == TEHMM_F32 && m.G > 0 && m.G <= 8 && m.LD == 32 && em4_smem_bytes(m) <= 227 * 1024;
+    return prec == TEHMM_F32 && m.G > 0 && m.G <= 8 && m.LD == 32 * m.NS && em4_smem_bytes(m) <= 227 * 1024;
 }
 
 // rows [row0, row1) of the batch; pieces must come in increasing order, the first one starting at
@@ -720,7 +734,7 @@ int tehmm_launch_emission(cudaStream_t st, const TehmmModelDev &m, const TehmmBa
         else if (prec == TEHMM_F32 && m.G > 0 && emg_smem_bytes(m) <= 227 * 1024) {
             // out-of-range symbols in the slow branch index the dense table: obs must be < S there too,
             // exactly the generic kernel's contract
-            if (m.LD == 32 && m.G <= 8 && em4_smem_bytes(m) <= 227 * 1024) {
+            if (m.LD == 32 * m.NS && m.G <= 8 && em4_smem_bytes(m) <= 227 * 1024) {
                 if (b.obs_bytes == 1) e = launch_em4<uint8_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);
                 else if (b.obs_bytes == 2) e = launch_em4<uint16_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);
                 else e = launch_em4<int32_t>(st, m, b, ratios, (float *)elog, (float *)blin, rowmax, seq_flag, sms, row0, row1);

@@ -504,7 +504,7 @@ def test_tcgen05_kernels_are_the_default_for_33_to_64_states(oracle, N, T):
     eng = engine(fine_len=150)
     eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
     eng.upload_batch([obs])
-    before = eng.ctx.stat("umma_passes")
+    before, repairs = eng.ctx.stat("umma_passes"), eng.ctx.stat("repair_passes_backward")
     out = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
     assert eng.ctx.stat("umma_passes") == before + 2             # forward and backward
     only_map = eng.posteriors(renorm_eps=False, want_post=False, want_map=True, precision="f32")
@@ -517,7 +517,7 @@ def test_tcgen05_kernels_are_the_default_for_33_to_64_states(oracle, N, T):
     finally:
         eng.ctx.set_option("umma64", 1)
     assert eng.ctx.stat("umma_passes") == before + 6
-    assert eng.ctx.stat("repair_passes_backward") == 0
+    assert eng.ctx.stat("repair_passes_backward") == repairs
     assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
     assert_allclose(out["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
     assert out["logprob"][0] == pytest.approx(base["logprob"][0], rel=1e-7)

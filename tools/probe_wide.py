@@ -16,6 +16,13 @@ for N in (50, 64, 33):
     eng.upload_batch([obs])
     prec, tdt = eng._prec("f32")
     _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
+    torch.cuda.synchronize()
+    ctx.set_option("timing", 1)
+    for _ in range(3):
+        _, blin, rowmax = eng.run_emission(prec, tdt, None, False, True)
+    torch.cuda.synchronize()
+    us_em = ctx.stat("us_emission")
+    ctx.set_option("timing", 0)
     res = {}
     bres = {}
     for opt in (1, 0):
@@ -37,7 +44,7 @@ for N in (50, 64, 33):
             del outs
         ctx.set_option("timing", 0)
     ctx.set_option("umma64", 1)
-    print(json.dumps({"N": N, "T": T, "tcgen05_us": res[1][0], "warp_kernel_us": res[0][0], "logprob_tcgen05": res[1][1],
+    print(json.dumps({"N": N, "T": T, "emission_us": us_em, "tcgen05_us": res[1][0], "warp_kernel_us": res[0][0], "logprob_tcgen05": res[1][1],
                       "logprob_warp": res[0][1], "rel_diff": abs(res[1][1] - res[0][1]) / abs(res[0][1]),
                       "umma_passes": res[1][2], "repaired": res[1][3],
                       "bwd_map_tcgen05_us": bres[1][2][0], "bwd_map_warp_us": bres[0][2][0],
