@@ -588,6 +588,7 @@ vit_traceback_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ lat
 // (ties: lowest state, as _hmm.pyx:232-247).  ~11 issue slots per chunk step.
 #define TB4_PF 8     // delta rows in flight per chunk
 
+template <int NS>
 __device__ __forceinline__ int tb4_argmax(float c0, float c1, float c2, float c3, int u, unsigned segshift, int lane0)
 {
     const unsigned b0 = __float_as_uint(c0), b1 = __float_as_uint(c1), b2 = __float_as_uint(c2), b3 = __float_as_uint(c3);
@@ -599,14 +600,16 @@ __device__ __forceinline__ int tb4_argmax(float c0, float c1, float c2, float c3
     mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 1));
     mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 2));
     mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 4));
+    if (NS == 2) mg = min(mg, __shfl_xor_sync(TEHMM_FULL, mg, 8));
     const unsigned vote = __ballot_sync(TEHMM_FULL, ml == mg);
-    const int ulo = __ffs((vote >> segshift) & 0xffu) - 1;
+    const int ulo = __ffs((vote >> segshift) & ((1u << (8 * NS)) - 1u)) - 1;
     return __shfl_sync(TEHMM_FULL, 4 * u + il, lane0 + ulo);
 }
 
 // RATIO: the from-state-0 candidate carries the reference's extra term (see viterbi_lean_kernel); the term
 // common to all from-states does not move the arg-max.
-template <bool RATIO>
+// NS = 2 (33..64 states, lattice rows of 64 floats; round 2): a chunk gets SIXTEEN lanes, two chunks per warp.
+template <bool RATIO, int NS>
 __global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, 4)
 vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ lattice,
                       uint8_t *__restrict__ states, int64_t *__restrict__ states64,
@@ -614,22 +617,23 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
                       const uint8_t *__restrict__ forced_end, const int *__restrict__ bad, int mode,
                       const double *__restrict__ ratios)
 {
-    __shared__ __align__(16) float AT[32 * 32];            // AT[s*32 + i] = min(logA[i][s], 0)
-    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
-        const int s = e >> 5, i = e & 31;
-        AT[e] = fminf((float)m.cut_trans[(int64_t)i * 32 + s], 0.f);
+    constexpr int NP = 32 * NS, LPC = 8 * NS, CPW = 32 / LPC;       // columns, lanes per chunk, chunks per warp
+    __shared__ __align__(16) float AT[NP * NP];            // AT[s*NP + i] = min(logA[i][s], 0)
+    for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
+        const int s = e / NP, i = e % NP;
+        AT[e] = fminf((float)m.cut_trans[(int64_t)i * NP + s], 0.f);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = lane >> 3, u = lane & 7;
-    const unsigned segshift = 8u * (unsigned)c;
-    const int lane0 = 8 * c;
+    const int c = lane / LPC, u = lane % LPC;
+    const unsigned segshift = (unsigned)(LPC * c);
+    const int lane0 = LPC * c;
     const uint32_t at_lane = (uint32_t)__cvta_generic_to_shared(AT) + (uint32_t)u * 16u;
     const float a00 = (float)m.cut_trans[0];
 
-    for (int64_t wg = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; wg * 4 < b.nchunks;
+    for (int64_t wg = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; wg * CPW < b.nchunks;
          wg += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
-        const int64_t ci = wg * 4 + c;
+        const int64_t ci = wg * CPW + c;
         bool valid = ci < b.nchunks;
         if (valid && mode == 1) valid = bad[ci] != 0;
         int row = 0, rlast = 0, st = 0;
@@ -645,10 +649,10 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
             else if (ch.t1 < ch.s1)                      // speculate: enter from `warmup` steps to the right
                 row = (int)min((int64_t)rlast + b.warmup, ch.s1 - 1 - tbase);
         }
-        const float *__restrict__ ll = lattice + tbase * 32 + 4 * u;
+        const float *__restrict__ ll = lattice + tbase * NP + 4 * u;
         {   // np.argmax of the row the walk starts from (not used by forced / invalid slots)
-            const float4 dv = *reinterpret_cast<const float4 *>(ll + (int64_t)row * 32);
-            const int s0 = tb4_argmax(dv.x, dv.y, dv.z, dv.w, u, segshift, lane0);
+            const float4 dv = *reinterpret_cast<const float4 *>(ll + (int64_t)row * NP);
+            const int s0 = tb4_argmax<NS>(dv.x, dv.y, dv.z, dv.w, u, segshift, lane0);
             if (valid && mode == 0) st = s0;
         }
         int spec = st;
@@ -657,7 +661,7 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
         const double *__restrict__ rr = RATIO ? ratios + tbase : nullptr;
 #pragma unroll
         for (int p = 0; p < TB4_PF; ++p) {
-            ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - p, 0) * 32);
+            ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - p, 0) * NP);
             rring[p] = RATIO ? (float)rr[max(row - p, 0)] : 1.f;
         }
         while (__any_sync(TEHMM_FULL, row >= 1)) {
@@ -671,19 +675,19 @@ vit_traceback4_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict_
                 }
                 const float4 dv = ring[p];
                 const float r = rring[p];
-                ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - TB4_PF, 0) * 32);
+                ring[p] = *reinterpret_cast<const float4 *>(ll + (int64_t)max(row - 1 - TB4_PF, 0) * NP);
                 if (RATIO) rring[p] = (float)rr[max(row - TB4_PF, 0)];
                 float4 a;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(at_lane + (uint32_t)st * 128u));
+                             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(at_lane + (uint32_t)st * (uint32_t)(NP * 4)));
                 if (RATIO) {
                     // candidate of from-state 0 (lane u = 0, first element): + logA_ss r - [r > 1] logA_ss (r - 1), - logA_00 for s = 0
-                    const float dgs = AT[st * 32 + st];
+                    const float dgs = AT[st * NP + st];
                     float extra0 = dgs > -INFINITY ? (r > 1.f ? dgs : dgs * r) : 0.f;
                     if (st == 0 && a00 > -INFINITY) extra0 -= a00;
                     if (u == 0) a.x += extra0;
                 }
-                const int sn = tb4_argmax(dv.x + a.x, dv.y + a.y, dv.z + a.z, dv.w + a.w, u, segshift, lane0);
+                const int sn = tb4_argmax<NS>(dv.x + a.x, dv.y + a.y, dv.z + a.z, dv.w + a.w, u, segshift, lane0);
                 if (act) { st = sn; row -= 1; }
             }
         }
@@ -842,13 +846,21 @@ cudaError_t tehmm_launch_traceback(cudaStream_t st, const TehmmModelDev &m, cons
                                    int mode, int grid)
 {
     if (prec == TEHMM_F32) {
-        if (m.NS == 1 && m.LD == 32) {
-            const int64_t need = ((b.nchunks + 3) / 4 + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
+        if (m.LD == 32 * m.NS) {
+            const int cpw = m.NS == 1 ? 4 : 2;
+            const int64_t need = ((b.nchunks + cpw - 1) / cpw + TEHMM_WARPS_PER_CTA - 1) / TEHMM_WARPS_PER_CTA;
             const int g4 = (int)(need < grid ? (need < 1 ? 1 : need) : grid);
-            if (ratios)
-                vit_traceback4_kernel<true><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, ratios);
-            else
-                vit_traceback4_kernel<false><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, nullptr);
+            if (m.NS == 1) {
+                if (ratios)
+                    vit_traceback4_kernel<true, 1><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, ratios);
+                else
+                    vit_traceback4_kernel<false, 1><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, nullptr);
+            } else {
+                if (ratios)
+                    vit_traceback4_kernel<true, 2><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, ratios);
+                else
+                    vit_traceback4_kernel<false, 2><<<g4, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, (const float *)lattice, states, states64, spec_end, pred, forced_end, bad, mode, nullptr);
+            }
             return cudaGetLastError();
         }
         if (m.NS == 1) return launch_tb<float, 1>(st, m, b, (const float *)lattice, ratios, states, states64, spec_end, pred, forced_end, bad, mode, grid);
