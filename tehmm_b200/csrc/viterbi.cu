@@ -32,15 +32,18 @@
 #define VIT_U 4
 #define TB_PF 6    // delta rows in flight ahead of the traceback walk
 
-template <typename T, int NS, bool RATIO>
-__global__ void __launch_bounds__(TEHMM_WARPS_PER_CTA * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
+#ifndef VIT_WIDE_WARPS
+#define VIT_WIDE_WARPS 12     // fp32, 33..64 states: warps per CTA (one CTA per SM; <= 168 registers)
+#endif
+template <typename T, int NS, bool RATIO, int WARPS = TEHMM_WARPS_PER_CTA>
+__global__ void __launch_bounds__(WARPS * 32, (sizeof(T) == 4 && NS == 1) ? 3 : 1)
 viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
                const double *__restrict__ ratios, T *__restrict__ lattice,
                T *__restrict__ start_vec, T *__restrict__ end_vec,
                const int *__restrict__ bad, int mode)
 {
     constexpr int NP = 32 * NS;
-    __shared__ __align__(16) T ds_all[TEHMM_WARPS_PER_CTA][2][NP];
+    __shared__ __align__(16) T ds_all[WARPS][2][NP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T(*ds)[NP] = ds_all[warp];
     const int N = m.N;
@@ -63,8 +66,8 @@ viterbi_kernel(TehmmModelDev m, TehmmBatchDev b, const T *__restrict__ elog,
     }
     const T a00 = (T)m.cut_trans[0];
 
-    for (int64_t ci = (int64_t)blockIdx.x * TEHMM_WARPS_PER_CTA + warp; ci < b.nchunks;
-         ci += (int64_t)gridDim.x * TEHMM_WARPS_PER_CTA) {
+    for (int64_t ci = (int64_t)blockIdx.x * WARPS + warp; ci < b.nchunks;
+         ci += (int64_t)gridDim.x * WARPS) {
         if (mode == 1 && !bad[ci]) continue;
         const TehmmChunk ch = b.chunks[ci];
         T d[NS];
@@ -394,6 +397,168 @@ viterbi_lean_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ 
             for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(TEHMM_FULL, rs, o);
             if (lane == 0) score_part[ci] = macc + (double)msum + rs;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 DP for 33..64 states (lattice rows of 64 floats, no segment ratios): TWO warps per chunk (round 2).
+//
+// viterbi_kernel<float, 2> gives a lane two whole columns of log A: 128 registers, so one CTA of 8-12 warps per
+// SM whatever the launch bounds, 16 broadcast LDS.128 per step, and (ncu, profiles/r02_notes_wide.md) 46 % issue
+// utilisation with the warps waiting on those loads.  Here warp w of a pair owns the to-states 32w .. 32w+31 and
+// lane l = 4a + h of it the candidates of sixteen from-states (16q + 4h + r) for the four to-states 32w+4a .. 32w+4a+3
+// (64 packed entries of log A = 64 registers, 16 warps per SM): 4 LDS.128 per step, four independent
+// FADD2 / FMNMX3 chains, and two xor-shuffle stages leave lane l with to-state 32w + l.  The halves of the row
+// meet in shared memory once per step (one 64-thread named barrier per pair).  The row is normalised LAZILY: a
+// lane publishes v_t = max_i(v_{t-1,i} + logA_ij) + e_tj - M_{t-1} and its warp's maximum; M_t = max of the two
+// is known to everybody behind the barrier, so the next step subtracts it (max_i(x_i - M + a) = max_i(x_i + a) - M)
+// and the owner stores delta_t = v_t - M_t one step late.  Same chunk protocol as viterbi_kernel (start_vec /
+// end_vec normalised, maximum 0).
+#define VW_PAIRS 8
+#ifndef VW_ENABLED
+#define VW_ENABLED 1
+#endif
+__global__ void __launch_bounds__(VW_PAIRS * 64, 1)
+viterbi_wide_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ elog,
+                    float *__restrict__ lattice, float *__restrict__ start_vec,
+                    float *__restrict__ end_vec, const int *__restrict__ bad, int mode)
+{
+    __shared__ __align__(16) float ds_all[VW_PAIRS][2][72];      // 64 values, the two warps' maxima at [64], [65]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp >> 1, w = warp & 1;
+    const int h = lane & 3, a4 = lane & ~3;
+    const int j = 32 * w + lane;                                   // the to-state this lane ends up with
+    // from-states of lane group h: 16q + 4h + r (q, r < 4) -- the four groups of one LDS.128 read one contiguous 64-byte
+    // span (16 distinct banks); 16h + 4q + r would put groups h and h + 2 on the same banks
+    // A2[k][2q + r/2] = (logA[16q+4h+r][32w+4a+k], logA[16q+4h+r+1][32w+4a+k]), r = 0, 2
+    u64 A2[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int i0 = 16 * (q >> 1) + 4 * h + 2 * (q & 1);
+            A2[k][q] = pk2((float)m.cut_trans[(int64_t)i0 * 64 + 32 * w + a4 + k],
+                           (float)m.cut_trans[(int64_t)(i0 + 1) * 64 + 32 * w + a4 + k]);
+        }
+    const float ls = (float)m.cut_start[j];
+    const bool own = j < m.N;
+    const uint32_t ds_base = (uint32_t)__cvta_generic_to_shared(&ds_all[pair][0][0]);
+    const uint32_t BUF = 72u * 4u;
+    const int bar_id = 1 + pair;
+    const bool h0 = (h & 1) != 0, h1 = (h & 2) != 0;
+
+    for (int64_t ci = (int64_t)blockIdx.x * VW_PAIRS + pair; ci < b.nchunks; ci += (int64_t)gridDim.x * VW_PAIRS) {
+        if (mode == 1 && !bad[ci]) continue;                       // the same decision in both warps of the pair
+        const TehmmChunk ch = b.chunks[ci];
+        int64_t tw = ch.t0;
+        bool from_start = ch.t0 == ch.s0;
+        if (mode == 0 && ch.t0 > ch.s0) {
+            tw = ch.t0 - b.warmup;
+            if (tw <= ch.s0) { tw = ch.s0; from_start = true; }
+        }
+        const float *ep = elog + tw * 64 + j;
+        float *lp = lattice + tw * 64 + j;
+        const int row0 = (int)(ch.t0 - tw), row1 = (int)(ch.t1 - tw);
+        int row = 0, cur = 0;
+        float vv;                                                  // this lane's published value of row - 1
+
+        // publish v (this lane's state) and the warp's maximum in buffer `buf`, meet the other warp
+        auto publish = [&](float v, int buf) {
+            const float mw = __uint_as_float(__reduce_min_sync(TEHMM_FULL, __float_as_uint(v)));   // values <= 0: see viterbi_lean_kernel
+            asm volatile("st.shared.f32 [%0], %1;" :: "r"(ds_base + (uint32_t)buf * BUF + 4u * (uint32_t)j), "f"(v) : "memory");
+            if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" :: "r"(ds_base + (uint32_t)buf * BUF + 256u + 4u * (uint32_t)w), "f"(mw) : "memory");
+            asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
+        };
+        // maximum of the row published in `buf`
+        auto row_max = [&](int buf) -> float {
+            float m0, m1;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(m0), "=f"(m1) : "r"(ds_base + (uint32_t)buf * BUF + 256u) : "memory");
+            return fmaxf(m0, m1);
+        };
+        // one step: row `row` from the row published in `cur`; stores the row before it if it is an output row
+        auto step = [&](float et) {
+            const uint32_t rd = ds_base + (uint32_t)cur * BUF + 16u * (uint32_t)h;
+            u64 x[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[2 * q]), "=l"(x[2 * q + 1]) : "r"(rd + 64u * q) : "memory");
+            const float M = row_max(cur);
+            if (row - 1 >= row0) lp[(int64_t)(row - 1) * 64] = fmaxf(vv - M, -INFINITY);      // all -inf: NaN -> -inf
+            float p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u64 c0 = fadd2(x[0], A2[k][0]);
+                p[k] = fmaxf(lo2(c0), hi2(c0));
+            }
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const u64 c = fadd2(x[q], A2[k][q]);
+                    p[k] = fmax3(p[k], lo2(c), hi2(c));
+                }
+            }
+            // from-state groups meet: xor 2 leaves to-states 2*h1, 2*h1+1 of the four, xor 1 leaves 2*h1 + h0 = h
+            float k0 = h1 ? p[2] : p[0], k1 = h1 ? p[3] : p[1];
+            const float g0 = h1 ? p[0] : p[2], g1 = h1 ? p[1] : p[3];
+            k0 = fmaxf(k0, __shfl_xor_sync(TEHMM_FULL, g0, 2));
+            k1 = fmaxf(k1, __shfl_xor_sync(TEHMM_FULL, g1, 2));
+            const float keep = h0 ? k1 : k0, give = h0 ? k0 : k1;
+            const float pj = fmaxf(keep, __shfl_xor_sync(TEHMM_FULL, give, 1));
+            vv = fmaxf(pj + et - M, -INFINITY);
+            publish(vv, cur ^ 1);
+            cur ^= 1;
+            row += 1;
+        };
+
+        if (mode == 1) {
+            vv = start_vec[ci * 64 + j];
+            publish(vv, cur);
+            row = 0;
+        } else if (from_start) {
+            vv = ls + (own ? *ep : -INFINITY);                     // _hmm.pyx:214-220
+            publish(vv, cur);
+            ep += 64;
+            row = 1;
+        } else {
+            vv = own ? 0.f : -INFINITY;
+            publish(vv, cur);
+            row = 0;
+        }
+        // (a virtual row -1 published by the first and the third branch is never stored: -1 < row0)
+        if (mode == 0 && row0 > 0) {
+            while (row < row0) { step(*ep); ep += 64; }
+            const float M = row_max(cur);
+            start_vec[ci * 64 + j] = fmaxf(vv - M, -INFINITY);
+        }
+        float en[VIT_U];
+        if (row + VIT_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 64];
+        }
+        while (row + 2 * VIT_U <= row1) {
+            float ec[VIT_U];
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) ec[u] = en[u];
+            ep += VIT_U * 64;
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) en[u] = ep[u * 64];
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) step(ec[u]);
+        }
+        if (row + VIT_U <= row1) {
+#pragma unroll
+            for (int u = 0; u < VIT_U; ++u) step(en[u]);
+            ep += VIT_U * 64;
+        }
+        while (row < row1) { step(*ep); ep += 64; }
+        {
+            const float M = row_max(cur);
+            const float dlast = fmaxf(vv - M, -INFINITY);
+            if (row - 1 >= row0) lp[(int64_t)(row - 1) * 64] = dlast;
+            end_vec[ci * 64 + j] = dlast;
+        }
+        // the pair's buffers are reused by its next chunk: nobody may still be reading this one's last row
+        asm volatile("bar.sync %0, 64;" :: "r"(bar_id) : "memory");
     }
 }
 
@@ -789,7 +954,12 @@ static cudaError_t launch_vit(cudaStream_t st, const TehmmModelDev &m, const Teh
 {
     if (ratios)
         viterbi_kernel<T, NS, true><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, lattice, start_vec, end_vec, bad, mode);
-    else
+    else if (sizeof(T) == 4 && NS == 2) {
+        // one CTA per SM either way (the transition matrix alone is 128 registers per lane): twelve warps at <= 168 registers
+        const int64_t need = (b.nchunks + VIT_WIDE_WARPS - 1) / VIT_WIDE_WARPS;
+        const int g = (int)(need < grid ? need : grid);
+        viterbi_kernel<T, NS, false, VIT_WIDE_WARPS><<<g, VIT_WIDE_WARPS * 32, 0, st>>>(m, b, elog, ratios, lattice, start_vec, end_vec, bad, mode);
+    } else
         viterbi_kernel<T, NS, false><<<grid, TEHMM_WARPS_PER_CTA * 32, 0, st>>>(m, b, elog, ratios, lattice, start_vec, end_vec, bad, mode);
     return cudaGetLastError();
 }
@@ -814,6 +984,11 @@ cudaError_t tehmm_launch_viterbi(cudaStream_t st, const TehmmModelDev &m, const 
             return cudaGetLastError();
         }
         if (m.NS == 1) return launch_vit<float, 1>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
+        if (m.LD == 64 && !ratios && VW_ENABLED) {
+            const int64_t need = (b.nchunks + VW_PAIRS - 1) / VW_PAIRS;
+            viterbi_wide_kernel<<<(int)(need < grid ? need : grid), VW_PAIRS * 64, 0, st>>>(m, b, (const float *)elog, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode);
+            return cudaGetLastError();
+        }
         return launch_vit<float, 2>(st, m, b, (const float *)elog, ratios, (float *)lattice, (float *)start_vec, (float *)end_vec, bad, mode, grid);
     }
     if (m.NS == 1) return launch_vit<double, 1>(st, m, b, (const double *)elog, ratios, (double *)lattice, (double *)start_vec, (double *)end_vec, bad, mode, grid);
