@@ -190,6 +190,29 @@ def test_wide_model_50_states(oracle):
     assert_allclose(st["obs"], ob, rtol=TOL["f32"], atol=ATOL["f32"])
 
 
+@pytest.mark.parametrize("N", [33, 64])
+@pytest.mark.parametrize("warmup", [1, 64])
+def test_wide_viterbi_two_warps_per_chunk_ragged(oracle, N, warmup):
+    """33..64 states, float32: viterbi_wide_kernel (two warps per chunk, lazily normalised rows) and the
+    two-chunks-per-warp traceback on a ragged multi-sequence batch incl. T = 1 and T = 2; warmup = 1 forces
+    the repair passes (mode 1 of both kernels).  Paths equal the oracle's except at float32 near-ties."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=N, seed=500 + N)
+    lens = [1, 2, 900, 65, 64, 1700, 131]
+    obs = [synth.sample_obs(m, T, seed=510 + i)[0] for i, T in enumerate(lens)]
+    eng = engine(chunk_tiles=2, warmup=warmup, fine_len=96)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(obs)
+    before = eng.ctx.stat("repair_passes_viterbi") + eng.ctx.stat("repair_passes_traceback")
+    lps, states = eng.viterbi(precision="f32")
+    for i, o in enumerate(obs):
+        ref = oracle_all(oracle, o, m["table"], 1.0, m["log_start"], m["log_trans"])
+        assert_near_ties_only(states[i], ref["vit_states"], ref["frame"], m["log_start"], m["log_trans"])
+        assert lps[i] == pytest.approx(ref["vit_logprob"], rel=1e-6)
+    if warmup == 1:
+        assert eng.ctx.stat("repair_passes_viterbi") + eng.ctx.stat("repair_passes_traceback") > before
+
+
 @pytest.mark.parametrize("N", [33, 50, 64])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
 def test_wide_emission_merged_tables(oracle, N, dtype):
