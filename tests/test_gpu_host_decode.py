@@ -76,6 +76,33 @@ def test_decode_host_equals_device_path_large():
     assert eng.h2d_bytes == (T + 200_003) * 10 and eng.d2h_bytes == T + 200_003 + 32
 
 
+@pytest.mark.parametrize("nseq", [1, 2])
+def test_decode_host_wide_model_equals_device_path(nseq):
+    """50 states (lattice rows of 64 floats): the host-buffer call streams the observations through the wide
+    four-states-per-lane emission kernel in pieces and runs the tcgen05 forward / backward kernels (one sequence)
+    or the generic ones (two), the two-warps-per-chunk Viterbi DP and the two-chunks-per-warp traceback:
+    bit-identical to the torch-plumbed device-pointer path."""
+    from tehmm_b200 import _lib, synth
+    m = synth.make_model(N=50, seed=3)
+    lens = [700_001] if nseq == 1 else [400_000, 300_001]
+    seqs = [synth.sample_obs(m, n, seed=20 + i)[0] for i, n in enumerate(lens)]
+    eng = _engine()
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch(seqs)
+    lp_d, st_d = eng.viterbi()
+    out = eng.posteriors(renorm_eps=True, want_post=False, want_map=True)
+    before = eng.ctx.stat("umma_passes")
+    lp, _, st = eng.decode_host(seqs, _lib.DECODE_VITERBI)
+    flp, sc, ms = eng.decode_host(seqs, _lib.DECODE_MAP)
+    assert eng.ctx.stat("umma_passes") == before + (2 if nseq == 1 else 0)
+    assert_array_equal(lp, lp_d)
+    assert_array_equal(flp, out["logprob"])
+    assert_array_equal(sc, out["map_score"])
+    for i in range(nseq):
+        assert_array_equal(st[i], st_d[i])
+        assert_array_equal(ms[i], out["map_states"][i])
+
+
 def test_device_side_widening_into_the_registered_result(monkeypatch):
     """TEHMM_WIDEN=gpu: the int64 path is written by the DMA engine straight into the (page-locked) result
     array of the Python layer's pool -- no host thread touches it; same states as the host-widening route."""
