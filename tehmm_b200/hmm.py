@@ -353,7 +353,6 @@ class MultitrackHmm(BaseHMM):
         wide = self._wide()
         ratios = None if wide else [self._seg_ratios(o) for o in obs_list]
         if wide or any(r is not None for r in ratios):
-            v = self.decode_batch(obs_list, "viterbi") if self._algorithm not in decoder_algorithms else None
             saved = self._algorithm
             try:
                 self._algorithm = "viterbi"
