@@ -93,9 +93,10 @@ int64_t tehmm_ctx_launch_count(tehmm_ctx *ctx);
 /* options: "chunk_tiles" (tiles of 64 steps per chunk, 0 = auto),
  * "warmup" (speculative warm-up steps, 0 = auto), "max_repair" (passes),
  * "tile" (0 = never use the tensor-core tile kernels), "fine_len" (steps per
- * chunk of the fine partition, 0 = auto), "umma" (1 = forward pass of a
+ * chunk of the fine partition, 0 = auto), "umma" (1 / 2 = forward pass of a
  * single-sequence batch of <= 32 states by the tcgen05 / tensor-memory kernel of
- * csrc/umma.cu; same results, not faster than the mma.sync kernel there),
+ * csrc/umma.cu with one / two threads per chunk; same results, 0.84 / 0.80 ms per
+ * 10 M steps against 0.54 ms for the mma.sync kernel there),
  * "umma64" (default 1: the same kernel, 64 columns, and its backward twin ARE the
  * forward and the backward / posterior / MAP pass of single-sequence batches of
  * 33..64 states; 0 = one chunk per warp; stat "umma_passes" counts the launches

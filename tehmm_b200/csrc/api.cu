@@ -39,7 +39,7 @@ cudaError_t tehmm_launch_forward_tile(cudaStream_t, const TehmmModelDev &, const
 cudaError_t tehmm_launch_backward_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, const int *, int, int, int64_t, int);
 int tehmm_tile_warps(void);
 bool tehmm_forward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int64_t);
-cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, int, int64_t, int *);
+cudaError_t tehmm_launch_forward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const double *, float *, float *, float *, double *, int, int64_t, int *, int);
 bool tehmm_backward_umma_ok(const TehmmModelDev &, const TehmmBatchDev &, int, int, int64_t);
 cudaError_t tehmm_launch_backward_umma(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, int, const float *, const float *, float *, uint8_t *, double *, float *, float *, int, int64_t, int *);
 cudaError_t tehmm_launch_xi_tile(cudaStream_t, const TehmmModelDev &, const TehmmBatchDev &, const float *, const float *, double *, float *, double *, int);
@@ -1146,7 +1146,7 @@ int tehmm_run_forward(tehmm_ctx *c, int prec, const void *d_blin, const double *
     auto launch = [&](int mode) -> cudaError_t {
         if (((tile && c->opt_umma) || wide_umma) && tehmm_forward_umma_ok(c->m, PB, mode, c->fine_len)) {
             cudaError_t eu = tehmm_launch_forward_umma(st, c->m, PB, (const float *)d_blin, d_rowmax, (float *)d_alpha,
-                                                       (float *)sv, (float *)ev, cs, c->sms, c->fine_len, c->d_fault);
+                                                       (float *)sv, (float *)ev, cs, c->sms, c->fine_len, c->d_fault, c->opt_umma == 2 ? 2 : 1);
             if (eu == cudaSuccess) { c->stat_umma_passes += 1; umma_used = true; return eu; }
             if (eu != cudaErrorNotSupported) return eu;
             cudaGetLastError();          // no tensor map: the mma.sync kernel below

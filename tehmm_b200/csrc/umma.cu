@@ -120,6 +120,28 @@ __device__ __forceinline__ void um_tmem_st32(uint32_t taddr, const uint32_t (&v)
                     "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
                  : "memory");
 }
+__device__ __forceinline__ void um_tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void um_tmem_st16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0],"
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr),
+                    "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void um_tmem_ld(uint32_t taddr, uint32_t (&v)[32]) { um_tmem_ld32(taddr, v); }
+__device__ __forceinline__ void um_tmem_ld(uint32_t taddr, uint32_t (&v)[16]) { um_tmem_ld16(taddr, v); }
+__device__ __forceinline__ void um_tmem_st(uint32_t taddr, const uint32_t (&v)[32]) { um_tmem_st32(taddr, v); }
+__device__ __forceinline__ void um_tmem_st(uint32_t taddr, const uint32_t (&v)[16]) { um_tmem_st16(taddr, v); }
 // D[tmem] (+)= A[tmem] * B[smem descriptor]; one thread issues on behalf of the CTA
 __device__ __forceinline__ void um_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -144,8 +166,9 @@ __device__ __forceinline__ uint64_t um_smem_desc(uint32_t addr, uint32_t lbo, ui
 // NH == 2 runs TWO threads per chunk (256 per CTA): warps 0-3 take columns 0-31 of the rows, warps 4-7 columns
 // 32-63 (a warp reaches the 32 tensor-memory lanes of its index modulo 4), which halves the serial epilogue
 // between two tensor-core steps; the halves of a row exchange their maxima through shared memory.
-template <int NH>
-__global__ void __launch_bounds__(UM_ROWS * NH, UM_CTAS)
+// TPR = threads per chunk: 2 for NH == 2; 1 or 2 for NH == 1 (two threads of 16 columns each: round 2, option "umma" = 2).
+template <int NH, int TPR>
+__global__ void __launch_bounds__(UM_ROWS * TPR, UM_CTAS)
 fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin,
                 const double *__restrict__ rowmax, float *__restrict__ alpha,
                 float *__restrict__ start_vec, float *__restrict__ end_vec, double *__restrict__ cscale,
@@ -154,6 +177,7 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
 {
     typedef UmCfg<NH> C;
     constexpr int UMTB = C::TB, NP = C::NP, LDS_ = 32 * NH;       // LDS_: lattice row stride in floats
+    constexpr int CPT = 32 * NH / TPR, CQ = CPT / 4, C2 = CPT / 2; // columns per thread, in 16-byte chunks, in pairs
     constexpr uint32_t UMBOX = C::BOX, UMBLK = C::BLK, BMAT = C::BMAT;
     extern __shared__ unsigned char um_raw[];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(um_raw);
@@ -165,8 +189,11 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
     int *esum_s = reinterpret_cast<int *>(gbase);                 // reused after the main loop (load buffer 0)
     float *mxs = reinterpret_cast<float *>(gbase + (UM_NLD + UM_NST) * UMBLK + 2 * BMAT + 256);   // [parity][half][row]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = tid % UM_ROWS, hh = tid / UM_ROWS;           // this thread's chunk of the tile and its column half
-    constexpr int NTHR = UM_ROWS * NH;
+    const int row = tid % UM_ROWS, hh = tid / UM_ROWS;           // this thread's chunk of the tile and its column part
+    constexpr int NTHR = UM_ROWS * TPR;
+    const int col0 = CPT * hh;                                    // its first column
+    const uint32_t boxoff = (uint32_t)(col0 / 32) * UMBOX;        // the box its columns are in, the 16-byte chunk they start at
+    const uint32_t cq0 = (uint32_t)(col0 % 32) / 4u;
     const int N = m.N, W = b.warmup;
 
     // ---- transition matrix, hi / lo TF32 parts, canonical K-major layout: B[n = j][k = i] = A[i][j]
@@ -234,15 +261,15 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
             for (int j = 0; j < UM_NLD && j < nblk; ++j) issue_load(j);
 
         // ---- initial operand: a flat vector (a row that starts its sequence stays empty until clock W)
-        uint32_t xh[32], xl[32];
+        uint32_t xh[CPT], xl[CPT];
         {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                xh[i] = (valid && !first && 32 * hh + i < N) ? __float_as_uint(1.f) : 0u;
+            for (int i = 0; i < CPT; ++i) {
+                xh[i] = (valid && !first && col0 + i < N) ? __float_as_uint(1.f) : 0u;
                 xl[i] = 0u;
             }
-            um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
-            um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
+            um_tmem_st(t_hi + col0 + my_lane, xh);
+            um_tmem_st(t_lo + col0 + my_lane, xl);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         float scp = 1.f;
@@ -299,28 +326,28 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                 float mx = 0.f;
                 {
                     // b row half of this clock: from the box (16-byte chunks XOR-swizzled) or direct
-                    float bt[32];
+                    float bt[CPT];
                     if (boxed) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
+                        for (int q = 0; q < CQ; ++q)
                             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                          : "=f"(bt[4 * q]), "=f"(bt[4 * q + 1]), "=f"(bt[4 * q + 2]), "=f"(bt[4 * q + 3])
-                                         : "r"(lb + hh * UMBOX + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)) : "memory");
+                                         : "r"(lb + boxoff + line * 128u + (((cq0 + (uint32_t)q) ^ (line & 7u)) << 4)) : "memory");
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 v = on ? *reinterpret_cast<const float4 *>(brow0 + (int64_t)k * LDS_ + 32 * hh + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int q = 0; q < CQ; ++q) {
+                            const float4 v = on ? *reinterpret_cast<const float4 *>(brow0 + (int64_t)k * LDS_ + col0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
                             bt[4 * q] = v.x; bt[4 * q + 1] = v.y; bt[4 * q + 2] = v.z; bt[4 * q + 3] = v.w;
                         }
                     }
-                    uint32_t dv[32];
-                    um_tmem_ld32(t_d + 32 * hh + my_lane, dv);
+                    uint32_t dv[CPT];
+                    um_tmem_ld(t_d + col0 + my_lane, dv);
                     UM_T(3);
                     // x' = D .* b * scale in packed fp32 (FMUL2), maximum as a 3-input tree
-                    u64 a2[16];
+                    u64 a2[C2];
                     float m0 = 0.f, m1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < C2; ++i) {
                         const u64 d2 = ((u64)dv[2 * i + 1] << 32) | (u64)dv[2 * i];
                         a2[i] = um_fmul2(d2, um_fmul2(pk2(bt[2 * i], bt[2 * i + 1]), sc2));
                         if (i & 1) m1 = fmax3(m1, lo2(a2[i]), hi2(a2[i])); else m0 = fmax3(m0, lo2(a2[i]), hi2(a2[i]));
@@ -329,15 +356,15 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                     if (start_here) {                            // alpha_0 = pi .* b_0
                         mh = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float p0 = (float)m.lin_start[32 * hh + 2 * i] * bt[2 * i], p1 = (float)m.lin_start[32 * hh + 2 * i + 1] * bt[2 * i + 1];
+                        for (int i = 0; i < C2; ++i) {
+                            const float p0 = (float)m.lin_start[col0 + 2 * i] * bt[2 * i], p1 = (float)m.lin_start[col0 + 2 * i + 1] * bt[2 * i + 1];
                             a2[i] = pk2(p0, p1);
                             mh = fmax3(mh, p0, p1);
                         }
                     }
                     if (!valid || k < ks) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) a2[i] = 0ull;
+                        for (int i = 0; i < C2; ++i) a2[i] = 0ull;
                         mh = 0.f;
                     }
                     mx = fmaxf(mx, mh);
@@ -345,46 +372,46 @@ fwd_umma_kernel(TehmmModelDev m, TehmmBatchDev b, const float *__restrict__ blin
                         if (alpha) {
                             if (boxed) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q)
+                                for (int q = 0; q < CQ; ++q)
                                     asm volatile("st.shared.v2.u64 [%0], {%1,%2};"
-                                                 :: "r"(sb + hh * UMBOX + line * 128u + (((uint32_t)q ^ (line & 7u)) << 4)), "l"(a2[2 * q]), "l"(a2[2 * q + 1]) : "memory");
+                                                 :: "r"(sb + boxoff + line * 128u + (((cq0 + (uint32_t)q) ^ (line & 7u)) << 4)), "l"(a2[2 * q]), "l"(a2[2 * q + 1]) : "memory");
                             } else if (valid && k < ke) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    *reinterpret_cast<ulonglong2 *>(arow0 + (int64_t)k * LDS_ + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                                for (int q = 0; q < CQ; ++q)
+                                    *reinterpret_cast<ulonglong2 *>(arow0 + (int64_t)k * LDS_ + col0 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                             }
                         }
                     } else if (k == W - 1 && pred) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<ulonglong2 *>(start_vec + c * NP + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                        for (int q = 0; q < CQ; ++q)
+                            *reinterpret_cast<ulonglong2 *>(start_vec + c * NP + col0 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                     }
                     if (valid && k + 1 == ke) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<ulonglong2 *>(end_vec + c * NP + 32 * hh + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
+                        for (int q = 0; q < CQ; ++q)
+                            *reinterpret_cast<ulonglong2 *>(end_vec + c * NP + col0 + 4 * q) = make_ulonglong2(a2[2 * q], a2[2 * q + 1]);
                     }
                     // next operand: hi = the 11 leading bits (a TF32 number), lo = the rest, exactly (FFMA2: a - hi)
                     const u64 neg1 = pk2(-1.f, -1.f);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < C2; ++i) {
                         const u64 h2 = a2[i] & 0xffffe000ffffe000ull;
                         const u64 l2 = ffma2(h2, neg1, a2[i]);
                         xh[2 * i] = (uint32_t)h2; xh[2 * i + 1] = (uint32_t)(h2 >> 32);
                         xl[2 * i] = (uint32_t)l2; xl[2 * i + 1] = (uint32_t)(l2 >> 32);
                     }
                     UM_T(4);
-                    um_tmem_st32(t_hi + 32 * hh + my_lane, xh);
-                    um_tmem_st32(t_lo + 32 * hh + my_lane, xl);
+                    um_tmem_st(t_hi + col0 + my_lane, xh);
+                    um_tmem_st(t_lo + col0 + my_lane, xl);
                 }
-                if (NH == 2) mxs[((k & 1) * 2 + hh) * UM_ROWS + row] = mx;       // the other half of the row reads it behind the barrier
+                if (TPR == 2) mxs[((k & 1) * 2 + hh) * UM_ROWS + row] = mx;       // the other half of the row reads it behind the barrier
                 if (k >= W) esum += k < ke ? sh_now : 0;
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 UM_T(5);
                 if (s == UMTB - 1 || k + 1 >= kmax) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // alpha rows -> TMA store
                 __syncthreads();
-                if (NH == 2) mx = fmaxf(mx, mxs[((k & 1) * 2 + (hh ^ 1)) * UM_ROWS + row]);
+                if (TPR == 2) mx = fmaxf(mx, mxs[((k & 1) * 2 + (hh ^ 1)) * UM_ROWS + row]);
                 {   // exact power-of-two scale for the NEXT step (scale_of in tile.cu)
                     const unsigned mb = __float_as_uint(mx);
                     scp = __uint_as_float(0x7f000000u - (mb & 0x7f800000u));
@@ -469,7 +496,7 @@ bool tehmm_forward_umma_ok(const TehmmModelDev &m, const TehmmBatchDev &b, int m
            b.total / fine_len >= 1;
 }
 
-template <int NH>
+template <int NH, int TPR>
 static cudaError_t launch_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                const float *blin, const double *rowmax, float *alpha,
                                float *start_vec, float *end_vec, double *cscale, int sms,
@@ -482,11 +509,11 @@ static cudaError_t launch_umma(cudaStream_t st, const TehmmModelDev &m, const Te
     const int64_t nfull = b.total / fine_len;
     if (!um_make_tmap(&tb, blin, fine_len, nfull, NH, C::TB) || (alpha && !um_make_tmap(&ta, alpha, fine_len, nfull, NH, C::TB)))
         return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(fwd_umma_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fwd_umma_kernel<NH, TPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) return e;
     const int64_t tiles = (b.nchunks + UM_ROWS - 1) / UM_ROWS;
     const int grid = (int)(tiles < (int64_t)sms * UM_CTAS ? tiles : (int64_t)sms * UM_CTAS);
-    fwd_umma_kernel<NH><<<grid, UM_ROWS * NH, C::SMEM, st>>>(m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, tb, ta,
+    fwd_umma_kernel<NH, TPR><<<grid, UM_ROWS * TPR, C::SMEM, st>>>(m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, tb, ta,
                                                         (int)fine_len, (int)nfull, fault);
     return cudaGetLastError();
 }
@@ -892,8 +919,9 @@ cudaError_t tehmm_launch_backward_umma(cudaStream_t st, const TehmmModelDev &m, 
 cudaError_t tehmm_launch_forward_umma(cudaStream_t st, const TehmmModelDev &m, const TehmmBatchDev &b,
                                       const float *blin, const double *rowmax, float *alpha,
                                       float *start_vec, float *end_vec, double *cscale, int sms,
-                                      int64_t fine_len, int *fault)
+                                      int64_t fine_len, int *fault, int threads_per_chunk)
 {
-    if (m.NS == 1) return launch_umma<1>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
-    return launch_umma<2>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
+    if (m.NS == 1 && threads_per_chunk == 2) return launch_umma<1, 2>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
+    if (m.NS == 1) return launch_umma<1, 1>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
+    return launch_umma<2, 2>(st, m, b, blin, rowmax, alpha, start_vec, end_vec, cscale, sms, fine_len, fault);
 }

@@ -486,8 +486,9 @@ def test_full_size_c2_properties(oracle):
     assert np.mean(out["map_states"][0][:150_000] == ref["map_states"][:150_000]) > 0.9999
 
 
-def test_forward_tcgen05_kernel_matches(oracle):
-    """csrc/umma.cu (context option "umma"): the forward pass of a single-sequence batch on
+@pytest.mark.parametrize("threads_per_chunk", [1, 2])
+def test_forward_tcgen05_kernel_matches(oracle, threads_per_chunk):
+    """csrc/umma.cu (context option "umma" = threads per chunk): the forward pass of a single-sequence batch on
     tcgen05.mma with accumulator and state in tensor memory, b / alpha rows as swizzled 3-D
     tensor-map boxes.  Same log-likelihood, posteriors and MAP path as the oracle and as the
     mma.sync kernel, including a ragged last chunk handled outside the boxes."""
@@ -501,12 +502,12 @@ def test_forward_tcgen05_kernel_matches(oracle):
     eng.upload_batch([obs])
     base = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
     before = eng.ctx.stat("umma_passes")
-    eng.ctx.set_option("umma", 1)
+    eng.ctx.set_option("umma", threads_per_chunk)
     try:
         out = eng.posteriors(renorm_eps=False, want_map=True, precision="f32")
     finally:
         eng.ctx.set_option("umma", 0)
-    assert eng.ctx.stat("umma_passes") == before + 1
+    assert eng.ctx.stat("umma_passes") >= before + 1
     assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
     assert_allclose(out["post"][0], ref["post"], rtol=TOL["f32"], atol=ATOL["f32"])
     assert out["logprob"][0] == pytest.approx(base["logprob"][0], rel=1e-7)
