@@ -107,7 +107,12 @@ struct tehmm_ctx {
     // (fallback.cu; -1 = never: the plain loop, one pass per link of a chain of bad chunks)
     int64_t opt_fallback_after = 2;
     int64_t stat_fallbacks = 0, stat_fallback_chunks = 0, stat_noise_accepted = 0;
-    double mix_rho = 0.0;             // modulus of the second eigenvalue of the transition matrix (set_model)
+    // modulus of the second eigenvalue of the transition matrix: computed on first use (mix_rho_of) from the
+    // row-normalised matrix kept by set_model -- only the exact fallback and the "mix_rho_ppm" statistic ask for it,
+    // and the estimate (2000 power iterations) costs more host time than the rest of set_model, once per EM iteration
+    double mix_rho = -1.0;
+    std::vector<double> mix_A;
+    int mix_N = 0;
     cudaEvent_t ev[TEHMM_NTIMED][TEHMM_TRING][2] = {};
     int ev_n[TEHMM_NTIMED] = {};          // launches recorded since "timing" was last set (ring of TEHMM_TRING)
     int64_t stat_repair_fwd = 0, stat_repair_bwd = 0, stat_repair_vit = 0;
@@ -235,6 +240,45 @@ int tehmm_ctx_set_option(tehmm_ctx *c, const char *name, int64_t v)
     return TEHMM_OK;
 }
 
+// How fast the chain forgets with NO help from the data (all-missing stretches): rho = |lambda_2(A)|,
+// estimated as ||B^256||_F^(1/256), B = A - 1 pi^T (pi = stationary distribution by power iteration).
+// Rounding noise of a filter is amplified by 1 / (1 - rho); see tolerance_after_fallback.
+static double mix_rho_of(tehmm_ctx *c)
+{
+    if (c->mix_rho >= 0.0) return c->mix_rho;
+    const int N = c->mix_N;
+    if (N <= 0 || c->mix_A.size() != (size_t)N * N) return 0.0;
+    const std::vector<double> &A = c->mix_A;
+    std::vector<double> pi(N, 1.0 / N), tmp(N), B((size_t)N * N), B2((size_t)N * N);
+    for (int it = 0; it < 2000; ++it) {
+        double sum = 0.0;
+        for (int j = 0; j < N; ++j) tmp[j] = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double p = pi[i];
+            for (int j = 0; j < N; ++j) tmp[j] += p * A[(size_t)i * N + j];
+        }
+        for (int j = 0; j < N; ++j) sum += tmp[j];
+        for (int j = 0; j < N; ++j) pi[j] = sum > 0.0 ? tmp[j] / sum : 1.0 / N;
+    }
+    for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) B[(size_t)i * N + j] = A[(size_t)i * N + j] - pi[j];
+    double lognorm = 0.0;                 // log ||B^(2^k)||_F accumulated with renormalisation
+    for (int sq = 0; sq < 8; ++sq) {
+        double f = 0.0;
+        for (double v : B) f += v * v;
+        f = sqrt(f);
+        if (!(f > 0.0)) { lognorm = -INFINITY; break; }
+        for (double &v : B) v /= f;
+        lognorm = 2.0 * (lognorm + log(f));
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) { double a = 0.0; for (int k = 0; k < N; ++k) a += B[(size_t)i * N + k] * B[(size_t)k * N + j]; B2[(size_t)i * N + j] = a; }
+        B.swap(B2);
+    }
+    if (lognorm > -INFINITY) { double f = 0.0; for (double v : B) f += v * v; lognorm += f > 0.0 ? 0.5 * log(f) : -INFINITY; }
+    const double rho = lognorm > -INFINITY ? exp(lognorm / 256.0) : 0.0;
+    c->mix_rho = std::min(1.0, std::max(0.0, rho));
+    return c->mix_rho;
+}
+
 int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
 {
     if (!c || !name) return -1;
@@ -257,7 +301,7 @@ int64_t tehmm_ctx_get_stat(tehmm_ctx *c, const char *name)
     if (!strcmp(name, "fallbacks")) return c->stat_fallbacks;
     if (!strcmp(name, "fallback_chunks")) return c->stat_fallback_chunks;
     if (!strcmp(name, "noise_accepted")) return c->stat_noise_accepted;
-    if (!strcmp(name, "mix_rho_ppm")) return (int64_t)(c->mix_rho * 1e6);
+    if (!strcmp(name, "mix_rho_ppm")) return (int64_t)(mix_rho_of(c) * 1e6);
     for (int i = 0; i < TEHMM_NTIMED; ++i)
         if (!strcmp(name, tk_names[i])) {
             // average over the launches recorded since "timing" was set (at most the last TEHMM_TRING)
@@ -596,36 +640,15 @@ int tehmm_set_model(tehmm_ctx *c, int N, int K, int S, const double *log_start,
             cutt[(size_t)i * NP + j] = okt ? log_trans[(size_t)i * N + j] : NEG;
         }
     }
-    {   // How fast the chain forgets with NO help from the data (all-missing stretches): rho = |lambda_2(A)|,
-        // estimated as ||B^256||_F^(1/256), B = A - 1 pi^T (pi = stationary distribution by power iteration).
-        // Rounding noise of a filter is amplified by 1 / (1 - rho); see tolerance_after_fallback.
-        std::vector<double> A((size_t)N * N), pi(N, 1.0 / N), tmp(N), B((size_t)N * N), B2((size_t)N * N);
+    {   // the row-normalised transition matrix, for mix_rho_of
+        c->mix_A.assign((size_t)N * N, 0.0);
+        c->mix_N = N;
+        c->mix_rho = -1.0;
         for (int i = 0; i < N; ++i) {
             double rs = 0.0;
-            for (int j = 0; j < N; ++j) { A[(size_t)i * N + j] = lint[(size_t)i * NP + j]; rs += A[(size_t)i * N + j]; }
-            for (int j = 0; j < N; ++j) A[(size_t)i * N + j] = rs > 0.0 ? A[(size_t)i * N + j] / rs : (i == j ? 1.0 : 0.0);
+            for (int j = 0; j < N; ++j) rs += lint[(size_t)i * NP + j];
+            for (int j = 0; j < N; ++j) c->mix_A[(size_t)i * N + j] = rs > 0.0 ? lint[(size_t)i * NP + j] / rs : (i == j ? 1.0 : 0.0);
         }
-        for (int it = 0; it < 2000; ++it) {
-            double sum = 0.0;
-            for (int j = 0; j < N; ++j) { double a = 0.0; for (int i = 0; i < N; ++i) a += pi[i] * A[(size_t)i * N + j]; tmp[j] = a; sum += a; }
-            for (int j = 0; j < N; ++j) pi[j] = sum > 0.0 ? tmp[j] / sum : 1.0 / N;
-        }
-        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) B[(size_t)i * N + j] = A[(size_t)i * N + j] - pi[j];
-        double lognorm = 0.0;                 // log ||B^(2^k)||_F accumulated with renormalisation
-        for (int sq = 0; sq < 8; ++sq) {
-            double f = 0.0;
-            for (double v : B) f += v * v;
-            f = sqrt(f);
-            if (!(f > 0.0)) { lognorm = -INFINITY; break; }
-            for (double &v : B) v /= f;
-            lognorm = 2.0 * (lognorm + log(f));
-            for (int i = 0; i < N; ++i)
-                for (int j = 0; j < N; ++j) { double a = 0.0; for (int k = 0; k < N; ++k) a += B[(size_t)i * N + k] * B[(size_t)k * N + j]; B2[(size_t)i * N + j] = a; }
-            B.swap(B2);
-        }
-        if (lognorm > -INFINITY) { double f = 0.0; for (double v : B) f += v * v; lognorm += f > 0.0 ? 0.5 * log(f) : -INFINITY; }
-        double rho = lognorm > -INFINITY ? exp(lognorm / 256.0) : 0.0;
-        c->mix_rho = std::min(1.0, std::max(0.0, rho));
     }
     CU(cudaStreamSynchronize(c->stream));
     if (total > c->model_blob_bytes) {
@@ -1112,7 +1135,7 @@ static double tolerance_after_fallback(const tehmm_ctx *c, int prec, bool log_sp
     const double base = 100.0 * tolerance(prec, log_space);
     if (log_space) return base;
     const double eps = prec == TEHMM_F32 ? 4.8e-7 : 2.3e-16;
-    const double floor_ = 8.0 * eps / std::max(1e-9, 1.0 - c->mix_rho);
+    const double floor_ = 8.0 * eps / std::max(1e-9, 1.0 - mix_rho_of(const_cast<tehmm_ctx *>(c)));
     return std::min(0.1, std::max(base, floor_));
 }
 #define TEHMM_MAX_FALLBACK_ROUNDS 10    // reach 8 * 4^round chunks: far beyond any partition; then the plain loop
