@@ -309,7 +309,7 @@ def run_split(world, rank):
     m0 = synth.make_model(N=N_STATES, seed=7, zero_frac=0.0)
     hmm, _ = make_hmm(m0, n_iter=2, thresh=0.0)
     hmm.fit(seqs)                       # warm-up (allocator, kernels, NCCL)
-    n_iter = 10
+    n_iter = 50                         # BASELINE.json configs[2]: 50 EM iterations (the one-time upload of the shard is part of the fit)
     hmm, _ = make_hmm(m0, n_iter=n_iter, thresh=0.0)
     barrier(); t0 = time.perf_counter()
     hmm.fit(seqs)
