@@ -30,3 +30,6 @@ pr.enable(); h.fit(seqs); torch.cuda.synchronize(); pr.disable()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
 print(s.getvalue()[:6000])
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+print(s.getvalue()[:7000])
