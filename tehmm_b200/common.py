@@ -43,3 +43,16 @@ def normalize(A, axis=None):
         shape[axis] = 1
         Asum.shape = shape
     return A / Asum
+
+
+def assert_almost_equal_fast(actual, desired, decimal=6):
+    """numpy.testing.assert_array_almost_equal's criterion (abs(desired - actual) < 1.5 * 10**-decimal, NaNs must
+    match) without its message machinery: validate() runs twice per EM iteration (hmm.py:576-616), and the numpy
+    helper costs 80 us a call.  Falls back to the numpy helper for the error message."""
+    a, d = np.asarray(actual, dtype=np.float64), np.asarray(desired, dtype=np.float64)
+    if a.shape == d.shape or a.ndim == 0 or d.ndim == 0:
+        diff = np.abs(d - a)
+        if bool(np.all(diff < 1.5 * 10.0 ** (-decimal))):
+            return
+    from numpy.testing import assert_array_almost_equal
+    assert_array_almost_equal(actual, desired, decimal)

@@ -13,7 +13,7 @@ import numpy as np
 from numpy.testing import assert_array_almost_equal
 
 from ._emission import canFast, fastAccumulateStats, fastAllLogProbs, fastUpdateCounts
-from .common import EPSILON, NEGINF, logger, myLog, normalize
+from .common import EPSILON, NEGINF, assert_almost_equal_fast, logger, myLog, normalize
 from .track import is_track_table
 
 
@@ -187,7 +187,7 @@ class IndependentMultinomialEmissionModel(object):
                 total *= np.exp(self.logProbs[track, :, off:self.numSymbolsPerTrack[track] + off]).sum(axis=1)
             else:
                 total *= np.exp(self.logProbs[track, :, 0])
-        assert_array_almost_equal(total, np.ones(self.numStates))
+        assert_almost_equal_fast(total, np.ones(self.numStates))
 
     def sample(self, state):
         return None

@@ -19,7 +19,7 @@ from numpy.testing import assert_array_almost_equal
 
 from . import _hmm as _strict_hmm
 from . import _lib, parallel
-from .common import EPSILON, logger, logsumexp, myLog, normalize
+from .common import EPSILON, assert_almost_equal_fast, logger, logsumexp, myLog, normalize
 from .engine import as_obs_array, get_engine
 
 decoder_algorithms = ("viterbi", "map")
@@ -149,8 +149,8 @@ class MultitrackHmm(BaseHMM):
         assert len(self.startprob_) == N
         assert not isinstance(self.startprob_[0], Iterable)
         assert self.transmat_.shape == (N, N)
-        assert_array_almost_equal(np.sum(self.startprob_), 1.)
-        assert_array_almost_equal(np.sum(self.transmat_, axis=1), np.ones(N))
+        assert_almost_equal_fast(np.sum(self.startprob_), 1.)
+        assert_almost_equal_fast(np.sum(self.transmat_, axis=1), np.ones(N))
         self.emissionModel.validate()
 
     # ------------------------------------------------------------ device plumbing
