@@ -556,3 +556,29 @@ def test_tcgen05_kernels_are_the_default_for_33_to_64_states(oracle, N, T):
     eng.upload_batch([obs[:20_000], obs[20_000:]])
     eng.posteriors(renorm_eps=False, want_post=False, want_map=True, precision="f32")
     assert eng.ctx.stat("umma_passes") == before + 6
+
+
+def test_tcgen05_kernels_several_tiles_per_cta():
+    """More tiles of 128 chunks than SMs (1.3 M steps in chunks of 64: 159 tiles): a CTA of fwd_umma_kernel<2> /
+    bwd_umma_kernel<2> walks a second tile with the same barriers, tensor-memory columns and shared-memory rings.
+    Against the one-chunk-per-warp kernels on the same partition."""
+    from tehmm_b200 import synth
+    m = synth.make_model(N=50, seed=43)
+    T = 1_300_000
+    obs, _ = synth.sample_obs(m, T, seed=44)
+    eng = engine(fine_len=64)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    before = eng.ctx.stat("umma_passes")
+    out = eng.posteriors(renorm_eps=False, want_post=True, want_map=True, precision="f32")
+    assert eng.ctx.stat("umma_passes") == before + 2
+    eng.ctx.set_option("umma64", 0)
+    try:
+        base = eng.posteriors(renorm_eps=False, want_post=True, want_map=True, precision="f32")
+    finally:
+        eng.ctx.set_option("umma64", 1)
+    assert out["logprob"][0] == pytest.approx(base["logprob"][0], rel=1e-7)
+    assert np.mean(out["map_states"][0] == base["map_states"][0]) > 0.99999
+    assert_allclose(out["map_score"], base["map_score"], rtol=1e-6)
+    # float32 against float32: a few ulp of the posterior's own magnitude
+    assert_allclose(out["post"][0], base["post"][0], rtol=2e-4, atol=1e-6)
