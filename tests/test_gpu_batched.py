@@ -132,10 +132,12 @@ def test_estep_matches_oracle(oracle, prec):
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_segment_ratios(oracle, prec):
-    """ratios in the emission and in the DP, including the Viterbi from-state-0 quirk."""
+@pytest.mark.parametrize("N", [12, 40])
+def test_segment_ratios(oracle, prec, N):
+    """ratios in the emission and in the DP, including the Viterbi from-state-0 quirk; N = 40: the
+    two-states-per-lane kernels and the two-chunks-per-warp traceback with the quirk's correction."""
     from tehmm_b200 import synth
-    m = synth.make_model(N=12, syms=(4, 8, 2), seed=61, zero_frac=0.0)
+    m = synth.make_model(N=N, syms=(4, 8, 2), seed=61, zero_frac=0.0)
     T = 900
     obs = synth.sample_obs(m, T, seed=62)[0]
     r = np.random.RandomState(63).uniform(0.05, 6.0, size=T)
