@@ -12,6 +12,8 @@ m = synth.make_model(N=30, seed=0)
 m0 = synth.make_model(N=30, seed=99)
 lens = synth.bench_lengths("c3")
 seqs = [synth.sample_obs(m, n, seed=400 + i)[0] for i, n in enumerate(lens)]
+if len(sys.argv) > 1:            # every k-th sequence only: the shard of one rank of k
+    seqs = seqs[::int(sys.argv[1])]
 
 def make(n_iter):
     em = IndependentMultinomialEmissionModel(30, list(m0["syms"]), zeroAsMissingData=True)
@@ -19,12 +21,12 @@ def make(n_iter):
     return MultitrackHmm(em, startprob=m0["pi"].copy(), transmat=m0["A"].copy(), n_iter=n_iter, thresh=0.0)
 
 make(2).fit(seqs)
-h = make(10)
+h = make(50)
 torch.cuda.synchronize(); t0 = time.perf_counter()
 h.fit(seqs)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print("seconds per iteration: %.5f" % (dt / 10))
-h = make(10)
+print("seconds per iteration: %.5f" % (dt / 50))
+h = make(50)
 pr = cProfile.Profile()
 pr.enable(); h.fit(seqs); torch.cuda.synchronize(); pr.disable()
 s = io.StringIO()
