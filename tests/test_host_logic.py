@@ -163,3 +163,26 @@ def test_host_thread_pool_back_to_back_jobs():
     lib = _lib.load()
     for threads in (2, 4, 16):
         assert lib.tehmm_host_pool_selftest(threads, 200_000) == 0
+
+
+def test_fast_almost_equal_keeps_numpys_criterion():
+    """validate() (hmm.py:576-616 calls it twice per EM iteration) uses a cheap restatement of
+    numpy.testing.assert_array_almost_equal: same verdicts, same AssertionError."""
+    import numpy as np
+    import pytest
+    from numpy.testing import assert_array_almost_equal
+    from tehmm_b200.common import assert_almost_equal_fast
+    ones = np.ones(30)
+    cases = [(ones + 1e-7, ones), (ones + 1.4e-6, ones), (ones + 1.6e-6, ones), (0.9, 1.0), (np.float64(1.0), 1.0),
+             (np.array([np.nan]), np.array([1.0])), (np.ones(3), np.ones(4)), (np.array([np.inf]), np.array([np.inf]))]
+    for got, want in cases:
+        try:
+            assert_array_almost_equal(got, want)
+            ok = True
+        except AssertionError:
+            ok = False
+        if ok:
+            assert_almost_equal_fast(got, want)
+        else:
+            with pytest.raises(AssertionError):
+                assert_almost_equal_fast(got, want)
