@@ -31,6 +31,9 @@ for case in range(ncases):
     for k, v in opts.items():
         eng.ctx.set_option(k, v)
     prec = str(rng.choice(["f32", "f32", "f64"]))
+    only = os.environ.get("FUZZ_ONLY")          # replay ONE case of a seed (the draws above keep the generator in step)
+    if only is not None and int(only) != case:
+        continue
     tol = 1e-5 if prec == "f32" else 1e-10
     # absolute floor of a log-likelihood: a model that explains every observation with probability 1 (one symbol per
     # track) has log P = 0, and float32 carries ~3e-10 per step of rounding in the transition rows
@@ -62,10 +65,21 @@ for case in range(ncases):
         if abs(es["logprob"] - lp_sum) > tol * abs(lp_sum) + floor:
             msg.append("estep logprob %r vs %r" % (es["logprob"], lp_sum))
         for name, got, want in (("start", es["start"], s0), ("trans", es["trans"], tr), ("obs", es["obs"], ob)):
-            # float64: the oracle's LOG-space lattices carry ulp(|log alpha|) ~ 6e-11 at |log alpha| = 3e5
-            # (T = 2e4), so raw counts of long sequences agree to ~1e-8 relative, not 1e-10
-            if not np.allclose(got, want, rtol=10 * tol if prec == "f32" else 1e-7, atol=2e-5 if prec == "f32" else 1e-9):
+            # float64: the oracle's (= the reference's) LOG-space lattices and normaliser carry absolute rounding that
+            # grows with |log alpha|: at T = 2e4 its raw counts are off by a uniform 1.1e-7 relative against an
+            # extended-precision evaluation while ours agree with it to 1e-15 (seed 13 case 56, replayed with
+            # FUZZ_ONLY=56: profiles/r02_fuzz.txt) -- so 1e-6 against the oracle here, 1e-10 on the short golden vectors
+            if not np.allclose(got, want, rtol=10 * tol if prec == "f32" else 1e-6, atol=2e-5 if prec == "f32" else 1e-9):
                 msg.append("estep %s max abs err %.3g" % (name, float(np.abs(got - want).max())))
+                if only is not None and name == "trans":
+                    # who is right: an extended-precision (64-bit mantissa) evaluation in scaled space
+                    sys.path.insert(0, os.path.join(ROOT, "tests"))
+                    from parity import oracle_frame, trans_counts_extended
+                    truth = trans_counts_extended([oracle_frame(orc, o, m["table"]) for o in seqs], m["log_start"], m["log_trans"])
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        print("trans counts (extended-precision arbiter):\n", truth)
+                        print("ours   - arbiter, relative:\n", (got - truth) / truth)
+                        print("oracle - arbiter, relative:\n", (want - truth) / truth)
     except Exception as e:                      # noqa: BLE001
         msg.append("EXCEPTION %r" % (e,))
     bad += bool(msg)
