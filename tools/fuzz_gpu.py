@@ -58,9 +58,10 @@ for case in range(ncases):
             if abs(flp[i] - ref["logprob"]) > tol * abs(ref["logprob"]) + floor:
                 msg.append("logprob seq %d: %r vs %r" % (i, flp[i], ref["logprob"]))
             agree = float(np.mean(st[i] == ref["vit_states"]))
-            if (prec == "f64" and agree < 1.0) or agree < 0.97:
+            slack = max(1.0, 0.03 * len(o)) / len(o)     # float32 near-ties: 3 % of the steps, at least one step
+            if (prec == "f64" and agree < 1.0) or agree < 1.0 - slack:
                 msg.append("viterbi path seq %d agreement %.4f" % (i, agree))
-            if float(np.mean(ms[i] == ref["map_states"])) < 0.97:
+            if float(np.mean(ms[i] == ref["map_states"])) < 1.0 - slack:
                 msg.append("map path seq %d agreement %.4f" % (i, float(np.mean(ms[i] == ref["map_states"]))))
         if abs(es["logprob"] - lp_sum) > tol * abs(lp_sum) + floor:
             msg.append("estep logprob %r vs %r" % (es["logprob"], lp_sum))
