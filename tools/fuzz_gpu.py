@@ -58,7 +58,8 @@ for case in range(ncases):
             if abs(flp[i] - ref["logprob"]) > tol * abs(ref["logprob"]) + floor:
                 msg.append("logprob seq %d: %r vs %r" % (i, flp[i], ref["logprob"]))
             agree = float(np.mean(st[i] == ref["vit_states"]))
-            slack = max(1.0, 0.03 * len(o)) / len(o)     # float32 near-ties: 3 % of the steps, at least one step
+            # float32 near-ties: 3 % of the steps -- at least one step from 8 steps on, none on shorter sequences
+            slack = max(1.0, 0.03 * len(o)) / len(o) if len(o) >= 8 else 0.0
             if (prec == "f64" and agree < 1.0) or agree < 1.0 - slack:
                 msg.append("viterbi path seq %d agreement %.4f" % (i, agree))
             if float(np.mean(ms[i] == ref["map_states"])) < 1.0 - slack:
