@@ -91,3 +91,37 @@ def test_plain_loop_agrees(oracle):
     assert_array_equal(res[2][2][0], res[-1][2][0])
     assert_allclose(res[2][0]["post"][0], res[-1][0]["post"][0], rtol=1e-8, atol=1e-13)
     assert res[2][0]["logprob"][0] == pytest.approx(res[-1][0]["logprob"][0], rel=1e-12)
+
+
+def test_gaps_on_a_50_state_model(oracle):
+    """The same input class on the 33..64-state kernels (tcgen05 forward / backward, two-warps-per-chunk Viterbi DP,
+    two-chunks-per-warp traceback): all-missing stretches longer than any warm-up, so the first passes of those
+    kernels hand flagged chunks to the repair kernels and to the exact resolution (transfer operators of 64 x 64)."""
+    from tehmm_b200 import synth
+    from tehmm_b200.engine import get_engine
+    m = synth.make_model(N=50, seed=2, sticky=0.9)
+    T = 120_000
+    obs, _ = synth.sample_obs(m, T, seed=4)
+    obs, spans = synth.add_missing_stretches(obs, n_stretches=3, lo=2_000, hi=9_000, seed=7)
+    eng = get_engine(0)
+    for k in ("chunk_tiles", "warmup", "fine_len"):
+        eng.ctx.set_option(k, 0)
+    eng.ctx.set_option("tile", 1)
+    eng.ctx.set_option("fallback_after", 2)
+    eng.upload_model(m["log_start"], m["log_trans"], m["table"], 1.0, m["widths"])
+    eng.upload_batch([obs])
+    before = eng.ctx.stat("umma_passes")
+    out, lps, states, d = _run(eng, "f32")
+    print("50 states: passes %s" % (d,))
+    # (the forward pass runs on tcgen05; its flagged chunks raise the warm-up beyond this batch's 64-step fine chunks,
+    #  so the backward pass of THIS batch takes the one-chunk-per-warp kernel: tehmm_backward_umma_ok)
+    assert eng.ctx.stat("umma_passes") >= before + 1
+    for k in PASS_STATS[:3]:
+        assert d[k] <= 6, (k, d)
+    assert d["repair_passes_traceback"] <= 10, d
+    ref = oracle_all(oracle, obs, m["table"], 1.0, m["log_start"], m["log_trans"])
+    assert out["logprob"][0] == pytest.approx(ref["logprob"], rel=TOL["f32"])
+    assert_allclose(out["post"][0], ref["post"], rtol=5e-4, atol=1e-5)
+    assert_map_near_ties_only(out["map_states"][0], ref["post"], rel=5e-4, label="gaps, 50 states")
+    assert_near_ties_only(states[0], ref["vit_states"], ref["frame"], m["log_start"], m["log_trans"], None, label="gaps, 50 states")
+    assert lps[0] == pytest.approx(ref["vit_logprob"], rel=1e-6)
